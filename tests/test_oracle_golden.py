@@ -1,0 +1,110 @@
+"""CPU suite: the oracle restatement against the fixtures minted from the
+unmodified reference (oracle/make_golden.py).  This is what pins the oracle."""
+import numpy as np
+import pytest
+
+from oracle import cases, hrnet_oracle, scoring_oracle
+
+
+def test_param_inventory_matches_reference():
+    shapes = hrnet_oracle.param_shapes()
+    assert len(shapes) == 31
+    assert sum(int(np.prod(s)) for s in shapes.values()) == 591818   # paper txt:824
+
+
+@pytest.mark.parametrize("name", [n for n in cases.HRNET_CASES if n != "c1_b2_l4_s128"])
+def test_hrnet_oracle_matches_reference_golden(golden, name):
+    params = hrnet_oracle.make_params(cases.WEIGHT_SEED)
+    lrs, alphas = cases.hrnet_inputs(name)
+    sr = hrnet_oracle.hrnet_forward(params, lrs, alphas).numpy()
+    ref = golden["hrnet_forward"][name]
+    assert sr.shape == ref.shape
+    # same ATen ops; thread-count dependent summation only (1.1e-7)
+    assert np.abs(sr - ref).max() <= 2e-6
+
+
+def test_hrnet_oracle_c1_config(golden):
+    """BASELINE.json configs[0]: B2 L4 128x128 fp32 on CPU."""
+    params = hrnet_oracle.make_params(cases.WEIGHT_SEED)
+    lrs, alphas = cases.hrnet_inputs("c1_b2_l4_s128")
+    sr = hrnet_oracle.hrnet_forward(params, lrs, alphas).numpy()
+    assert sr.shape == (2, 1, 384, 384)
+    assert np.abs(sr - golden["hrnet_forward"]["c1_b2_l4_s128"]).max() <= 2e-6
+
+
+def test_hrnet_oracle_fp64_arbiter(golden):
+    params = hrnet_oracle.make_params(cases.WEIGHT_SEED)
+    lrs, alphas = cases.hrnet_inputs("b2_l4_s32")
+    import torch
+    sr64 = hrnet_oracle.hrnet_forward(params, lrs, alphas, dtype=torch.float64).numpy()
+    assert np.abs(sr64 - golden["hrnet_forward"]["b2_l4_s32__f64"]).max() <= 1e-12
+
+
+def test_odd_view_is_dropped():
+    """HRNet.py:115 - with odd L the last view never reaches the output."""
+    params = hrnet_oracle.make_params(cases.WEIGHT_SEED)
+    lrs, alphas = cases.hrnet_inputs("b1_l5_s24")
+    a = hrnet_oracle.hrnet_forward(params, lrs, alphas).numpy()
+    lrs2 = lrs.copy()
+    # keep the median unchanged: view 4 only enters through the anchor, so perturb
+    # it towards a value that leaves the lower median (index 2 of 5) in place
+    enc = {}
+    hrnet_oracle.hrnet_forward(params, lrs, alphas, trace=enc)
+    fused_a = enc["fused"].numpy()
+    feats = enc["encoded"].clone()
+    feats[:, 4] += 1.0
+    import torch
+    fused_b = hrnet_oracle.fuse(params, feats, torch.from_numpy(alphas)).numpy()
+    assert np.array_equal(fused_a, fused_b)
+    assert a.shape == (1, 1, 72, 72) and lrs2.shape == lrs.shape
+
+
+def test_alpha_zero_is_skip_connection():
+    """alphas [1,1,0,0] -> result == h0 + fuse(cat(h0,h1))."""
+    import torch
+    params = hrnet_oracle.make_params(cases.WEIGHT_SEED)
+    rng = np.random.RandomState(5)
+    x = torch.from_numpy(rng.randn(1, 4, 64, 8, 8).astype(np.float32))
+    al = torch.tensor([[1.0, 1.0, 0.0, 0.0]])
+    lvl1, al1 = hrnet_oracle.fuse_level(params, x, al)
+    assert torch.equal(lvl1, x[:, :2])          # both bobs are padded views
+    out = hrnet_oracle.fuse(params, x, al)
+    direct, _ = hrnet_oracle.fuse_level(params, x[:, :2], torch.ones(1, 2))
+    assert torch.allclose(out, direct[:, 0], atol=1e-6)
+
+
+@pytest.mark.parametrize("name", list(cases.LANCZOS_CASES))
+def test_lanczos_oracle_matches_reference_golden(golden, name):
+    img, shift, p = cases.lanczos_inputs(name)
+    out = scoring_oracle.lanczos_shift(img, shift, p=p)
+    assert np.abs(out - golden["lanczos"][name]).max() <= 2e-6
+
+
+def test_lanczos_taps_known_answers(golden):
+    taps = scoring_oracle.lanczos_taps(np.array(cases.LANCZOS_TAP_SHIFTS, dtype=np.float32))
+    assert np.abs(taps - golden["lanczos"]["taps"]).max() <= 3e-7
+    assert np.allclose(taps.sum(1), 1.0, atol=1e-6)                      # lanczos.py:41
+    # SURVEY.md section 9 KAT: lanczos_kernel(0.3)
+    kat = np.array([0.0070, 0.0310, -0.1419, 0.8417, 0.3348, -0.0830, 0.0104], dtype=np.float32)
+    assert np.abs(taps[1] - kat).max() < 6e-5
+    assert np.argmax(taps[0]) == 3 and np.argmax(taps[2]) == 4           # d=0 -> tap 3, d=1 -> tap 4
+
+
+@pytest.mark.parametrize("name", list(cases.CPSNR_CASES))
+def test_cpsnr_oracle_matches_reference_golden(golden, name):
+    sr, hr, hm = cases.cpsnr_inputs(name)
+    g = golden["cpsnr"]
+    for i in range(sr.shape[0]):
+        mx, am, sites = scoring_oracle.shift_cpsnr(sr[i], hr[i], hm[i])
+        assert np.array_equal(np.float32(mx), g[name + "__max"][i], equal_nan=True)   # bit-exact, same numpy ops
+        assert int(am) == int(g[name + "__argmax"][i])
+        assert np.array_equal(sites.astype(np.float32), g[name + "__sites"][i], equal_nan=True)
+
+
+def test_cpsnr_known_shift_convention():
+    """sr = roll(hr, (+1, -2)) -> best site 19 = (x=2, y=5)."""
+    rng = np.random.RandomState(11)
+    hr = rng.rand(64, 64).astype(np.float32)
+    sr = np.roll(hr, (1, -2), axis=(0, 1))
+    mx, am, _ = scoring_oracle.shift_cpsnr(sr, hr, np.ones_like(hr))
+    assert int(am) == 19 and np.isinf(mx)
