@@ -1,0 +1,516 @@
+// C ABI of libhrn_b200.so (declared in include/hrn_b200.h): handle, weight
+// repacking, workspace and the layer schedule of HRNet.forward (HRNet.py:186-211).
+#include "../../include/hrn_b200.h"
+#include "internal.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <set>
+#include <string>
+#include <vector>
+
+namespace hrn {
+
+static thread_local char g_error[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+void note_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+struct ConvLayer {
+    int cin = 0, cout = 0;
+    uint8_t* w_img = nullptr;   // device, pre-swizzled bf16
+    float* bias = nullptr;      // device
+    float prelu = 0.0f;
+    bool has_prelu = false;
+};
+
+}  // namespace hrn
+
+struct hrn_handle {
+    hrn_config cfg;
+    int device = 0, sm_count = 0;
+    std::set<std::string> have;
+    int expected = 0;
+    // first conv (2 -> 64) and decoder parameters (fp32, device)
+    float *w_init = nullptr, *b_init = nullptr;
+    float prelu_init = 0.0f;
+    std::vector<hrn::ConvLayer> enc;   // 2 * num_layers residual convs + the final conv
+    hrn::ConvLayer fuse[3];
+    float *wd = nullptr, *bd = nullptr, *wf = nullptr;
+    float prelu_dec = 0.0f, bf = 0.0f;
+    // workspace
+    size_t act_cap = 0;                // bytes of each activation buffer
+    __nv_bfloat16* act[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t anchor_cap = 0;
+    float* anchor = nullptr;
+    size_t io_cap[3] = {0, 0, 0};
+    float* io[3] = {nullptr, nullptr, nullptr};   // device staging for hrn_forward_host: lrs, alphas, sr
+    int bo_mode = 0;
+    int strip_h = 0;                   // 0 = automatic
+};
+
+namespace {
+
+using hrn::set_error;
+
+int grow(void** p, size_t* cap, size_t need) {
+    if (need <= *cap) return 0;
+    if (*p != nullptr) HRN_CUDA_OK(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    HRN_CUDA_OK(cudaMalloc(p, need));
+    *cap = need;
+    return 0;
+}
+
+int upload(float** dst, const float* src, size_t n) {
+    if (*dst == nullptr) HRN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(dst), n * sizeof(float)));
+    HRN_CUDA_OK(cudaMemcpy(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+bool shape_is(const int64_t* shape, int ndim, std::initializer_list<int64_t> want) {
+    if (ndim != static_cast<int>(want.size())) return false;
+    int i = 0;
+    for (int64_t w : want)
+        if (shape[i++] != w) return false;
+    return true;
+}
+
+int set_conv_weight(hrn::ConvLayer& l, const float* data, const int64_t* shape, int ndim) {
+    if (!shape_is(shape, ndim, {l.cout, l.cin, 3, 3})) {
+        set_error("conv weight: expected shape (%d, %d, 3, 3)", l.cout, l.cin);
+        return -1;
+    }
+    const size_t bytes = hrn::conv3x3_bytes_per_weight_image(l.cin, l.cout);
+    std::vector<uint8_t> img(bytes);
+    hrn::conv3x3_pack_weights(data, l.cin, l.cout, img.data());
+    if (l.w_img == nullptr) HRN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&l.w_img), bytes));
+    HRN_CUDA_OK(cudaMemcpy(l.w_img, img.data(), bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int set_conv_bias(hrn::ConvLayer& l, const float* data, const int64_t* shape, int ndim) {
+    if (!shape_is(shape, ndim, {l.cout})) {
+        set_error("conv bias: expected shape (%d,)", l.cout);
+        return -1;
+    }
+    return upload(&l.bias, data, l.cout);
+}
+
+int set_prelu(float* slot, bool* flag, const int64_t* shape, int ndim, const float* data) {
+    if (!shape_is(shape, ndim, {1})) {
+        set_error("PReLU weight: expected shape (1,) (single shared slope, nn.PReLU() default)");
+        return -1;
+    }
+    *slot = data[0];
+    if (flag != nullptr) *flag = true;
+    return 0;
+}
+
+struct Dump {
+    int stage;
+    float* dst;
+    bool hit;
+};
+
+int maybe_dump(Dump* d, int stage, const __nv_bfloat16* t, int n, int H, int W, int C, cudaStream_t s) {
+    if (d == nullptr || d->stage != stage) return 0;
+    d->hit = true;
+    return hrn::nhwc_bf16_to_nchw_f32_launch(t, n, H, W, C, d->dst, s);
+}
+
+int run_conv(hrn_handle* h, const hrn::ConvLayer& l, hrn::ConvArgs a, cudaStream_t s) {
+    a.cin = l.cin;
+    a.cout = l.cout;
+    a.w_img = l.w_img;
+    a.bias = l.bias;
+    a.prelu = l.prelu;
+    a.has_prelu = l.has_prelu ? 1 : 0;
+    a.desc_base_offset_mode = h->bo_mode;
+    a.strip_h = h->strip_h;
+    return hrn::conv3x3_launch(a, h->sm_count, s);
+}
+
+int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, int L, int H, int W, float* sr,
+                 cudaStream_t s, Dump* dump) {
+    if (h == nullptr) {
+        set_error("null handle");
+        return -1;
+    }
+    if (hrn_missing_weights(h) != 0) {
+        set_error("hrn_forward: %d of %d state_dict tensors have not been set", hrn_missing_weights(h), h->expected);
+        return -1;
+    }
+    if (B <= 0 || L <= 0 || H <= 0 || W <= 0) {
+        set_error("hrn_forward: empty input (B=%d L=%d H=%d W=%d)", B, L, H, W);
+        return -1;
+    }
+    if (H != W) {
+        set_error("hrn_forward: square inputs only (got %d x %d); the reference view() at HRNet.py:204 swaps H and W",
+                  H, W);
+        return -1;
+    }
+    HRN_CUDA_OK(cudaSetDevice(h->device));
+    const size_t hw = static_cast<size_t>(H) * W;
+    const size_t n_img = static_cast<size_t>(B) * L;
+    const size_t act_bytes = n_img * hw * 64 * sizeof(__nv_bfloat16);
+    if (act_bytes > h->act_cap) {
+        for (int i = 0; i < 5; ++i) {
+            if (h->act[i] != nullptr) HRN_CUDA_OK(cudaFree(h->act[i]));
+            h->act[i] = nullptr;
+        }
+        h->act_cap = 0;
+        for (int i = 0; i < 5; ++i) HRN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->act[i]), act_bytes));
+        h->act_cap = act_bytes;
+    }
+    if (grow(reinterpret_cast<void**>(&h->anchor), &h->anchor_cap, static_cast<size_t>(B) * hw * sizeof(float))) return -1;
+
+    // ---- anchor + first conv (HRNet.py:200-204, 51-53)
+    if (hrn::median_anchor_launch(lrs, B, L, H, W, h->anchor, s)) return -1;
+    if (dump != nullptr && dump->stage == HRN_STAGE_ANCHOR) {
+        HRN_CUDA_OK(cudaMemcpyAsync(dump->dst, h->anchor, static_cast<size_t>(B) * hw * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, s));
+        dump->hit = true;
+    }
+    if (hrn::conv_init_launch(lrs, h->anchor, B, L, H, W, h->w_init, h->b_init, h->prelu_init, h->act[0], s)) return -1;
+    int stage = 0;
+    if (maybe_dump(dump, HRN_STAGE_ENC(stage), h->act[0], static_cast<int>(n_img), H, W, 64, s)) return -1;
+
+    // ---- encoder residual blocks + final conv (HRNet.py:55-60, 17-33)
+    hrn::ConvArgs base{};
+    base.n_img = static_cast<int>(n_img);
+    base.H = H;
+    base.W = W;
+    base.in_images = static_cast<int>(n_img);
+    base.in_c = 64;
+    int cur = 0;
+    for (int r = 0; r < h->cfg.enc_num_layers; ++r) {
+        const int t1 = (cur + 1) % 3, t2 = (cur + 2) % 3;
+        hrn::ConvArgs a = base;
+        a.in = h->act[cur];
+        a.out = h->act[t1];
+        a.res_mode = hrn::RES_NONE;
+        if (run_conv(h, h->enc[2 * r], a, s)) return -1;
+        if (maybe_dump(dump, HRN_STAGE_ENC(++stage), h->act[t1], base.n_img, H, W, 64, s)) return -1;
+        a.in = h->act[t1];
+        a.out = h->act[t2];
+        a.res_mode = hrn::RES_SAME;
+        a.res = h->act[cur];
+        if (run_conv(h, h->enc[2 * r + 1], a, s)) return -1;
+        if (maybe_dump(dump, HRN_STAGE_ENC(++stage), h->act[t2], base.n_img, H, W, 64, s)) return -1;
+        cur = t2;
+    }
+    {
+        hrn::ConvArgs a = base;
+        a.in = h->act[cur];
+        a.out = h->act[(cur + 1) % 3];
+        a.res_mode = hrn::RES_NONE;
+        if (run_conv(h, h->enc.back(), a, s)) return -1;
+        cur = (cur + 1) % 3;
+        if (maybe_dump(dump, HRN_STAGE_ENC(++stage), h->act[cur], base.n_img, H, W, 64, s)) return -1;
+    }
+
+    // ---- recursive fusion (HRNet.py:99-134)
+    int n = L, level = 0;
+    __nv_bfloat16 *t1 = h->act[3], *t2 = h->act[4];
+    while (n / 2 > 0) {
+        const int half = n / 2, top = n - (n % 2);
+        const int next = (cur + 1) % 3;
+        hrn::ConvArgs a{};
+        a.n_img = B * half;
+        a.H = H;
+        a.W = W;
+        a.half = half;
+        a.src_views = n;
+        a.top = top;
+        // conv 1 of the residual block on cat(alice, bob): the concat is two K chunks from two views
+        a.pair_mode = 1;
+        a.in = h->act[cur];
+        a.in_images = B * n;
+        a.in_c = 64;
+        a.out = t1;
+        a.res_mode = hrn::RES_NONE;
+        if (run_conv(h, h->fuse[0], a, s)) return -1;
+        if (maybe_dump(dump, HRN_STAGE_FUSE(level, 0), t1, B * half, H, W, 128, s)) return -1;
+        // conv 2 + skip connection onto cat(alice, bob)
+        a.pair_mode = 0;
+        a.in = t1;
+        a.in_images = B * half;
+        a.in_c = 128;
+        a.out = t2;
+        a.res_mode = hrn::RES_PAIR;
+        a.res = h->act[cur];
+        if (run_conv(h, h->fuse[1], a, s)) return -1;
+        if (maybe_dump(dump, HRN_STAGE_FUSE(level, 1), t2, B * half, H, W, 128, s)) return -1;
+        // conv 128 -> 64 + PReLU, then alice + alpha_bob * x
+        a.in = t2;
+        a.out = h->act[next];
+        a.res_mode = h->cfg.rec_alpha_residual ? hrn::RES_ALPHA : hrn::RES_NONE;
+        a.res = h->act[cur];
+        a.alphas = alphas;
+        a.alpha_stride = L;
+        if (run_conv(h, h->fuse[2], a, s)) return -1;
+        if (maybe_dump(dump, HRN_STAGE_FUSE(level, 2), h->act[next], B * half, H, W, 64, s)) return -1;
+        cur = next;
+        n = half;
+        ++level;
+    }
+    // torch.mean over the single remaining view (HRNet.py:134) is the identity: the loop always ends at n == 1.
+
+    // ---- decoder (HRNet.py:147-156)
+    if (hrn::decoder_launch(h->act[cur], B, H, W, h->wd, h->bd, h->prelu_dec, h->wf, h->bf, sr, s)) return -1;
+    if (dump != nullptr && !dump->hit) {
+        set_error("hrn_forward_dump: stage 0x%x does not exist for L=%d", dump->stage, L);
+        return -1;
+    }
+    return 0;
+}
+
+}  // namespace
+
+// ============================================================================ C ABI
+extern "C" {
+
+int32_t hrn_abi_version(void) { return HRN_ABI_VERSION; }
+const char* hrn_last_error(void) { return hrn::g_error; }
+int64_t hrn_kernel_launch_count(void) { return hrn::g_launches.load(); }
+
+int32_t hrn_create(const hrn_config* cfg, int32_t device, hrn_handle** out) {
+    if (cfg == nullptr || out == nullptr) {
+        set_error("hrn_create: null argument");
+        return -1;
+    }
+    *out = nullptr;
+    const hrn_config& c = *cfg;
+    if (c.enc_in_channels != 2 || c.enc_kernel_size != 3 || c.enc_channels != 64 || c.rec_in_channels != 64 ||
+        c.rec_kernel_size != 3 || c.dec_in_channels != 64 || c.dec_out_channels != 64 || c.dec_kernel_size != 3 ||
+        c.dec_stride != 3 || c.fin_in_channels != 64 || c.fin_kernel_size != 1 || c.fin_out_channels != 1 ||
+        c.enc_num_layers < 0 || c.enc_num_layers > 16) {
+        set_error("hrn_create: unsupported network config; kernels are specialised for encoder 2->64 k3, "
+                  "recursive 64 k3, deconv 64->64 k3 s3, final 64->1 k1 (config/config.json), num_layers 0..16");
+        return -1;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        set_error("hrn_create: no CUDA device visible; this library has no CPU fallback");
+        return -1;
+    }
+    if (device < 0 || device >= ndev) {
+        set_error("hrn_create: device %d out of range (0..%d)", device, ndev - 1);
+        return -1;
+    }
+    cudaDeviceProp prop;
+    HRN_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("hrn_create: device %d is sm_%d%d; kernels are built for sm_100a (B200) only", device, prop.major,
+                  prop.minor);
+        return -1;
+    }
+    HRN_CUDA_OK(cudaSetDevice(device));
+    hrn_handle* h = new hrn_handle();
+    h->cfg = c;
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->enc.resize(2 * c.enc_num_layers + 1);
+    for (size_t i = 0; i < h->enc.size(); ++i) {
+        h->enc[i].cin = h->enc[i].cout = 64;
+        h->enc[i].has_prelu = false;   // set when its PReLU slope arrives; the final conv has none
+    }
+    h->fuse[0].cin = h->fuse[0].cout = 128;
+    h->fuse[1].cin = h->fuse[1].cout = 128;
+    h->fuse[2].cin = 128;
+    h->fuse[2].cout = 64;
+    h->expected = 3 + 6 * c.enc_num_layers + 2 + 9 + 5;
+    *out = h;
+    return 0;
+}
+
+void hrn_destroy(hrn_handle* h) {
+    if (h == nullptr) return;
+    cudaSetDevice(h->device);
+    auto rel = [](void* p) {
+        if (p != nullptr) cudaFree(p);
+    };
+    rel(h->w_init);
+    rel(h->b_init);
+    for (auto& l : h->enc) {
+        rel(l.w_img);
+        rel(l.bias);
+    }
+    for (auto& l : h->fuse) {
+        rel(l.w_img);
+        rel(l.bias);
+    }
+    rel(h->wd);
+    rel(h->bd);
+    rel(h->wf);
+    for (auto* p : h->act) rel(p);
+    rel(h->anchor);
+    for (auto* p : h->io) rel(p);
+    delete h;
+}
+
+int32_t hrn_missing_weights(const hrn_handle* h) {
+    return h == nullptr ? -1 : h->expected - static_cast<int>(h->have.size());
+}
+
+int32_t hrn_set_weight(hrn_handle* h, const char* key, const float* data, const int64_t* shape, int32_t ndim) {
+    if (h == nullptr || key == nullptr || data == nullptr || shape == nullptr) {
+        set_error("hrn_set_weight: null argument");
+        return -1;
+    }
+    HRN_CUDA_OK(cudaSetDevice(h->device));
+    const std::string k(key);
+    int rc = -2;
+    int r = 0, j = 0;
+    char tail[16] = "";
+    if (k == "encode.init_layer.0.weight") {
+        rc = shape_is(shape, ndim, {64, 2, 3, 3}) ? upload(&h->w_init, data, 64 * 18) : -3;
+    } else if (k == "encode.init_layer.0.bias") {
+        rc = shape_is(shape, ndim, {64}) ? upload(&h->b_init, data, 64) : -3;
+    } else if (k == "encode.init_layer.1.weight") {
+        rc = set_prelu(&h->prelu_init, nullptr, shape, ndim, data);
+    } else if (sscanf(key, "encode.res_layers.%d.block.%d.%15s", &r, &j, tail) == 3 && r >= 0 &&
+               r < h->cfg.enc_num_layers && j >= 0 && j <= 3) {
+        hrn::ConvLayer& l = h->enc[2 * r + j / 2];
+        if ((j & 1) == 0 && strcmp(tail, "weight") == 0) rc = set_conv_weight(l, data, shape, ndim);
+        else if ((j & 1) == 0 && strcmp(tail, "bias") == 0) rc = set_conv_bias(l, data, shape, ndim);
+        else if ((j & 1) == 1 && strcmp(tail, "weight") == 0) rc = set_prelu(&l.prelu, &l.has_prelu, shape, ndim, data);
+    } else if (k == "encode.final.0.weight") {
+        rc = set_conv_weight(h->enc.back(), data, shape, ndim);
+    } else if (k == "encode.final.0.bias") {
+        rc = set_conv_bias(h->enc.back(), data, shape, ndim);
+    } else if (sscanf(key, "fuse.fuse.0.block.%d.%15s", &j, tail) == 2 && j >= 0 && j <= 3) {
+        hrn::ConvLayer& l = h->fuse[j / 2];
+        if ((j & 1) == 0 && strcmp(tail, "weight") == 0) rc = set_conv_weight(l, data, shape, ndim);
+        else if ((j & 1) == 0 && strcmp(tail, "bias") == 0) rc = set_conv_bias(l, data, shape, ndim);
+        else if ((j & 1) == 1 && strcmp(tail, "weight") == 0) rc = set_prelu(&l.prelu, &l.has_prelu, shape, ndim, data);
+    } else if (k == "fuse.fuse.1.weight") {
+        rc = set_conv_weight(h->fuse[2], data, shape, ndim);
+    } else if (k == "fuse.fuse.1.bias") {
+        rc = set_conv_bias(h->fuse[2], data, shape, ndim);
+    } else if (k == "fuse.fuse.2.weight") {
+        rc = set_prelu(&h->fuse[2].prelu, &h->fuse[2].has_prelu, shape, ndim, data);
+    } else if (k == "decode.deconv.0.weight") {
+        if (shape_is(shape, ndim, {64, 64, 3, 3})) {
+            // ConvTranspose2d weight (ci, co, ky, kx) -> [pos = ky*3+kx][co][ci]
+            std::vector<float> packed(9 * 64 * 64);
+            for (int ci = 0; ci < 64; ++ci)
+                for (int co = 0; co < 64; ++co)
+                    for (int pos = 0; pos < 9; ++pos)
+                        packed[(static_cast<size_t>(pos) * 64 + co) * 64 + ci] = data[(static_cast<size_t>(ci) * 64 + co) * 9 + pos];
+            rc = upload(&h->wd, packed.data(), packed.size());
+        } else rc = -3;
+    } else if (k == "decode.deconv.0.bias") {
+        rc = shape_is(shape, ndim, {64}) ? upload(&h->bd, data, 64) : -3;
+    } else if (k == "decode.deconv.1.weight") {
+        rc = set_prelu(&h->prelu_dec, nullptr, shape, ndim, data);
+    } else if (k == "decode.final.weight") {
+        rc = shape_is(shape, ndim, {1, 64, 1, 1}) ? upload(&h->wf, data, 64) : -3;
+    } else if (k == "decode.final.bias") {
+        if (shape_is(shape, ndim, {1})) {
+            h->bf = data[0];
+            rc = 0;
+        } else rc = -3;
+    }
+    if (rc == -2) {
+        set_error("hrn_set_weight: unknown state_dict key '%s'", key);
+        return -1;
+    }
+    if (rc == -3) {
+        set_error("hrn_set_weight: wrong shape for '%s'", key);
+        return -1;
+    }
+    if (rc != 0) return -1;
+    h->have.insert(k);
+    return 0;
+}
+
+int32_t hrn_forward(hrn_handle* h, const float* lrs, const float* alphas, int32_t B, int32_t L, int32_t H, int32_t W,
+                    float* sr, void* stream) {
+    return forward_impl(h, lrs, alphas, B, L, H, W, sr, static_cast<cudaStream_t>(stream), nullptr);
+}
+
+int32_t hrn_forward_dump(hrn_handle* h, const float* lrs, const float* alphas, int32_t B, int32_t L, int32_t H,
+                         int32_t W, float* sr, int32_t stage, float* dump, void* stream) {
+    Dump d{stage, dump, false};
+    return forward_impl(h, lrs, alphas, B, L, H, W, sr, static_cast<cudaStream_t>(stream), &d);
+}
+
+int32_t hrn_forward_host(hrn_handle* h, const float* lrs_host, const float* alphas_host, int32_t B, int32_t L,
+                         int32_t H, int32_t W, float* sr_host, void* stream) {
+    if (h == nullptr) {
+        set_error("null handle");
+        return -1;
+    }
+    if (B <= 0 || L <= 0 || H <= 0 || W <= 0) {
+        set_error("hrn_forward_host: empty input");
+        return -1;
+    }
+    HRN_CUDA_OK(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t n_lrs = static_cast<size_t>(B) * L * H * W, n_al = static_cast<size_t>(B) * L;
+    const size_t n_sr = static_cast<size_t>(B) * 9 * H * W;
+    if (grow(reinterpret_cast<void**>(&h->io[0]), &h->io_cap[0], n_lrs * 4)) return -1;
+    if (grow(reinterpret_cast<void**>(&h->io[1]), &h->io_cap[1], n_al * 4)) return -1;
+    if (grow(reinterpret_cast<void**>(&h->io[2]), &h->io_cap[2], n_sr * 4)) return -1;
+    HRN_CUDA_OK(cudaMemcpyAsync(h->io[0], lrs_host, n_lrs * 4, cudaMemcpyHostToDevice, s));
+    HRN_CUDA_OK(cudaMemcpyAsync(h->io[1], alphas_host, n_al * 4, cudaMemcpyHostToDevice, s));
+    if (forward_impl(h, h->io[0], h->io[1], B, L, H, W, h->io[2], s, nullptr)) return -1;
+    HRN_CUDA_OK(cudaMemcpyAsync(sr_host, h->io[2], n_sr * 4, cudaMemcpyDeviceToHost, s));
+    HRN_CUDA_OK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int32_t hrn_lanczos_shift(const float* img, const float* shift, int32_t Nb, int32_t C, int32_t H, int32_t W, int32_t p,
+                          int32_t a, int32_t ntaps, float* out, void* stream) {
+    if (img == nullptr || shift == nullptr || out == nullptr) {
+        set_error("hrn_lanczos_shift: null pointer");
+        return -1;
+    }
+    return hrn::lanczos_shift_launch(img, shift, Nb, C, H, W, p, a, ntaps, out, static_cast<cudaStream_t>(stream));
+}
+
+int32_t hrn_lanczos_taps(const float* d, int32_t n, int32_t a, int32_t ntaps, float* taps, void* stream) {
+    if (d == nullptr || taps == nullptr) {
+        set_error("hrn_lanczos_taps: null pointer");
+        return -1;
+    }
+    return hrn::lanczos_taps_launch(d, n, a, ntaps, taps, static_cast<cudaStream_t>(stream));
+}
+
+int32_t hrn_shift_cpsnr(const float* sr, const float* hr, const float* hr_map, int32_t B, int32_t H, int32_t W,
+                        int32_t border_w, int32_t clip_sr, float* best_db, int32_t* best_site, float* site_db,
+                        void* stream) {
+    if (sr == nullptr || hr == nullptr || hr_map == nullptr || best_db == nullptr || best_site == nullptr) {
+        set_error("hrn_shift_cpsnr: null pointer");
+        return -1;
+    }
+    return hrn::shift_cpsnr_launch(sr, hr, hr_map, B, H, W, border_w, clip_sr, best_db, best_site, site_db,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value) {
+    if (h == nullptr || knob == nullptr) {
+        set_error("hrn_debug_set: null argument");
+        return -1;
+    }
+    if (strcmp(knob, "desc_base_offset_mode") == 0) h->bo_mode = value;
+    else if (strcmp(knob, "strip_h") == 0) h->strip_h = value;
+    else {
+        set_error("hrn_debug_set: unknown knob '%s'", knob);
+        return -1;
+    }
+    return 0;
+}
+
+}  // extern "C"

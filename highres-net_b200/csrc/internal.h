@@ -1,0 +1,79 @@
+// Internal declarations shared by the translation units of libhrn_b200.so.
+// Nothing here crosses the C ABI (see include/hrn_b200.h for that).
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace hrn {
+
+// ------------------------------------------------------------------ errors
+void set_error(const char* fmt, ...);
+void note_launches(int n);   // feeds hrn_kernel_launch_count()
+#define HRN_CUDA_OK(expr)                                                                      \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            ::hrn::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                             __LINE__);                                                        \
+            return -1;                                                                         \
+        }                                                                                      \
+    } while (0)
+
+// ------------------------------------------------------------------ conv3x3 (tcgen05)
+// Residual / merge modes of the conv epilogue.
+enum ResMode : int {
+    RES_NONE = 0,
+    RES_SAME = 1,    // out = y + res[m]                         (ResidualBlock skip, HRNet.py:32-33)
+    RES_PAIR = 2,    // out = y + cat(alice, bob)[m]             (ResidualBlock(128) skip on the fused pair)
+    RES_ALPHA = 3,   // out = alice[m] + alpha_bob[m] * y        (HRNet.py:123-128)
+};
+
+struct ConvArgs {
+    // geometry of the OUTPUT images (same H, W as the input: 3x3, pad 1)
+    int n_img, H, W;
+    int cin, cout;            // cin in {64, 128}; cout in {64, 128}
+    int strip_h;              // output rows handled per work item
+    // A operand gather.  pair_mode: output image m = (b, i) reads chunk 0 from view i and chunk 1 from
+    // view top-1-i of the 64-channel view stack (HRNet.py:114-119); otherwise chunk c = channels [64c, 64c+64).
+    int pair_mode, half, src_views, top;
+    const void* in;           // bf16 NHWC source tensor (for the TMA map)
+    int in_images, in_c;      // its image count and channels per pixel
+    // B operand: pre-swizzled smem image, [cout / n_tile][9 taps][cin / 64][n_tile rows x 128 B]
+    const uint8_t* w_img;
+    const float* bias;        // [cout]
+    float prelu;
+    int has_prelu;
+    // epilogue
+    __nv_bfloat16* out;       // bf16 NHWC, cout channels per pixel
+    int res_mode;
+    const __nv_bfloat16* res; // RES_SAME: cout-channel tensor; RES_PAIR / RES_ALPHA: the 64-channel view stack
+    const float* alphas;      // (B, alpha_stride) original alphas, RES_ALPHA only
+    int alpha_stride;
+    int desc_base_offset_mode;   // bring-up knob: 0 = base_offset 0, 1 = (start >> 7) & 7
+};
+int conv3x3_bytes_per_weight_image(int cin, int cout);
+// Repack OIHW fp32 (cout, cin, 3, 3) host weights into the pre-swizzled bf16 smem image (host memory).
+void conv3x3_pack_weights(const float* oihw, int cin, int cout, uint8_t* dst);
+int conv3x3_launch(const ConvArgs& a, int sm_count, cudaStream_t stream);
+
+// ------------------------------------------------------------------ pointwise / CUDA-core kernels
+int median_anchor_launch(const float* lrs, int B, int L, int H, int W, float* anchor, cudaStream_t s);
+// conv 2->64 + PReLU on (view, anchor) pairs; writes bf16 NHWC (B*L, H, W, 64).  w: (64, 2, 3, 3) fp32 device.
+int conv_init_launch(const float* lrs, const float* anchor, int B, int L, int H, int W, const float* w,
+                     const float* bias, float prelu, __nv_bfloat16* out, cudaStream_t s);
+// stride-3 deconv + PReLU + 1x1 conv, fused; in: bf16 NHWC (B, H, W, 64) -> out fp32 (B, 3H, 3W).
+// wd: (9, 64 co, 64 ci) fp32 device (repacked), bd (64), wf (64), bf scalar.
+int decoder_launch(const __nv_bfloat16* in, int B, int H, int W, const float* wd, const float* bd, float prelu,
+                   const float* wf, float bf, float* out, cudaStream_t s);
+int nhwc_bf16_to_nchw_f32_launch(const __nv_bfloat16* in, int n, int H, int W, int C, float* out, cudaStream_t s);
+
+// ------------------------------------------------------------------ scoring
+int lanczos_shift_launch(const float* img, const float* shift, int nb, int c, int H, int W, int p, int a,
+                         int ntaps, float* out, cudaStream_t s);
+int lanczos_taps_launch(const float* d, int n, int a, int ntaps, float* out, cudaStream_t s);
+int shift_cpsnr_launch(const float* sr, const float* hr, const float* hm, int B, int H, int W, int border,
+                       int clip_sr, float* best_db, int32_t* best_site, float* site_db, cudaStream_t s);
+
+}  // namespace hrn

@@ -1,0 +1,233 @@
+// CUDA-core kernels of the HRNet path that are HBM-bound (or tiny) rather than
+// dense contractions: the median anchor (HRNet.py:200), the 2->64 first conv on
+// (view, anchor) pairs with the repeat/cat of HRNet.py:201-204 fused away, the
+// decoder (stride-3 deconv + PReLU + 1x1 conv, HRNet.py:147-156, fused so that the
+// 64 x 3H x 3W tensor is never materialised) and a layout-conversion helper used
+// by the stage-dump test hook.
+#include "internal.h"
+
+namespace hrn {
+namespace {
+
+// ------------------------------------------------------------------ median anchor
+// Lower median of the first k = min(L, 9) views per pixel: element (k-1)/2 of the
+// sorted values (torch.median semantics; zero-padded views take part).
+__global__ void median_anchor_kernel(const float* __restrict__ lrs, int L, int k, size_t hw, size_t total,
+                                     float* __restrict__ anchor) {
+    const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (idx >= total) return;
+    const size_t b = idx / hw, p = idx % hw;
+    const float* src = lrs + b * L * hw + p;
+    float v[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) v[i] = i < k ? __ldg(src + i * hw) : __int_as_float(0x7f800000);
+    // 9-element insertion sort, fully unrolled (registers only)
+#pragma unroll
+    for (int i = 1; i < 9; ++i) {
+#pragma unroll
+        for (int j = i; j > 0; --j) {
+            const float lo = fminf(v[j - 1], v[j]), hi = fmaxf(v[j - 1], v[j]);
+            v[j - 1] = lo;
+            v[j] = hi;
+        }
+    }
+    const int sel = (k - 1) >> 1;
+    float out = v[0];
+#pragma unroll
+    for (int i = 1; i < 9; ++i) out = (i == sel) ? v[i] : out;
+    anchor[idx] = out;
+}
+
+// ------------------------------------------------------------------ conv 2 -> 64 + PReLU
+// Block = 32 x 8 output pixels of one (imageset, view).  Input channel 0 is the view,
+// channel 1 the per-imageset anchor.  fp32 math, bf16 NHWC store (128 B per pixel).
+constexpr int CI_TX = 32, CI_TY = 8;
+__global__ void __launch_bounds__(CI_TX* CI_TY)
+conv_init_kernel(const float* __restrict__ lrs, const float* __restrict__ anchor, int L, int H, int W,
+                 const float* __restrict__ w, const float* __restrict__ bias, float prelu,
+                 __nv_bfloat16* __restrict__ out) {
+    __shared__ float tile[2][CI_TY + 2][CI_TX + 2];
+    __shared__ __align__(16) float ws[18][64];   // [ci*9 + tap][co]
+    __shared__ float bs[64];
+    const int m = blockIdx.z;                    // image index b * L + view
+    const int b = m / L;
+    const int x0 = blockIdx.x * CI_TX, y0 = blockIdx.y * CI_TY;
+    const int tid = threadIdx.y * CI_TX + threadIdx.x;
+    const size_t hw = static_cast<size_t>(H) * W;
+    const float* src0 = lrs + static_cast<size_t>(m) * hw;
+    const float* src1 = anchor + static_cast<size_t>(b) * hw;
+    for (int i = tid; i < 2 * (CI_TY + 2) * (CI_TX + 2); i += CI_TX * CI_TY) {
+        const int c = i / ((CI_TY + 2) * (CI_TX + 2));
+        const int r = (i / (CI_TX + 2)) % (CI_TY + 2), q = i % (CI_TX + 2);
+        const int y = y0 + r - 1, x = x0 + q - 1;
+        float v = 0.0f;
+        if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg((c ? src1 : src0) + static_cast<size_t>(y) * W + x);
+        tile[c][r][q] = v;
+    }
+    for (int i = tid; i < 18 * 64; i += CI_TX * CI_TY) {
+        const int k = i / 64, co = i % 64;          // k = ci * 9 + tap ; w is (co, ci, ky, kx)
+        ws[k][co] = __ldg(w + co * 18 + k);
+    }
+    if (tid < 64) bs[tid] = __ldg(bias + tid);
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    float in[18];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) in[c * 9 + ky * 3 + kx] = tile[c][threadIdx.y + ky][threadIdx.x + kx];
+    uint4* op = reinterpret_cast<uint4*>(out + (static_cast<size_t>(m) * hw + static_cast<size_t>(y) * W + x) * 64);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = bs[g * 8 + e];
+#pragma unroll
+        for (int k = 0; k < 18; ++k) {
+            const float4 wa = *reinterpret_cast<const float4*>(&ws[k][g * 8]);
+            const float4 wb = *reinterpret_cast<const float4*>(&ws[k][g * 8 + 4]);
+            acc[0] = fmaf(in[k], wa.x, acc[0]);
+            acc[1] = fmaf(in[k], wa.y, acc[1]);
+            acc[2] = fmaf(in[k], wa.z, acc[2]);
+            acc[3] = fmaf(in[k], wa.w, acc[3]);
+            acc[4] = fmaf(in[k], wb.x, acc[4]);
+            acc[5] = fmaf(in[k], wb.y, acc[5]);
+            acc[6] = fmaf(in[k], wb.z, acc[6]);
+            acc[7] = fmaf(in[k], wb.w, acc[7]);
+        }
+        uint4 o;
+        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float p0 = acc[2 * e], p1 = acc[2 * e + 1];
+            p0 = p0 >= 0.0f ? p0 : prelu * p0;
+            p1 = p1 >= 0.0f ? p1 : prelu * p1;
+            o2[e] = __floats2bfloat162_rn(p0, p1);
+        }
+        op[g] = o;
+    }
+}
+
+// ------------------------------------------------------------------ decoder (CUDA-core version)
+// stride == kernel (3) => no overlap: every LR pixel produces its own 3x3 HR block:
+//   sr[3y+ky, 3x+kx] = bf + sum_co wf[co] * PReLU(bd[co] + sum_ci in[ci] * Wd[ci, co, ky, kx])
+// Block = 128 LR pixels (one per thread); the repacked deconv weight for ONE (ky, kx)
+// position at a time (64 x 64 fp32 = 16 KB) is staged in shared memory.
+constexpr int DEC_THREADS = 128;
+__global__ void __launch_bounds__(DEC_THREADS)
+decoder_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, size_t npix, const float* __restrict__ wd,
+               const float* __restrict__ bd, float prelu, const float* __restrict__ wf, float bf,
+               float* __restrict__ out) {
+    __shared__ __align__(16) float wsm[64][64];   // [co][ci] of the current position
+    __shared__ float bds[64], wfs[64];
+    const size_t pix = blockIdx.x * static_cast<size_t>(DEC_THREADS) + threadIdx.x;
+    const bool valid = pix < npix;
+    if (threadIdx.x < 64) {
+        bds[threadIdx.x] = __ldg(bd + threadIdx.x);
+        wfs[threadIdx.x] = __ldg(wf + threadIdx.x);
+    }
+    float xin[64];
+    if (valid) {
+        const uint4* ip = reinterpret_cast<const uint4*>(in + pix * 64);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            const uint4 raw = __ldg(ip + v);
+            const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(r2[e]);
+                xin[v * 8 + 2 * e] = f.x;
+                xin[v * 8 + 2 * e + 1] = f.y;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) xin[i] = 0.0f;
+    }
+    const size_t hw = static_cast<size_t>(H) * W;
+    const size_t b = valid ? pix / hw : 0;
+    const int y = valid ? static_cast<int>((pix % hw) / W) : 0, x = valid ? static_cast<int>(pix % W) : 0;
+    float* obase = out + b * 9 * hw + (static_cast<size_t>(3 * y) * (3 * W) + 3 * x);
+    for (int pos = 0; pos < 9; ++pos) {
+        __syncthreads();
+        const float4* wsrc = reinterpret_cast<const float4*>(wd + static_cast<size_t>(pos) * 4096);
+        float4* wdst = reinterpret_cast<float4*>(&wsm[0][0]);
+        for (int i = threadIdx.x; i < 1024; i += DEC_THREADS) wdst[i] = __ldg(wsrc + i);
+        __syncthreads();
+        float sr = bf;
+#pragma unroll 4
+        for (int co = 0; co < 64; ++co) {
+            float acc = bds[co];
+#pragma unroll
+            for (int c4 = 0; c4 < 16; ++c4) {
+                const float4 wv = *reinterpret_cast<const float4*>(&wsm[co][c4 * 4]);
+                acc = fmaf(xin[c4 * 4 + 0], wv.x, acc);
+                acc = fmaf(xin[c4 * 4 + 1], wv.y, acc);
+                acc = fmaf(xin[c4 * 4 + 2], wv.z, acc);
+                acc = fmaf(xin[c4 * 4 + 3], wv.w, acc);
+            }
+            acc = acc >= 0.0f ? acc : prelu * acc;
+            sr = fmaf(wfs[co], acc, sr);
+        }
+        if (valid) obase[static_cast<size_t>(pos / 3) * (3 * W) + (pos % 3)] = sr;
+    }
+}
+
+// ------------------------------------------------------------------ bf16 NHWC -> fp32 NCHW (test hook)
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, size_t hw, int C, size_t total,
+                                    float* __restrict__ out) {
+    const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;   // over n * C * hw (NCHW order)
+    if (idx >= total) return;
+    const size_t p = idx % hw;
+    const size_t c = (idx / hw) % C;
+    const size_t n = idx / (hw * C);
+    out[idx] = __bfloat162float(in[(n * hw + p) * C + c]);
+}
+
+}  // namespace
+
+int median_anchor_launch(const float* lrs, int B, int L, int H, int W, float* anchor, cudaStream_t s) {
+    const size_t hw = static_cast<size_t>(H) * W, total = hw * B;
+    const int k = L < 9 ? L : 9;
+    median_anchor_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(lrs, L, k, hw, total, anchor);
+    note_launches(1);
+    HRN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int conv_init_launch(const float* lrs, const float* anchor, int B, int L, int H, int W, const float* w,
+                     const float* bias, float prelu, __nv_bfloat16* out, cudaStream_t s) {
+    const long long imgs = static_cast<long long>(B) * L;
+    if (imgs > 65535) {
+        set_error("conv_init: B*L = %lld exceeds the grid z limit (65535); split the batch", imgs);
+        return -1;
+    }
+    dim3 grid((W + CI_TX - 1) / CI_TX, (H + CI_TY - 1) / CI_TY, static_cast<unsigned>(imgs));
+    conv_init_kernel<<<grid, dim3(CI_TX, CI_TY), 0, s>>>(lrs, anchor, L, H, W, w, bias, prelu, out);
+    note_launches(1);
+    HRN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int decoder_launch(const __nv_bfloat16* in, int B, int H, int W, const float* wd, const float* bd, float prelu,
+                   const float* wf, float bf, float* out, cudaStream_t s) {
+    const size_t npix = static_cast<size_t>(B) * H * W;
+    decoder_kernel<<<static_cast<unsigned>((npix + DEC_THREADS - 1) / DEC_THREADS), DEC_THREADS, 0, s>>>(
+        in, H, W, npix, wd, bd, prelu, wf, bf, out);
+    note_launches(1);
+    HRN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int nhwc_bf16_to_nchw_f32_launch(const __nv_bfloat16* in, int n, int H, int W, int C, float* out, cudaStream_t s) {
+    const size_t hw = static_cast<size_t>(H) * W, total = hw * C * n;
+    nhwc_to_nchw_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, hw, C, total, out);
+    note_launches(1);
+    HRN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace hrn

@@ -1,0 +1,299 @@
+// Scoring half of the hot path:
+//   * lanczos_shift_kernel : separable 7-tap Lanczos sub-pixel shift with reflect padding
+//     (lanczos.py:47-107 + lanczos_kernel lanczos.py:5-43); one launch for all images
+//     instead of ~25 tiny launches per image.
+//   * cpsnr_*              : brightness-bias-corrected clear-PSNR for all (2*border+1)^2
+//     integer shifts of HR against the border-cropped SR (Evaluator.py:11-43, 52-73),
+//     with the max AND the argmax (first maximum in row-major (x, y) order, np.argmax).
+//
+// cPSNR arithmetic mirrors the reference element-wise ops in fp32 (diff, diff*map,
+// (diff-bias)*map, square); only the big sums are carried in fp64 and reduced in a
+// fixed order, so results are deterministic and within ~1e-6 dB of the fp32 numpy loop.
+#include "internal.h"
+
+namespace hrn {
+namespace {
+
+constexpr int MAX_TAPS = 15;
+
+// ------------------------------------------------------------------ Lanczos
+constexpr int LZ_TW = 64, LZ_TH = 32, LZ_THREADS = 256;
+
+// lanczos.py:26-41 in fp32: w(t) = sinc(pi t) sinc(pi t / a), pi t == 0 -> 1e-6, no |t| < a support clamp,
+// normalised to sum 1.
+__device__ __forceinline__ void lanczos_taps_device(float d, int a, int ntaps, float* taps) {
+    const int half = ntaps / 2;
+    float k[MAX_TAPS], sum = 0.0f;
+    for (int i = 0; i < ntaps; ++i) {
+        const float x = static_cast<float>(i - half) - d;
+        float pix = 3.14159265358979323846f * x;
+        pix = pix == 0.0f ? 1e-6f : pix;
+        const float pa = pix / static_cast<float>(a);
+        k[i] = (sinf(pix) / pix) * (sinf(pa) / pa);
+        sum += k[i];
+    }
+    for (int i = 0; i < ntaps; ++i) taps[i] = k[i] / sum;
+}
+
+__global__ void lanczos_taps_kernel(const float* __restrict__ d, int n, int a, int ntaps, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float t[MAX_TAPS];
+    lanczos_taps_device(d[i], a, ntaps, t);
+    for (int k = 0; k < ntaps; ++k) out[static_cast<size_t>(i) * ntaps + k] = t[k];
+}
+
+__device__ __forceinline__ int padded_index(int q, int size, int p, bool* ok) {
+    // reflect (no edge repeat) inside the p-wide ReflectionPad2d ring, zero outside (conv2d zero padding)
+    *ok = (q >= -p) && (q < size + p);
+    int r = q < 0 ? -q : q;
+    r = r >= size ? 2 * (size - 1) - r : r;
+    return min(max(r, 0), size - 1);
+}
+
+__global__ void __launch_bounds__(LZ_THREADS)
+lanczos_shift_kernel(const float* __restrict__ img, const float* __restrict__ shift, int C, int H, int W, int p,
+                     int a, int ntaps, float* __restrict__ out) {
+    extern __shared__ float lz_smem[];
+    const int half = ntaps / 2;
+    const int in_w = LZ_TW + 2 * half, in_h = LZ_TH + 2 * half;
+    float* tile = lz_smem;                        // [in_h][in_w]
+    float* tmp = tile + in_h * in_w;              // [LZ_TH][in_w]
+    __shared__ float taps[2][MAX_TAPS];
+    const int plane = blockIdx.z;                 // n * C + c
+    const int c = plane % C;
+    const int x0 = blockIdx.x * LZ_TW, y0 = blockIdx.y * LZ_TH;
+    const float* src = img + static_cast<size_t>(plane) * H * W;
+
+    if (threadIdx.x < 2) lanczos_taps_device(shift[c * 2 + threadIdx.x], a, ntaps, taps[threadIdx.x]);
+    for (int i = threadIdx.x; i < in_h * in_w; i += LZ_THREADS) {
+        const int r = i / in_w, q = i % in_w;
+        bool oky, okx;
+        const int yy = padded_index(y0 + r - half, H, p, &oky);
+        const int xx = padded_index(x0 + q - half, W, p, &okx);
+        tile[i] = (oky && okx) ? __ldg(src + static_cast<size_t>(yy) * W + xx) : 0.0f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < LZ_TH * in_w; i += LZ_THREADS) {      // y pass (dim 0 taps first, lanczos.py:90)
+        const int r = i / in_w, q = i % in_w;
+        float acc = 0.0f;
+        for (int t = 0; t < ntaps; ++t) acc = fmaf(taps[0][t], tile[(r + t) * in_w + q], acc);
+        tmp[i] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < LZ_TH * LZ_TW; i += LZ_THREADS) {     // x pass (lanczos.py:94)
+        const int r = i / LZ_TW, q = i % LZ_TW;
+        const int y = y0 + r, x = x0 + q;
+        if (y < H && x < W) {
+            float acc = 0.0f;
+            for (int t = 0; t < ntaps; ++t) acc = fmaf(taps[1][t], tmp[r * in_w + q + t], acc);
+            out[static_cast<size_t>(plane) * H * W + static_cast<size_t>(y) * W + x] = acc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ cPSNR shift search
+constexpr int CP_COLS = 32;       // crop columns per block (threadIdx.x)
+constexpr int CP_MAXS = 7;        // shifts per axis supported (border_w <= 3)
+constexpr int CP_BANDS = 6;       // row bands per imageset
+
+struct CpGeom {
+    int H, W, border, S, size, col_blocks, band_rows, blocks_per_set;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// PASS 1: per site sum(m) and sum((hr - sr) * m).  PASS 2: per site sum(((hr - sr - bias) * m)^2).
+// Block = (32 columns) x (S row-shifts x); each thread keeps the S column-shifts y in registers.
+template <int PASS>
+__global__ void __launch_bounds__(CP_COLS* CP_MAXS)
+cpsnr_pass_kernel(const float* __restrict__ sr, const float* __restrict__ hr, const float* __restrict__ hm,
+                  CpGeom g, int clip_sr, const float* __restrict__ bias, double* __restrict__ partial) {
+    const int set = blockIdx.y;
+    const int band = blockIdx.x / g.col_blocks, cb = blockIdx.x % g.col_blocks;
+    const int j = cb * CP_COLS + threadIdx.x;      // crop column
+    const int x = threadIdx.y;                     // row shift handled by this thread
+    const size_t plane = static_cast<size_t>(g.H) * g.W;
+    const float* srp = sr + set * plane;
+    const float* hrp = hr + set * plane;
+    const float* hmp = hm + set * plane;
+    const int i0 = band * g.band_rows, i1 = min(g.size, i0 + g.band_rows);
+    double s0[CP_MAXS], s1[CP_MAXS];
+    float b[CP_MAXS];
+#pragma unroll
+    for (int y = 0; y < CP_MAXS; ++y) {
+        s0[y] = 0.0;
+        s1[y] = 0.0;
+        b[y] = (PASS == 2 && y < g.S) ? bias[(set * g.S + x) * g.S + y] : 0.0f;
+    }
+    if (j < g.size) {
+        for (int i = i0; i < i1; ++i) {
+            float s = __ldg(srp + static_cast<size_t>(i + g.border) * g.W + j + g.border);
+            if (clip_sr) s = fminf(fmaxf(s, 0.0f), 1.0f);
+            const float* hrow = hrp + static_cast<size_t>(i + x) * g.W + j;
+            const float* mrow = hmp + static_cast<size_t>(i + x) * g.W + j;
+#pragma unroll
+            for (int y = 0; y < CP_MAXS; ++y) {
+                if (y < g.S) {
+                    const float m = __ldg(mrow + y);
+                    const float d = __ldg(hrow + y) - s;           // diff = hr - sr            (Evaluator.py:35)
+                    if (PASS == 1) {
+                        s0[y] += static_cast<double>(m);           // n_clear                   (Evaluator.py:34)
+                        s1[y] += static_cast<double>(d * m);       // sum(diff * hr_map)        (Evaluator.py:36)
+                    } else {
+                        const float t = (d - b[y]) * m;            // (diff - bias) * hr_map    (Evaluator.py:37)
+                        s0[y] += static_cast<double>(t * t);
+                    }
+                }
+            }
+        }
+    }
+    // fixed-order block reduction over the 32 columns (one warp per x), then one partial per block
+    double* dst = partial + ((static_cast<size_t>(set) * g.blocks_per_set + blockIdx.x) * g.S + x) * g.S * 2;
+#pragma unroll
+    for (int y = 0; y < CP_MAXS; ++y) {
+        if (y < g.S) {
+            const double r0 = warp_sum(s0[y]);
+            const double r1 = PASS == 1 ? warp_sum(s1[y]) : 0.0;
+            if (threadIdx.x == 0) {
+                dst[y * 2] = r0;
+                dst[y * 2 + 1] = r1;
+            }
+        }
+    }
+}
+
+// One block per imageset, one thread per site.  MODE 1: bias = sum(d*m) / n.  MODE 2: scores + argmax.
+template <int MODE>
+__global__ void cpsnr_finalize_kernel(const double* __restrict__ partial, CpGeom g, float* __restrict__ bias,
+                                      double* __restrict__ nclear, float* __restrict__ best_db,
+                                      int32_t* __restrict__ best_site, float* __restrict__ site_db) {
+    __shared__ float score[CP_MAXS * CP_MAXS];
+    const int set = blockIdx.x, site = threadIdx.x, sites = g.S * g.S;
+    if (site < sites) {
+        double a0 = 0.0, a1 = 0.0;
+        const double* src = partial + (static_cast<size_t>(set) * g.blocks_per_set * sites + site) * 2;
+        for (int blk = 0; blk < g.blocks_per_set; ++blk) {
+            a0 += src[static_cast<size_t>(blk) * sites * 2];
+            a1 += src[static_cast<size_t>(blk) * sites * 2 + 1];
+        }
+        if (MODE == 1) {
+            nclear[set * sites + site] = a0;
+            bias[set * sites + site] = static_cast<float>(a1 / a0);          // 0/0 -> NaN like numpy
+        } else {
+            const double cmse = a0 / nclear[set * sites + site];
+            const float s = static_cast<float>(-10.0 * log10(cmse));          // cMSE = 0 -> +inf
+            score[site] = s;
+            if (site_db != nullptr) site_db[set * sites + site] = s;
+        }
+    }
+    if (MODE == 2) {
+        __syncthreads();
+        if (site == 0) {
+            // np.max / np.argmax semantics: NaN wins and the first NaN (else first maximum) is the argmax
+            int arg = 0;
+            float best = score[0];
+            for (int k = 1; k < sites; ++k) {
+                const float v = score[k];
+                if (best != best) break;
+                if (v != v || v > best) {
+                    best = v;
+                    arg = k;
+                }
+            }
+            best_db[set] = best;
+            best_site[set] = arg;
+        }
+    }
+}
+
+}  // namespace
+
+int lanczos_shift_launch(const float* img, const float* shift, int nb, int c, int H, int W, int p, int a, int ntaps,
+                         float* out, cudaStream_t s) {
+    if (ntaps < 1 || ntaps > MAX_TAPS || (ntaps & 1) == 0) {
+        set_error("lanczos_shift: kernel width N=%d unsupported (odd, <= %d)", ntaps, MAX_TAPS);
+        return -1;
+    }
+    if (p < 0 || p >= H || p >= W) {
+        set_error("lanczos_shift: reflect padding p=%d must be smaller than the image (%d x %d)", p, H, W);
+        return -1;
+    }
+    if (a <= 0) {
+        set_error("lanczos_shift: a must be positive");
+        return -1;
+    }
+    const long long planes = static_cast<long long>(nb) * c;
+    if (planes <= 0 || planes > 65535) {
+        set_error("lanczos_shift: %lld planes outside [1, 65535]", planes);
+        return -1;
+    }
+    const int half = ntaps / 2;
+    const size_t smem = (static_cast<size_t>(LZ_TH + 2 * half) + LZ_TH) * (LZ_TW + 2 * half) * sizeof(float);
+    dim3 grid((W + LZ_TW - 1) / LZ_TW, (H + LZ_TH - 1) / LZ_TH, static_cast<unsigned>(planes));
+    lanczos_shift_kernel<<<grid, LZ_THREADS, smem, s>>>(img, shift, c, H, W, p, a, ntaps, out);
+    note_launches(1);
+    HRN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int lanczos_taps_launch(const float* d, int n, int a, int ntaps, float* out, cudaStream_t s) {
+    if (ntaps < 1 || ntaps > MAX_TAPS || (ntaps & 1) == 0 || a <= 0 || n <= 0) {
+        set_error("lanczos_taps: need n > 0, a > 0 and odd N <= %d (got n=%d a=%d N=%d)", MAX_TAPS, n, a, ntaps);
+        return -1;
+    }
+    lanczos_taps_kernel<<<(n + 127) / 128, 128, 0, s>>>(d, n, a, ntaps, out);
+    note_launches(1);
+    HRN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int shift_cpsnr_launch(const float* sr, const float* hr, const float* hm, int B, int H, int W, int border,
+                       int clip_sr, float* best_db, int32_t* best_site, float* site_db, cudaStream_t s) {
+    if (H != W) {
+        set_error("shift_cpsnr: square images only (got %d x %d), like Evaluator.py:64", H, W);
+        return -1;
+    }
+    if (border < 0 || 2 * border + 1 > CP_MAXS || W - 2 * border <= 0) {
+        set_error("shift_cpsnr: border_w=%d unsupported for %d x %d (0 <= border_w <= 3)", border, H, W);
+        return -1;
+    }
+    if (B <= 0 || B > 65535) {
+        set_error("shift_cpsnr: batch %d outside [1, 65535]", B);
+        return -1;
+    }
+    CpGeom g;
+    g.H = H;
+    g.W = W;
+    g.border = border;
+    g.S = 2 * border + 1;
+    g.size = W - 2 * border;
+    g.col_blocks = (g.size + CP_COLS - 1) / CP_COLS;
+    g.band_rows = (g.size + CP_BANDS - 1) / CP_BANDS;
+    const int bands = (g.size + g.band_rows - 1) / g.band_rows;
+    g.blocks_per_set = bands * g.col_blocks;
+    const int sites = g.S * g.S;
+    const size_t partial_bytes = static_cast<size_t>(B) * g.blocks_per_set * sites * 2 * sizeof(double);
+    const size_t nclear_bytes = static_cast<size_t>(B) * sites * sizeof(double);
+    const size_t bias_bytes = static_cast<size_t>(B) * sites * sizeof(float);
+    uint8_t* ws = nullptr;
+    HRN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&ws), partial_bytes + nclear_bytes + bias_bytes, s));
+    double* partial = reinterpret_cast<double*>(ws);
+    double* nclear = reinterpret_cast<double*>(ws + partial_bytes);
+    float* bias = reinterpret_cast<float*>(ws + partial_bytes + nclear_bytes);
+    dim3 grid(g.blocks_per_set, B), block(CP_COLS, g.S);
+    cpsnr_pass_kernel<1><<<grid, block, 0, s>>>(sr, hr, hm, g, clip_sr, nullptr, partial);
+    cpsnr_finalize_kernel<1><<<B, 64, 0, s>>>(partial, g, bias, nclear, nullptr, nullptr, nullptr);
+    cpsnr_pass_kernel<2><<<grid, block, 0, s>>>(sr, hr, hm, g, clip_sr, bias, partial);
+    cpsnr_finalize_kernel<2><<<B, 64, 0, s>>>(partial, g, bias, nclear, best_db, best_site, site_db);
+    note_launches(4);
+    HRN_CUDA_OK(cudaGetLastError());
+    HRN_CUDA_OK(cudaFreeAsync(ws, s));
+    return 0;
+}
+
+}  // namespace hrn

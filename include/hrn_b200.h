@@ -1,0 +1,117 @@
+/* hrn_b200 -- C ABI of the B200-native HighRes-net inference + scoring path.
+ *
+ * The reference (gwall-ceres/HighRes-net) has no FFI: its boundary is the Python
+ * module API.  Each entry point below names the reference interface it replaces;
+ * INTEGRATION.md shows the ctypes binding a maintainer would add on the reference
+ * side.  Conventions: plain pointers and sizes only, status-code returns (0 = ok,
+ * non-zero = error, message via hrn_last_error()), no exceptions across the ABI,
+ * caller-owned buffers, handle-owned weights and workspace, all work enqueued on
+ * the CUDA stream passed in (a cudaStream_t cast to void*; NULL = default stream).
+ * One handle per device; a handle is not thread-safe.  There is NO CPU fallback:
+ * every function fails with an error if no sm_100 device is usable.
+ */
+#ifndef HRN_B200_H
+#define HRN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HRN_ABI_VERSION 1
+
+typedef struct hrn_handle hrn_handle;
+
+/* Mirrors config/config.json:9-35 ("network") of the reference.  The kernels are
+ * specialised for the shipped values; anything else is rejected by hrn_create. */
+typedef struct hrn_config {
+    int32_t enc_in_channels;   /* network.encoder.in_channels     (2)  */
+    int32_t enc_num_layers;    /* network.encoder.num_layers      (2)  residual blocks */
+    int32_t enc_kernel_size;   /* network.encoder.kernel_size     (3)  */
+    int32_t enc_channels;      /* network.encoder.channel_size    (64) */
+    int32_t rec_alpha_residual;/* network.recursive.alpha_residual (1) */
+    int32_t rec_in_channels;   /* network.recursive.in_channels   (64) */
+    int32_t rec_kernel_size;   /* network.recursive.kernel_size   (3)  */
+    int32_t dec_in_channels;   /* network.decoder.deconv.in_channels  (64) */
+    int32_t dec_kernel_size;   /* network.decoder.deconv.kernel_size  (3)  */
+    int32_t dec_stride;        /* network.decoder.deconv.stride       (3)  */
+    int32_t dec_out_channels;  /* network.decoder.deconv.out_channels (64) */
+    int32_t fin_in_channels;   /* network.decoder.final.in_channels   (64) */
+    int32_t fin_kernel_size;   /* network.decoder.final.kernel_size   (1)  */
+    int32_t fin_out_channels;  /* network.decoder.final.out_channels  (1)  */
+} hrn_config;
+
+/* ABI version of the loaded library (== HRN_ABI_VERSION of the header it was built from). */
+int32_t hrn_abi_version(void);
+
+/* Last error message of the calling thread ("" if none). */
+const char* hrn_last_error(void);
+
+/* Replaces HRNet.__init__ (src/DeepNetworks/HRNet.py:175-184) + .to(device).
+ * Creates a handle on CUDA device `device`; fails unless it is compute capability 10.x. */
+int32_t hrn_create(const hrn_config* cfg, int32_t device, hrn_handle** out);
+void hrn_destroy(hrn_handle* h);
+
+/* Replaces load_state_dict (predict.py:98-99): upload one tensor by its reference
+ * state_dict key (e.g. "fuse.fuse.0.block.2.weight").  `data` is
+ * HOST fp32 in the reference layout (Conv2d OIHW, ConvTranspose2d (in, out, kH, kW),
+ * PReLU (1,)); the handle repacks it (bf16, pre-swizzled UMMA B-operand images). */
+int32_t hrn_set_weight(hrn_handle* h, const char* key, const float* data, const int64_t* shape, int32_t ndim);
+/* Number of the 31 expected tensors still missing (0 = ready to run). */
+int32_t hrn_missing_weights(const hrn_handle* h);
+
+/* Replaces HRNet.forward (HRNet.py:186-211).  DEVICE pointers:
+ *   lrs (B, L, H, W) fp32 contiguous, alphas (B, L) fp32, sr (B, 1, 3H, 3W) fp32 out.
+ * Square inputs only (H == W), as the reference's view() at HRNet.py:204 requires. */
+int32_t hrn_forward(hrn_handle* h, const float* lrs, const float* alphas, int32_t B, int32_t L, int32_t H,
+                    int32_t W, float* sr, void* stream);
+
+/* Same with HOST buffers (the train.py:200-208 / predict.py:36-40 pattern: H2D of
+ * lrs/alphas, forward, D2H of sr), synchronous.  Pinned host memory is used as is. */
+int32_t hrn_forward_host(hrn_handle* h, const float* lrs_host, const float* alphas_host, int32_t B, int32_t L,
+                         int32_t H, int32_t W, float* sr_host, void* stream);
+
+/* Replaces lanczos.lanczos_shift (src/lanczos.py:47-107) incl. lanczos_kernel (5-43).
+ * DEVICE pointers: img (Nb, C, H, W) fp32, shift (C, 2) = (dy, dx) per channel, out like img.
+ * p = reflect padding width, a = lobes, ntaps = N (odd). */
+int32_t hrn_lanczos_shift(const float* img, const float* shift, int32_t Nb, int32_t C, int32_t H, int32_t W,
+                          int32_t p, int32_t a, int32_t ntaps, float* out, void* stream);
+
+/* Replaces lanczos.lanczos_kernel (src/lanczos.py:5-43).  DEVICE pointers: d (n) fp32 shifts ->
+ * taps (n, ntaps) fp32, normalised; a = lobes, ntaps = N (odd). */
+int32_t hrn_lanczos_taps(const float* d, int32_t n, int32_t a, int32_t ntaps, float* taps, void* stream);
+
+/* Replaces Evaluator.shift_cPSNR (src/Evaluator.py:52-73, cPSNR 11-43) for a batch.
+ * DEVICE pointers: sr, hr, hr_map (B, H, W) fp32 (H == W); best_db (B) fp32 = max cPSNR,
+ * best_site (B) int32 = argmax over itertools.product(range(S), range(S)) with S = 2*border_w+1
+ * (site = x*S + y, x = row offset), site_db (B, S*S) fp32 or NULL.  clip_sr != 0 fuses the
+ * np.clip(sr, 0, 1) of the call sites (train.py:212, predict.py:43). */
+int32_t hrn_shift_cpsnr(const float* sr, const float* hr, const float* hr_map, int32_t B, int32_t H, int32_t W,
+                        int32_t border_w, int32_t clip_sr, float* best_db, int32_t* best_site, float* site_db,
+                        void* stream);
+
+/* ---- test / profiling hooks (not part of the reference surface) ---- */
+
+/* Stage identifiers for hrn_forward_dump. */
+#define HRN_STAGE_ANCHOR 1            /* (B, 1, H, W)  median anchor                       */
+#define HRN_STAGE_ENC(i) (0x100 + (i))/* (B*L, 64, H, W) after encoder conv i (0 = init, .. last = encoder out) */
+#define HRN_STAGE_FUSE(level, j) (0x200 + 4 * (level) + (j))
+                                      /* j = 0: (B*half, 128, H, W) after block conv 1; 1: after the residual block;
+                                         2: (B*half, 64, H, W) merged views of the next level */
+/* Runs the forward like hrn_forward and additionally copies the named intermediate,
+ * converted to fp32 NCHW, into `dump` (device, caller-sized).  Returns -1 if the stage does not exist. */
+int32_t hrn_forward_dump(hrn_handle* h, const float* lrs, const float* alphas, int32_t B, int32_t L, int32_t H,
+                         int32_t W, float* sr, int32_t stage, float* dump, void* stream);
+
+/* Bring-up knob for the tcgen05 shared-memory descriptors: 0 = matrix base offset 0 (default),
+ * 1 = base offset (start_address >> 7) & 7. */
+int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value);
+
+/* Number of kernels launched by this library (all handles) since load; bench.py reports the delta. */
+int64_t hrn_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HRN_B200_H */
