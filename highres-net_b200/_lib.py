@@ -38,6 +38,8 @@ SYMBOLS = {
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
     "hrn_forward_dump": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                    c_int32, c_void_p, c_void_p]),
+    "hrn_profile_begin": (c_int32, [c_void_p]),
+    "hrn_profile_end": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "hrn_debug_set": (c_int32, [c_void_p, c_char_p, c_int32]),
     "hrn_kernel_launch_count": (c_int64, []),
 }

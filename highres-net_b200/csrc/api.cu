@@ -55,6 +55,10 @@ struct hrn_handle {
     float* io[3] = {nullptr, nullptr, nullptr};   // device staging for hrn_forward_host: lrs, alphas, sr
     int bo_mode = 0;
     int strip_h = 0;                   // 0 = automatic
+    // optional per-launch timing (hrn_profile_begin / hrn_profile_end)
+    bool profiling = false;
+    struct Span { cudaEvent_t e0, e1; int cls; double flops; };
+    std::vector<Span> spans;
 };
 
 namespace {
@@ -128,7 +132,30 @@ int maybe_dump(Dump* d, int stage, const __nv_bfloat16* t, int n, int H, int W, 
     return hrn::nhwc_bf16_to_nchw_f32_launch(t, n, H, W, C, d->dst, s);
 }
 
+// Brackets one kernel launch with CUDA events on its own stream when profiling is on.
+struct SpanGuard {
+    hrn_handle* h;
+    cudaStream_t s;
+    hrn_handle::Span sp{};
+    bool on;
+    SpanGuard(hrn_handle* h_, cudaStream_t s_, int cls, double flops) : h(h_), s(s_), on(h_->profiling) {
+        if (!on) return;
+        sp.cls = cls;
+        sp.flops = flops;
+        cudaEventCreate(&sp.e0);
+        cudaEventCreate(&sp.e1);
+        cudaEventRecord(sp.e0, s);
+    }
+    ~SpanGuard() {
+        if (!on) return;
+        cudaEventRecord(sp.e1, s);
+        h->spans.push_back(sp);
+    }
+};
+
 int run_conv(hrn_handle* h, const hrn::ConvLayer& l, hrn::ConvArgs a, cudaStream_t s) {
+    SpanGuard guard(h, s, l.cin == 64 ? HRN_PROF_CONV64 : HRN_PROF_CONV128,
+                    2.0 * 9.0 * l.cin * l.cout * static_cast<double>(a.n_img) * a.H * a.W);
     a.cin = l.cin;
     a.cout = l.cout;
     a.w_img = l.w_img;
@@ -175,13 +202,19 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
     if (grow(reinterpret_cast<void**>(&h->anchor), &h->anchor_cap, static_cast<size_t>(B) * hw * sizeof(float))) return -1;
 
     // ---- anchor + first conv (HRNet.py:200-204, 51-53)
-    if (hrn::median_anchor_launch(lrs, B, L, H, W, h->anchor, s)) return -1;
+    {
+        SpanGuard guard(h, s, HRN_PROF_MEDIAN, 0.0);
+        if (hrn::median_anchor_launch(lrs, B, L, H, W, h->anchor, s)) return -1;
+    }
     if (dump != nullptr && dump->stage == HRN_STAGE_ANCHOR) {
         HRN_CUDA_OK(cudaMemcpyAsync(dump->dst, h->anchor, static_cast<size_t>(B) * hw * sizeof(float),
                                     cudaMemcpyDeviceToDevice, s));
         dump->hit = true;
     }
-    if (hrn::conv_init_launch(lrs, h->anchor, B, L, H, W, h->w_init, h->b_init, h->prelu_init, h->act[0], s)) return -1;
+    {
+        SpanGuard guard(h, s, HRN_PROF_CONV_INIT, 2.0 * 18.0 * 64.0 * static_cast<double>(n_img) * hw);
+        if (hrn::conv_init_launch(lrs, h->anchor, B, L, H, W, h->w_init, h->b_init, h->prelu_init, h->act[0], s)) return -1;
+    }
     int stage = 0;
     if (maybe_dump(dump, HRN_STAGE_ENC(stage), h->act[0], static_cast<int>(n_img), H, W, 64, s)) return -1;
 
@@ -267,7 +300,10 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
     // torch.mean over the single remaining view (HRNet.py:134) is the identity: the loop always ends at n == 1.
 
     // ---- decoder (HRNet.py:147-156)
-    if (hrn::decoder_launch(h->act[cur], B, H, W, h->wd, h->bd, h->prelu_dec, h->wf, h->bf, sr, s)) return -1;
+    {
+        SpanGuard guard(h, s, HRN_PROF_DECODER, 74880.0 * static_cast<double>(B) * hw);
+        if (hrn::decoder_launch(h->act[cur], B, H, W, h->wd, h->bd, h->prelu_dec, h->wf, h->bf, sr, s)) return -1;
+    }
     if (dump != nullptr && !dump->hit) {
         set_error("hrn_forward_dump: stage 0x%x does not exist for L=%d", dump->stage, L);
         return -1;
@@ -497,6 +533,46 @@ int32_t hrn_shift_cpsnr(const float* sr, const float* hr, const float* hr_map, i
     }
     return hrn::shift_cpsnr_launch(sr, hr, hr_map, B, H, W, border_w, clip_sr, best_db, best_site, site_db,
                                    static_cast<cudaStream_t>(stream));
+}
+
+int32_t hrn_profile_begin(hrn_handle* h) {
+    if (h == nullptr) {
+        set_error("null handle");
+        return -1;
+    }
+    for (auto& sp : h->spans) {
+        cudaEventDestroy(sp.e0);
+        cudaEventDestroy(sp.e1);
+    }
+    h->spans.clear();
+    h->profiling = true;
+    return 0;
+}
+
+int32_t hrn_profile_end(hrn_handle* h, double* ms, double* flops, int64_t* launches) {
+    if (h == nullptr || ms == nullptr || flops == nullptr || launches == nullptr) {
+        set_error("hrn_profile_end: null argument");
+        return -1;
+    }
+    h->profiling = false;
+    HRN_CUDA_OK(cudaSetDevice(h->device));
+    HRN_CUDA_OK(cudaDeviceSynchronize());
+    for (int c = 0; c < HRN_PROF_CLASSES; ++c) {
+        ms[c] = 0.0;
+        flops[c] = 0.0;
+        launches[c] = 0;
+    }
+    for (auto& sp : h->spans) {
+        float t = 0.0f;
+        HRN_CUDA_OK(cudaEventElapsedTime(&t, sp.e0, sp.e1));
+        ms[sp.cls] += t;
+        flops[sp.cls] += sp.flops;
+        launches[sp.cls] += 1;
+        cudaEventDestroy(sp.e0);
+        cudaEventDestroy(sp.e1);
+    }
+    h->spans.clear();
+    return 0;
 }
 
 int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value) {

@@ -98,6 +98,20 @@ class HRNet(nn.Module):
         handle = self._handle_for(torch.device(device))
         _lib.check(_lib.load().hrn_debug_set(handle, knob.encode(), int(value)), "hrn_debug_set")
 
+    PROFILE_CLASSES = ("conv3x3_umma<64>", "conv3x3_umma<128>", "conv_init", "decoder", "median_anchor")
+
+    def profile_begin(self, device) -> None:
+        """Arm per-launch CUDA-event timing of the following forward calls (hrn_profile_begin)."""
+        _lib.check(_lib.load().hrn_profile_begin(self._handle_for(torch.device(device))), "hrn_profile_begin")
+
+    def profile_end(self, device) -> dict:
+        """-> {kernel class: {"ms": total, "flops": total algorithmic, "launches": n}} (hrn_profile_end)."""
+        n = len(self.PROFILE_CLASSES)
+        ms, fl, cnt = (ctypes.c_double * n)(), (ctypes.c_double * n)(), (ctypes.c_int64 * n)()
+        _lib.check(_lib.load().hrn_profile_end(self._handle_for(torch.device(device)), ms, fl, cnt), "hrn_profile_end")
+        return {name: {"ms": ms[i], "flops": fl[i], "launches": int(cnt[i])}
+                for i, name in enumerate(self.PROFILE_CLASSES)}
+
     # ------------------------------------------------------------------ forward
     def _check_inputs(self, lrs, alphas):
         _lib.require_cuda_tensor(lrs, "lrs")

@@ -108,6 +108,19 @@ int32_t hrn_forward_dump(hrn_handle* h, const float* lrs, const float* alphas, i
  * 1 = base offset (start_address >> 7) & 7. */
 int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value);
 
+/* Per-launch device timing of HRNet.forward, by kernel class, with CUDA events recorded on the stream the
+ * kernels run on.  hrn_profile_begin arms it; every later hrn_forward* call records one event pair per launch;
+ * hrn_profile_end synchronises the device and returns, per class, the summed milliseconds, the summed
+ * algorithmic FLOPs (MAC = 2) and the launch count (arrays of HRN_PROF_CLASSES entries), then disarms. */
+#define HRN_PROF_CONV64 0     /* tcgen05 conv 64 -> 64            */
+#define HRN_PROF_CONV128 1    /* tcgen05 conv 128 -> 128 / 64     */
+#define HRN_PROF_CONV_INIT 2  /* conv 2 -> 64 (+ PReLU)           */
+#define HRN_PROF_DECODER 3    /* deconv + PReLU + 1x1             */
+#define HRN_PROF_MEDIAN 4     /* median anchor                    */
+#define HRN_PROF_CLASSES 5
+int32_t hrn_profile_begin(hrn_handle* h);
+int32_t hrn_profile_end(hrn_handle* h, double* ms, double* flops, int64_t* launches);
+
 /* Number of kernels launched by this library (all handles) since load; bench.py reports the delta. */
 int64_t hrn_kernel_launch_count(void);
 
