@@ -1,0 +1,314 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every check goes through the
+C ABI (ctypes -> libhrn_b200.so) and compares against the CPU oracle and/or the golden
+fixtures minted from the unmodified reference.  Nothing here reads /root/reference.
+
+Gates (BASELINE.json north_star): SR max-abs <= 1e-2 vs the fp32 reference (bf16
+activations, fp32 tensor-core accumulation); cPSNR within 0.01 dB; best shift bit-exact;
+Lanczos <= 1e-5 max-abs (fp32 kernel).  Tighter regression gates sit beside them so a
+real bug cannot hide inside the loose north-star tolerance."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases, hrnet_oracle, scoring_oracle
+
+pytestmark = pytest.mark.gpu
+
+SR_GATE = 1e-2            # north star
+SR_REGRESSION_GATE = 1.5e-3
+LAYER_REL_GATE = 1.5e-2   # per-stage error relative to the stage's max magnitude (bf16 storage)
+CPSNR_GATE_DB = 0.01      # north star
+CPSNR_KERNEL_GATE_DB = 1e-4
+LANCZOS_GATE = 1e-5
+
+
+@pytest.fixture(scope="module")
+def hb():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device; there is no CPU fallback")
+    import highres_net_b200 as m
+    import os
+    assert os.path.exists(m.library_path()), "libhrn_b200.so missing"
+    return m
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def net(hb, dev):
+    model = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval()
+    model.load_state_dict(hrnet_oracle.make_params(cases.WEIGHT_SEED))
+    return model.to(dev)
+
+
+# ---------------------------------------------------------------------------- HRNet.forward
+@pytest.mark.parametrize("name", list(cases.HRNET_CASES))
+def test_hrnet_forward_matches_reference_golden(hb, net, dev, golden, name):
+    lrs, alphas = cases.hrnet_inputs(name)
+    before = hb.kernel_launch_count()
+    sr = net(torch.from_numpy(lrs).to(dev), torch.from_numpy(alphas).to(dev))
+    assert hb.kernel_launch_count() > before, "forward did not launch any native kernel"
+    ref = golden["hrnet_forward"][name]
+    assert sr.dtype == torch.float32 and tuple(sr.shape) == ref.shape and sr.device.type == "cuda"
+    err = np.abs(sr.cpu().numpy() - ref).max()
+    assert err <= SR_GATE
+    assert err <= SR_REGRESSION_GATE, err
+
+
+@pytest.mark.parametrize("name", ["b2_l4_s32", "b2_l9_s16", "b1_l16_s16", "b1_l5_s24"])
+def test_hrnet_stages_match_oracle(net, dev, name):
+    from highres_net_b200 import hrnet as hm
+    params = hrnet_oracle.make_params(cases.WEIGHT_SEED)
+    lrs, alphas = cases.hrnet_inputs(name)
+    b, l, s, _ = lrs.shape
+    tr = {}
+    hrnet_oracle.hrnet_forward(params, lrs, alphas, trace=tr)
+    tl, ta = torch.from_numpy(lrs).to(dev), torch.from_numpy(alphas).to(dev)
+    _, anchor = net.forward_stage(tl, ta, hm.stage_anchor(), (b, 1, s, s))
+    assert torch.equal(anchor.cpu()[:, 0], tr["anchor"])                 # lower median: exact selection
+    _, enc = net.forward_stage(tl, ta, hm.stage_enc(5), (b * l, 64, s, s))
+    ref = tr["encoded"].reshape(b * l, 64, s, s)
+    assert (enc.cpu() - ref).abs().max() <= LAYER_REL_GATE * ref.abs().max()
+    n, level = l, 0
+    while n // 2 > 0:
+        half = n // 2
+        _, lv = net.forward_stage(tl, ta, hm.stage_fuse(level, 2), (b * half, 64, s, s))
+        ref = tr["levels"][level].reshape(b * half, 64, s, s)
+        assert (lv.cpu() - ref).abs().max() <= LAYER_REL_GATE * ref.abs().max(), (name, level)
+        n, level = half, level + 1
+
+
+def _conv_layer_ref(x, w, b, slope):
+    import torch.nn.functional as F
+    y = F.conv2d(x, w.to(torch.bfloat16).to(torch.float32), b, padding=1)
+    return F.prelu(y, slope)
+
+
+@pytest.mark.parametrize("taps", [[(1, 0)], [(1, 2)], [(0, 1), (2, 2)], None])
+def test_conv64_single_taps(hb, dev, taps):
+    """tcgen05 conv in isolation: keep only some of the 9 taps (each tap = one shifted smem descriptor)."""
+    from highres_net_b200 import hrnet as hm
+    params = dict(hrnet_oracle.make_params(0))
+    key = "encode.res_layers.0.block.0"
+    w = params[key + ".weight"].clone()
+    if taps is not None:
+        mask = torch.zeros(3, 3)
+        for ky, kx in taps:
+            mask[ky, kx] = 1
+        w = w * mask
+    params[key + ".weight"] = w
+    model = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval()
+    model.load_state_dict(params)
+    model = model.to(dev)
+    s = 40
+    lrs = torch.from_numpy(np.random.RandomState(7).rand(2, 1, s, s).astype(np.float32)).to(dev)
+    al = torch.ones(2, 1, device=dev)
+    _, x0 = model.forward_stage(lrs, al, hm.stage_enc(0), (2, 64, s, s))
+    _, y1 = model.forward_stage(lrs, al, hm.stage_enc(1), (2, 64, s, s))
+    ref = _conv_layer_ref(x0.cpu(), w, params[key + ".bias"], params["encode.res_layers.0.block.1.weight"])
+    # same bf16 inputs and weights on both sides: only accumulation order and the bf16 store differ
+    assert (y1.cpu() - ref).abs().max() <= 4e-3 * max(1.0, float(ref.abs().max()))
+
+
+def test_alpha_zero_views_are_skipped(net, dev):
+    """utils.py:89-95 contract: a padded view (alpha = 0) must not change the fused state (HRNet.py:123-128)."""
+    rng = np.random.RandomState(3)
+    lrs = rng.rand(1, 4, 32, 32).astype(np.float32)
+    lrs[:, 2:] = 0.0
+    alphas = np.array([[1, 1, 0, 0]], dtype=np.float32)
+    params = hrnet_oracle.make_params(cases.WEIGHT_SEED)
+    sr = net(torch.from_numpy(lrs).to(dev), torch.from_numpy(alphas).to(dev)).cpu().numpy()
+    ref = hrnet_oracle.hrnet_forward(params, lrs, alphas).numpy()
+    assert np.abs(sr - ref).max() <= SR_REGRESSION_GATE
+    alphas_on = np.ones_like(alphas)
+    sr_on = net(torch.from_numpy(lrs).to(dev), torch.from_numpy(alphas_on).to(dev)).cpu().numpy()
+    assert np.abs(sr_on - sr).max() > 1e-4         # the alpha mask really is consulted
+
+
+def test_full_size_properties_c2(net, dev):
+    """BASELINE.json configs[1] size (B32 L16 128x128): size-independent properties.
+    Imagesets are independent => each batch row equals the same imageset run alone (bit-exact:
+    the kernels are deterministic), a batch permutation permutes the output, and one row is
+    checked against the oracle."""
+    g = torch.Generator().manual_seed(5)
+    lrs = torch.rand(32, 16, 128, 128, generator=g)
+    alphas = torch.ones(32, 16)
+    alphas[3, 11:] = 0
+    lrs[3, 11:] = 0
+    tl, ta = lrs.to(dev), alphas.to(dev)
+    sr = net(tl, ta)
+    assert tuple(sr.shape) == (32, 1, 384, 384) and torch.isfinite(sr).all()
+    for i in (0, 3, 31):
+        alone = net(tl[i:i + 1], ta[i:i + 1])
+        assert torch.equal(alone[0], sr[i])
+    perm = torch.randperm(32, generator=g)
+    sr_p = net(tl[perm.to(dev)], ta[perm.to(dev)])
+    assert torch.equal(sr_p, sr[perm.to(dev)])
+    again = net(tl, ta)
+    assert torch.equal(again, sr)                                        # run-to-run determinism
+    params = hrnet_oracle.make_params(cases.WEIGHT_SEED)
+    ref = hrnet_oracle.hrnet_forward(params, lrs[3:4].numpy(), alphas[3:4].numpy()).numpy()
+    err = np.abs(sr[3:4].cpu().numpy() - ref).max()
+    assert err <= SR_GATE and err <= SR_REGRESSION_GATE, err
+
+
+def test_forward_host_equals_device_path(net, dev):
+    lrs, alphas = cases.hrnet_inputs("b2_l4_s32")
+    a = net(torch.from_numpy(lrs).to(dev), torch.from_numpy(alphas).to(dev)).cpu()
+    b = net.forward_host(torch.from_numpy(lrs).pin_memory(), torch.from_numpy(alphas).pin_memory(), device=dev)
+    assert torch.equal(a, b)
+
+
+def test_forward_rejects_bad_inputs(hb, net, dev):
+    with pytest.raises(RuntimeError):
+        net(torch.rand(1, 2, 16, 16), torch.ones(1, 2))                  # CPU tensors: no fallback
+    with pytest.raises(ValueError):
+        net(torch.rand(1, 2, 16, 24, device=dev), torch.ones(1, 2, device=dev))   # non-square (HRNet.py:204)
+    fresh = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).to(dev)
+    with pytest.raises(RuntimeError):
+        fresh(torch.rand(1, 2, 16, 16, device=dev), torch.ones(1, 2, device=dev))  # train mode + grad: unsupported
+    with torch.no_grad():
+        out = fresh(torch.rand(1, 2, 16, 16, device=dev), torch.ones(1, 2, device=dev))
+    assert tuple(out.shape) == (1, 1, 48, 48)
+
+
+def test_state_dict_roundtrip_changes_output(hb, dev):
+    """load_state_dict (predict.py:98-99) must reach the device copy of the weights."""
+    model = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval().to(dev)
+    x, a = torch.rand(1, 2, 16, 16, device=dev), torch.ones(1, 2, device=dev)
+    y0 = model(x, a)
+    model.load_state_dict(hrnet_oracle.make_params(123))
+    y1 = model(x, a)
+    ref = hrnet_oracle.hrnet_forward(hrnet_oracle.make_params(123), x.cpu().numpy(), a.cpu().numpy())
+    assert not torch.equal(y0, y1)
+    assert (y1.cpu() - ref).abs().max() <= SR_REGRESSION_GATE
+
+
+# ---------------------------------------------------------------------------- Lanczos
+def test_lanczos_taps_known_answers(hb, dev, golden):
+    d = torch.tensor(cases.LANCZOS_TAP_SHIFTS, dtype=torch.float32, device=dev).view(-1, 1)
+    taps = hb.lanczos_kernel(d, a=3, N=7).cpu().numpy()
+    assert np.abs(taps - golden["lanczos"]["taps"]).max() <= 5e-7
+    assert np.allclose(taps.sum(1), 1.0, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", list(cases.LANCZOS_CASES))
+def test_lanczos_shift_matches_reference_golden(hb, dev, golden, name):
+    img, shift, p = cases.lanczos_inputs(name)
+    out = hb.lanczos_shift(torch.from_numpy(img).to(dev), torch.from_numpy(shift).to(dev), p=p, a=3, N=7)
+    assert tuple(out.shape) == img.shape
+    out = out.cpu().numpy()
+    assert np.abs(out - golden["lanczos"][name]).max() <= LANCZOS_GATE
+    assert np.abs(out - scoring_oracle.lanczos_shift(img, shift, p=p)).max() <= LANCZOS_GATE
+
+
+def test_lanczos_properties_full_size(hb, dev):
+    """384x384 SR size: linearity, and an integer shift is a plain translation away from the border."""
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(1, 32, 384, 384, generator=g).to(dev)
+    y = torch.rand(1, 32, 384, 384, generator=g).to(dev)
+    shift = (torch.rand(32, 2, generator=g) * 2 - 1).to(dev)
+    lin = hb.lanczos_shift(2.0 * x - 0.5 * y, shift, p=5)
+    sep = 2.0 * hb.lanczos_shift(x, shift, p=5) - 0.5 * hb.lanczos_shift(y, shift, p=5)
+    assert (lin - sep).abs().max() <= 1e-5
+    ones = torch.ones(32, 2, device=dev)
+    moved = hb.lanczos_shift(x, ones, p=5)                    # d = +1 samples the image at y+1, x+1
+    assert (moved[..., 4:-4, 4:-4] - x[..., 5:-3, 5:-3]).abs().max() <= 1e-5
+
+
+def test_lanczos_rejects_bad_arguments(hb, dev):
+    img = torch.rand(1, 2, 8, 8, device=dev)
+    with pytest.raises(RuntimeError):
+        hb.lanczos_shift(img, torch.zeros(2, 2, device=dev), p=8)        # ReflectionPad2d needs p < size
+    with pytest.raises(RuntimeError):
+        hb.lanczos_shift(img, torch.zeros(2, 2, device=dev), N=6)        # even kernel width
+    with pytest.raises(RuntimeError):
+        hb.lanczos_shift(img.cpu(), torch.zeros(2, 2))
+
+
+# ---------------------------------------------------------------------------- cPSNR shift search
+@pytest.mark.parametrize("name", list(cases.CPSNR_CASES))
+def test_shift_cpsnr_matches_reference_golden(hb, golden, name):
+    sr, hr, hm = cases.cpsnr_inputs(name)
+    g = golden["cpsnr"]
+    best, xy, table = hb.shift_cPSNR_argmax(sr, hr, hm, border_w=3)
+    assert best.dtype == np.float32 and best.shape == (sr.shape[0],)
+    ref_max, ref_arg, ref_sites = g[name + "__max"], g[name + "__argmax"], g[name + "__sites"]
+    assert np.array_equal(xy[:, 0] * 7 + xy[:, 1], ref_arg)                       # best shift: bit-exact
+    assert np.array_equal(np.isnan(table), np.isnan(ref_sites))
+    assert np.array_equal(np.isposinf(table), np.isposinf(ref_sites))
+    fin = np.isfinite(ref_sites)
+    assert np.abs(table[fin] - ref_sites[fin]).max(initial=0.0) <= CPSNR_KERNEL_GATE_DB
+    finm = np.isfinite(ref_max)
+    assert np.abs(best[finm] - ref_max[finm]).max(initial=0.0) <= CPSNR_KERNEL_GATE_DB
+    assert np.array_equal(np.isnan(best), np.isnan(ref_max)) and np.array_equal(np.isposinf(best), np.isposinf(ref_max))
+    # 2-D call signature of the reference (Evaluator.py:21-24): scalar out
+    with np.errstate(all="ignore"):
+        one = hb.shift_cPSNR(sr[0], hr[0], hm[0])
+    assert np.ndim(one) == 0
+    if np.isfinite(ref_max[0]):
+        assert abs(one - ref_max[0]) <= CPSNR_KERNEL_GATE_DB
+
+
+def test_cpsnr_plain_and_uint16(hb):
+    rng = np.random.RandomState(21)
+    sr, hr = rng.rand(2, 50, 50).astype(np.float32), rng.rand(2, 50, 50).astype(np.float32)
+    hm = (rng.rand(2, 50, 50) > 0.2).astype(np.float32)
+    assert np.abs(hb.cPSNR(sr, hr, hm) - scoring_oracle.cpsnr(sr, hr, hm)).max() <= CPSNR_KERNEL_GATE_DB
+    sr16, hr16 = (sr * 65535).astype(np.uint16), (hr * 65535).astype(np.uint16)
+    assert np.abs(hb.cPSNR(sr16, hr16, hm) - scoring_oracle.cpsnr(sr16, hr16, hm)).max() <= CPSNR_KERNEL_GATE_DB
+    with pytest.raises(AssertionError):
+        hb.cPSNR(sr + 1.0, hr, hm)                                              # Evaluator.py:30
+
+
+def test_shift_cpsnr_known_shift_full_size(hb, dev):
+    """384x384, batch 32 on device: hr = roll(sr, (ry, rx)) -> best site (3+ry, 3+rx), cMSE = 0 -> +inf."""
+    g = torch.Generator().manual_seed(4)
+    sr = torch.rand(32, 384, 384, generator=g)
+    shifts = torch.randint(-3, 4, (32, 2), generator=g)
+    hr = torch.stack([torch.roll(sr[i], (int(shifts[i, 0]), int(shifts[i, 1])), (0, 1)) for i in range(32)])
+    hm = (torch.rand(32, 384, 384, generator=g) > 0.1).float()
+    best, xy, _ = hb.shift_cPSNR_argmax(sr.to(dev), hr.to(dev), hm.to(dev))
+    assert best.is_cuda and torch.isinf(best).all()
+    assert torch.equal(xy.cpu().long(), shifts + 3)
+
+
+def test_shift_cpsnr_rejects_bad_arguments(hb, dev):
+    sr = torch.rand(1, 20, 24, device=dev)
+    with pytest.raises(RuntimeError):
+        hb.shift_cPSNR(sr, sr, sr)                                              # non-square
+    sq = torch.rand(1, 20, 20, device=dev)
+    with pytest.raises(RuntimeError):
+        hb.shift_cPSNR(sq, sq, sq, border_w=4)                                  # more than 7x7 shifts
+
+
+# ---------------------------------------------------------------------------- the composite path (C4)
+def test_full_scoring_path_against_oracle(hb, net, dev):
+    """HRNet -> lanczos_shift -> clip -> shift_cPSNR on 16-view imagesets (BASELINE configs[3], reduced batch).
+    HR is built from the ORACLE's fp32 SR (roll + bias + sigma = 0.01 noise) so the best
+    shift is known and well separated; end-to-end gate: cPSNR within 0.01 dB, identical argmax."""
+    b, l, s = 3, 16, 64
+    rng = np.random.RandomState(17)
+    lrs = rng.rand(b, l, s, s).astype(np.float32)
+    alphas = np.ones((b, l), dtype=np.float32)
+    params = hrnet_oracle.make_params(cases.WEIGHT_SEED)
+    sr_ref = hrnet_oracle.hrnet_forward(params, lrs, alphas).numpy()[:, 0]
+    shift = rng.uniform(-1, 1, size=(b, 2)).astype(np.float32)
+    moved_ref = np.clip(scoring_oracle.lanczos_shift(sr_ref[None], shift, p=5)[0], 0, 1)
+    rolls = rng.randint(-3, 4, size=(b, 2))
+    hr = np.stack([np.roll(moved_ref[i], tuple(rolls[i]), (0, 1)) for i in range(b)])
+    hr = np.clip(hr + 0.02 + 0.01 * rng.randn(*hr.shape), 0, 1).astype(np.float32)
+    hm = (rng.rand(*hr.shape) > 0.1).astype(np.float32)
+    ref_scores = [scoring_oracle.shift_cpsnr(moved_ref[i], hr[i], hm[i]) for i in range(b)]
+
+    sr = net(torch.from_numpy(lrs).to(dev), torch.from_numpy(alphas).to(dev))[:, 0]          # (B, 3s, 3s)
+    moved = hb.lanczos_shift(sr[None], torch.from_numpy(shift).to(dev), p=5, a=3, N=7)[0]    # ShiftNet.py:87-89 layout
+    best, xy, _ = hb.shift_cPSNR_argmax(moved, torch.from_numpy(hr).to(dev), torch.from_numpy(hm).to(dev),
+                                        clip_sr=True)
+    best, xy = best.cpu().numpy(), xy.cpu().numpy()
+    for i in range(b):
+        assert abs(best[i] - ref_scores[i][0]) <= CPSNR_GATE_DB
+        assert xy[i, 0] * 7 + xy[i, 1] == ref_scores[i][1] == (3 + rolls[i, 0]) * 7 + (3 + rolls[i, 1])
