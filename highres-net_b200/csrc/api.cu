@@ -53,8 +53,7 @@ struct hrn_handle {
     float* anchor = nullptr;
     size_t io_cap[3] = {0, 0, 0};
     float* io[3] = {nullptr, nullptr, nullptr};   // device staging for hrn_forward_host: lrs, alphas, sr
-    int bo_mode = 0;
-    int strip_h = 0;                   // 0 = automatic
+    int max_ctas = 0;                  // 0 = one CTA per SM (test knob)
     // optional per-launch timing (hrn_profile_begin / hrn_profile_end)
     bool profiling = false;
     struct Span { cudaEvent_t e0, e1; int cls; double flops; };
@@ -162,8 +161,7 @@ int run_conv(hrn_handle* h, const hrn::ConvLayer& l, hrn::ConvArgs a, cudaStream
     a.bias = l.bias;
     a.prelu = l.prelu;
     a.has_prelu = l.has_prelu ? 1 : 0;
-    a.desc_base_offset_mode = h->bo_mode;
-    a.strip_h = h->strip_h;
+    a.max_ctas = h->max_ctas;
     return hrn::conv3x3_launch(a, h->sm_count, s);
 }
 
@@ -580,8 +578,7 @@ int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value) {
         set_error("hrn_debug_set: null argument");
         return -1;
     }
-    if (strcmp(knob, "desc_base_offset_mode") == 0) h->bo_mode = value;
-    else if (strcmp(knob, "strip_h") == 0) h->strip_h = value;
+    if (strcmp(knob, "max_ctas") == 0) h->max_ctas = value;
     else {
         set_error("hrn_debug_set: unknown knob '%s'", knob);
         return -1;

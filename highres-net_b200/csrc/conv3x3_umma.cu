@@ -8,19 +8,26 @@
 // the A operand come from two different views) and the alpha-masked merge
 // `alice + alpha_bob * x` (HRNet.py:123-128).
 //
-// Mapping.  One UMMA tile = 128 consecutive output pixels of one image row (M)
-// x N_TILE output channels (N), K = 9 taps x CIN.  Per tap the A operand is the
-// SAME shared-memory row buffer read through a descriptor whose start address is
-// shifted by (kx) pixels = kx * 128 B; ky selects one of three resident input
-// rows.  Each CTA walks a vertical strip of rows, so an input row is fetched by
-// TMA once (130 pixels: 128 + halo, out-of-bounds pixels zero-filled by TMA = the
-// conv padding) and reused by the three output rows that touch it.  The weight
-// slice of the CTA (9 x CIN x N_TILE bf16, 72 KB) stays resident in smem.
+// Mapping ("row-stationary, ky-stacked").  A = 128 consecutive pixels of ONE input
+// row (M = 128, K = 64 channels per chunk), fetched once by TMA as 130 pixels
+// (halo; out-of-bounds pixels are zero-filled by TMA = the conv padding).  The
+// kx = 0,1,2 taps read the same smem buffer through descriptors whose start
+// address is shifted by kx pixels (kx * 128 B; SWIZZLE_128B is address based, so
+// the shifted view stays consistent with what TMA wrote).  Input row r feeds
+// output rows r+1, r, r-1 through taps ky = 0, 1, 2, so B stacks
+// [W(ky=2) | W(ky=1) | W(ky=0)] (3 x 64 output channels = N 192) and ONE MMA
+// updates the three accumulators of output rows r-1, r, r+1, which live in
+// adjacent 64-column TMEM slots.  Versus one MMA per (tap, output row) this
+// issues a third of the MMAs and reads a third of the A bytes from shared memory.
+// The CTA's weight slice (9 x CIN x 64 bf16) stays resident in smem; every input
+// row is consumed exactly once, so the A ring is a plain FIFO.
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one
-// thread), warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> registers ->
-// bias/PReLU/residual -> bf16 NHWC global).  TMEM holds ACC_STAGES accumulators
-// so the epilogue of tile t overlaps the MMAs of tiles t+1...
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one
+// elected thread), warp 2 = TMEM allocator, warps 4..11 = epilogue (TMEM ->
+// registers -> bias/PReLU/residual -> bf16 NHWC global).  TMEM holds 8
+// accumulator slots (all 512 columns), so epilogues overlap the MMAs of later rows.
+// Work is split evenly: each CTA (group) owns a contiguous range of the flattened
+// (image, column tile, row) space and walks it as per-image strips.
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -33,58 +40,77 @@ namespace {
 
 constexpr int TILE_M = 128;
 constexpr int SLOT_PIX = TILE_M + 2;
-constexpr int CHUNK_BYTES = 17408;   // 130 px * 128 B = 16640, rounded up to 1024 (keeps the SW128 phase)
-constexpr int NUM_THREADS = 256;
-constexpr int ACC_STAGES = 4;
+constexpr int CHUNK_BYTES = 17408;     // 130 px * 128 B = 16640, rounded up to 1024 (keeps the SW128 phase)
+constexpr int CHUNK_TX = SLOT_PIX * 128;
+constexpr int NT = 64;                 // output channels per CTA
+constexpr int ACC_SLOTS = 8;           // 8 x 64 fp32 columns = the whole TMEM
+constexpr int TMEM_COLS = ACC_SLOTS * NT;
+constexpr int EPI_WARPS = 8;
+constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;
+constexpr int BTILE_BYTES = 3 * NT * 128;   // one (kx, chunk) B tile: 192 rows x 64 bf16
+constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
 
 template <int CIN>
 struct Cfg {
-    static constexpr int CHUNKS = CIN / 64;                 // 64-channel (128-byte) K chunks per pixel
-    static constexpr int NT = (CIN == 64) ? 64 : 32;        // output channels per CTA (UMMA N)
-    static constexpr int RING = (CIN == 64) ? 8 : 4;        // resident input rows
-    static constexpr int SLOT_BYTES = CHUNKS * CHUNK_BYTES;
-    static constexpr int WTILE_BYTES = NT * 128;            // one (tap, chunk) B tile: NT rows x 64 bf16
-    static constexpr int W_BYTES = 9 * CHUNKS * WTILE_BYTES;
-    static constexpr int TMEM_COLS = ACC_STAGES * NT;
-    static constexpr int BAR_OFFSET = W_BYTES + RING * SLOT_BYTES;
-    static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;
+    static constexpr int CHUNKS = CIN / 64;
+    static constexpr int RING = (CIN == 64) ? 8 : 4;          // resident (input row, chunk) buffers
+    static constexpr int W_BYTES = 3 * CHUNKS * BTILE_BYTES;  // 73,728 or 147,456
+    static constexpr int BAR_OFFSET = W_BYTES + RING * CHUNK_BYTES;
+    static constexpr int BIAS_OFFSET = BAR_OFFSET + 512;
     static constexpr int SMEM_BYTES = BIAS_OFFSET + NT * 4 + 1024;
-    static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32 && TMEM_COLS <= 512, "TMEM columns");
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
 struct Geometry {
-    int n_parts, items_per_part, strips, x_tiles;
+    int n_parts;      // cout / 64
+    int groups;       // CTAs per part
+    int x_tiles;      // ceil(W / 128)
+    long long total_rows;   // n_img * x_tiles * H
 };
 
-struct Item {
+struct Strip {
     int m, xt, y0, rows;
 };
 
-__device__ __forceinline__ Item decode_item(int t, const ConvArgs& a, const Geometry& g) {
-    Item it;
-    it.xt = t % g.x_tiles;
-    const int s = (t / g.x_tiles) % g.strips;
-    it.m = t / (g.x_tiles * g.strips);
-    it.y0 = s * a.strip_h;
-    it.rows = min(a.strip_h, a.H - it.y0);
-    return it;
+// The range of flattened rows owned by CTA group gi, cut into per-image strips.
+struct StripWalker {
+    long long g, g_end;
+    int H, x_tiles;
+    __device__ StripWalker(const Geometry& geo, int gi, int H_) : H(H_), x_tiles(geo.x_tiles) {
+        g = geo.total_rows * gi / geo.groups;
+        g_end = geo.total_rows * (gi + 1) / geo.groups;
+    }
+    __device__ bool next(Strip& s) {
+        if (g >= g_end) return false;
+        const long long col = g / H;
+        s.y0 = static_cast<int>(g % H);
+        s.rows = static_cast<int>(min(static_cast<long long>(H - s.y0), g_end - g));
+        s.m = static_cast<int>(col / x_tiles);
+        s.xt = static_cast<int>(col % x_tiles);
+        g += s.rows;
+        return true;
+    }
+};
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t lo) {
+    return (static_cast<uint64_t>(DESC_HI) << 32) | lo;
 }
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return (saddr >> 4) | (1u << 16); }
 
 template <int CIN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a, const Geometry g) {
+conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a, const Geometry geo) {
     using C = Cfg<CIN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t w_s = base;
     const uint32_t ring_s = base + C::W_BYTES;
     const uint32_t bars = base + C::BAR_OFFSET;
-    const uint32_t bar_full = bars;                                  // [RING]
-    const uint32_t bar_empty = bars + 8 * C::RING;                   // [RING]
-    const uint32_t bar_tfull = bars + 16 * C::RING;                  // [ACC_STAGES]
-    const uint32_t bar_tempty = bar_tfull + 8 * ACC_STAGES;          // [ACC_STAGES]
-    const uint32_t bar_w = bar_tempty + 8 * ACC_STAGES;
+    const uint32_t bar_full = bars;                              // [RING]
+    const uint32_t bar_empty = bars + 8 * C::RING;               // [RING]
+    const uint32_t bar_tfull = bars + 16 * C::RING;              // [ACC_SLOTS]
+    const uint32_t bar_tempty = bar_tfull + 8 * ACC_SLOTS;       // [ACC_SLOTS]
+    const uint32_t bar_w = bar_tempty + 8 * ACC_SLOTS;
     const uint32_t tmem_slot = bar_w + 8;
     uint8_t* smem_gen = smem_raw + (base - ptx::smem_u32(smem_raw));
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
@@ -92,146 +118,186 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int part = blockIdx.x % g.n_parts;
-    const int first = blockIdx.x / g.n_parts;
-    const int step = gridDim.x / g.n_parts;
+    const int part = blockIdx.x % geo.n_parts;
+    const int group = blockIdx.x / geo.n_parts;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::RING; ++i) {
             ptx::mbar_init(bar_full + 8 * i, 1);
             ptx::mbar_init(bar_empty + 8 * i, 1);
         }
-        for (int i = 0; i < ACC_STAGES; ++i) {
+        for (int i = 0; i < ACC_SLOTS; ++i) {
             ptx::mbar_init(bar_tfull + 8 * i, 1);
-            ptx::mbar_init(bar_tempty + 8 * i, 4);   // one arrive per epilogue warp
+            ptx::mbar_init(bar_tempty + 8 * i, EPI_WARPS);   // one arrive per epilogue warp
         }
         ptx::mbar_init(bar_w, 1);
         ptx::fence_barrier_init();
         ptx::prefetch_tensormap(&in_map);
     }
-    if (warp == 2) ptx::tmem_alloc<C::TMEM_COLS>(tmem_slot);
-    if (threadIdx.x >= 128 && threadIdx.x < 128 + C::NT) bias_s[threadIdx.x - 128] = a.bias[part * C::NT + threadIdx.x - 128];
+    if (warp == 2) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
+    if (threadIdx.x >= 128 && threadIdx.x < 128 + NT) bias_s[threadIdx.x - 128] = a.bias[part * NT + threadIdx.x - 128];
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
 
     if (warp == 0) {
-        // ===================================================== TMA producer
-        if (lane == 0) {
+        // ===================================================== TMA producer (whole warp loops, one lane issues)
+        if (ptx::elect_one()) {
             ptx::mbar_expect_tx(bar_w, C::W_BYTES);
             const uint8_t* wsrc = a.w_img + static_cast<size_t>(part) * C::W_BYTES;
-            for (int off = 0; off < C::W_BYTES; off += C::WTILE_BYTES)
-                ptx::bulk_copy_g2s(w_s + off, wsrc + off, C::WTILE_BYTES, bar_w);
-            uint32_t it = 0;
-            for (int t = first; t < g.items_per_part; t += step) {
-                const Item w = decode_item(t, a, g);
-                int img[2], ch[2];
-                if (a.pair_mode) {
-                    const int b = w.m / a.half, i = w.m % a.half;
-                    img[0] = b * a.src_views + i;
-                    img[1] = b * a.src_views + (a.top - 1 - i);
-                    ch[0] = ch[1] = 0;
-                } else {
-                    img[0] = img[1] = w.m;
-                    ch[0] = 0;
-                    ch[1] = 64;
-                }
-                for (int r = 0; r < w.rows + 2; ++r, ++it) {
+            for (int off = 0; off < C::W_BYTES; off += 8192) ptx::bulk_copy_g2s(w_s + off, wsrc + off, 8192, bar_w);
+        }
+        uint32_t it = 0;
+        StripWalker walk(geo, group, a.H);
+        Strip s;
+        while (walk.next(s)) {
+            int img[2], ch[2];
+            if (a.pair_mode) {
+                const int b = s.m / a.half, i = s.m % a.half;
+                img[0] = b * a.src_views + i;
+                img[1] = b * a.src_views + (a.top - 1 - i);
+                ch[0] = ch[1] = 0;
+            } else {
+                img[0] = img[1] = s.m;
+                ch[0] = 0;
+                ch[1] = 64;
+            }
+            for (int q = 0; q < s.rows + 2; ++q) {
+#pragma unroll
+                for (int c = 0; c < C::CHUNKS; ++c, ++it) {
                     const uint32_t slot = it % C::RING, ph = (it / C::RING) & 1;
                     ptx::mbar_wait(bar_empty + 8 * slot, ph ^ 1, 1);
-                    ptx::mbar_expect_tx(bar_full + 8 * slot, C::CHUNKS * SLOT_PIX * 128);
-                    const int y = w.y0 - 1 + r;
-#pragma unroll
-                    for (int c = 0; c < C::CHUNKS; ++c)
-                        ptx::tma_load_4d(ring_s + slot * C::SLOT_BYTES + c * CHUNK_BYTES, &in_map, ch[c],
-                                         w.xt * TILE_M - 1, y, img[c], bar_full + 8 * slot);
+                    if (ptx::elect_one()) {
+                        ptx::mbar_expect_tx(bar_full + 8 * slot, CHUNK_TX);
+                        ptx::tma_load_4d(ring_s + slot * CHUNK_BYTES, &in_map, ch[c], s.xt * TILE_M - 1, s.y0 - 1 + q,
+                                         img[c], bar_full + 8 * slot);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================================================== MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::umma_idesc_bf16(TILE_M, C::NT);
-            ptx::mbar_wait(bar_w, 0, 2);
-            uint32_t it = 0, tile = 0;
-            auto wait_full = [&](uint32_t k) {
-                ptx::mbar_wait(bar_full + 8 * (k % C::RING), (k / C::RING) & 1, 3);
-            };
-            for (int t = first; t < g.items_per_part; t += step) {
-                const Item w = decode_item(t, a, g);
-                for (int i = 0; i < w.rows; ++i, ++tile) {
-                    const uint32_t acc = tile % ACC_STAGES, aph = (tile / ACC_STAGES) & 1;
-                    ptx::mbar_wait(bar_tempty + 8 * acc, aph ^ 1, 4);
-                    if (i == 0) {
-                        wait_full(it);
-                        wait_full(it + 1);
+        // ===================================================== MMA issuer (whole warp loops, one lane issues)
+        constexpr uint32_t idesc_base = ptx::umma_idesc_bf16(TILE_M, 0);
+        ptx::mbar_wait(bar_w, 0, 2);
+        uint32_t it = 0, tile0 = 0;
+        StripWalker walk(geo, group, a.H);
+        Strip s;
+        while (walk.next(s)) {
+            for (int q = 0; q < s.rows + 2; ++q) {
+                // input row q feeds output rows o = q - ky; B block blk = 2 - ky <-> output o = q - 2 + blk
+                const int ky_lo = max(0, q - (s.rows - 1)), ky_hi = min(2, q);
+                const int blk_lo = 2 - ky_hi, blk_hi = 2 - ky_lo;
+                const uint32_t t_lo = tile0 + q - 2 + blk_lo;           // accumulator (tile) index of block blk_lo
+                const bool opens = (ky_lo == 0);                        // block 2 starts a new accumulator
+                if (opens) {
+                    const uint32_t t_new = tile0 + q;
+                    ptx::mbar_wait(bar_tempty + 8 * (t_new % ACC_SLOTS), ((t_new / ACC_SLOTS) & 1) ^ 1, 4);
+                }
+                // split [blk_lo, blk_hi] into runs that are contiguous in TMEM (slot wrap) and, for the very first
+                // k-step, share the same accumulate flag (the new accumulator must be overwritten, not added to)
+                int run_blk[3], run_len[3], n_runs = 0;
+                int first_blk[3], first_len[3], first_acc[3], n_first = 0;
+                {
+                    int b0 = blk_lo;
+                    for (int b = blk_lo; b <= blk_hi; ++b) {
+                        const bool last = (b == blk_hi);
+                        const bool wrap_next = ((t_lo + (b - blk_lo)) % ACC_SLOTS) == ACC_SLOTS - 1;
+                        if (last || wrap_next) {
+                            run_blk[n_runs] = b0;
+                            run_len[n_runs++] = b - b0 + 1;
+                            b0 = b + 1;
+                        }
                     }
-                    wait_full(it + i + 2);
+                    for (int r = 0; r < n_runs; ++r) {
+                        const int rb = run_blk[r], rl = run_len[r];
+                        if (opens && rb + rl - 1 == 2 && rl > 1) {
+                            first_blk[n_first] = rb;
+                            first_len[n_first] = rl - 1;
+                            first_acc[n_first++] = 1;
+                            first_blk[n_first] = 2;
+                            first_len[n_first] = 1;
+                            first_acc[n_first++] = 0;
+                        } else {
+                            first_blk[n_first] = rb;
+                            first_len[n_first] = rl;
+                            first_acc[n_first++] = (opens && rb == 2) ? 0 : 1;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < C::CHUNKS; ++c, ++it) {
+                    const uint32_t slot = it % C::RING;
+                    ptx::mbar_wait(bar_full + 8 * slot, (it / C::RING) & 1, 3);
                     ptx::tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + acc * C::NT;
-                    uint32_t accumulate = 0;
+                    if (ptx::elect_one()) {
+                        const uint32_t a_lo = desc_lo(ring_s + slot * CHUNK_BYTES);
 #pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-                        const uint32_t a_row = ring_s + ((it + i + ky) % C::RING) * C::SLOT_BYTES;
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const uint32_t b_lo = desc_lo(w_s + (kx * C::CHUNKS + c) * BTILE_BYTES);
 #pragma unroll
-                        for (int c = 0; c < C::CHUNKS; ++c) {
-#pragma unroll
-                            for (int kx = 0; kx < 3; ++kx) {
-                                const uint32_t a_addr = a_row + c * CHUNK_BYTES + kx * 128;
-                                const uint32_t b_addr = w_s + ((ky * 3 + kx) * C::CHUNKS + c) * C::WTILE_BYTES;
-                                const uint32_t bo = a.desc_base_offset_mode ? ((a_addr >> 7) & 7) : 0;
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    ptx::umma_bf16(d_tmem, ptx::smem_desc_sw128(a_addr + j * 32, bo),
-                                                   ptx::smem_desc_sw128(b_addr + j * 32, 0), idesc, accumulate);
-                                    accumulate = 1;
+                            for (int j = 0; j < 4; ++j) {
+                                const uint64_t adesc = make_desc(a_lo + kx * 8 + j * 2);   // +128 B per kx, +32 B per k-step
+                                if (c == 0 && kx == 0 && j == 0) {
+                                    for (int r = 0; r < n_first; ++r) {
+                                        const uint32_t t = t_lo + (first_blk[r] - blk_lo);
+                                        ptx::umma_bf16(tmem_base + (t % ACC_SLOTS) * NT, adesc,
+                                                       make_desc(b_lo + first_blk[r] * (NT * 128 / 16) + j * 2),
+                                                       idesc_base | (static_cast<uint32_t>(first_len[r] * NT >> 3) << 17),
+                                                       first_acc[r]);
+                                    }
+                                } else {
+                                    for (int r = 0; r < n_runs; ++r) {
+                                        const uint32_t t = t_lo + (run_blk[r] - blk_lo);
+                                        ptx::umma_bf16(tmem_base + (t % ACC_SLOTS) * NT, adesc,
+                                                       make_desc(b_lo + run_blk[r] * (NT * 128 / 16) + j * 2),
+                                                       idesc_base | (static_cast<uint32_t>(run_len[r] * NT >> 3) << 17), 1);
+                                    }
                                 }
                             }
                         }
+                        ptx::umma_commit(bar_empty + 8 * slot);                 // this (row, chunk) buffer is consumed
+                        if (c == C::CHUNKS - 1 && ky_hi == 2)                   // output row q-2 has all 9 taps
+                            ptx::umma_commit(bar_tfull + 8 * ((tile0 + q - 2) % ACC_SLOTS));
                     }
-                    ptx::umma_commit(bar_empty + 8 * ((it + i) % C::RING));
-                    if (i == w.rows - 1) {
-                        ptx::umma_commit(bar_empty + 8 * ((it + i + 1) % C::RING));
-                        ptx::umma_commit(bar_empty + 8 * ((it + i + 2) % C::RING));
-                    }
-                    ptx::umma_commit(bar_tfull + 8 * acc);
+                    __syncwarp();
                 }
-                it += w.rows + 2;
             }
+            tile0 += s.rows;
         }
     } else if (warp >= 4) {
-        // ===================================================== epilogue
-        const int wq = warp - 4;   // TMEM lane quadrant of this warp (warp % 4)
-        const int co0 = part * C::NT;
-        constexpr int VEC = C::NT / 8;   // 16-byte vectors of bf16 per pixel
+        // ===================================================== epilogue: 8 warps, (lane quadrant) x (column half)
+        const int wq = warp & 3;                 // TMEM lanes [32 wq, 32 wq + 32)
+        const int hf = (warp - 4) >> 2;          // accumulator columns [32 hf, 32 hf + 32)
+        const int co0 = part * NT + hf * 32;     // first output channel handled by this thread
+        constexpr int VEC = 4;                   // 4 x 16 B = 32 bf16 per pixel
         uint32_t tile = 0;
-        for (int t = first; t < g.items_per_part; t += step) {
-            const Item w = decode_item(t, a, g);
-            const int x = w.xt * TILE_M + wq * 32 + lane;
+        StripWalker walk(geo, group, a.H);
+        Strip s;
+        while (walk.next(s)) {
+            const int x = s.xt * TILE_M + wq * 32 + lane;
             const bool valid = x < a.W;
-            // residual source for this work item
             const __nv_bfloat16* res_img = nullptr;
             int res_c = 0;
             float scale = 1.0f;
             if (a.res_mode == RES_SAME) {
-                res_img = a.res + (static_cast<size_t>(w.m) * a.H * a.W) * a.cout + co0;
+                res_img = a.res + (static_cast<size_t>(s.m) * a.H * a.W) * a.cout + co0;
                 res_c = a.cout;
             } else if (a.res_mode == RES_PAIR) {
-                const int b = w.m / a.half, i = w.m % a.half;
+                const int b = s.m / a.half, i = s.m % a.half;
                 const int side = co0 >= 64;
                 const int img = b * a.src_views + (side ? (a.top - 1 - i) : i);
                 res_img = a.res + (static_cast<size_t>(img) * a.H * a.W) * 64 + (co0 - 64 * side);
                 res_c = 64;
             } else if (a.res_mode == RES_ALPHA) {
-                const int b = w.m / a.half, i = w.m % a.half;
+                const int b = s.m / a.half, i = s.m % a.half;
                 res_img = a.res + (static_cast<size_t>(b * a.src_views + i) * a.H * a.W) * 64 + co0;
                 res_c = 64;
                 scale = a.alphas[b * a.alpha_stride + (a.top - 1 - i)];
             }
-            for (int i = 0; i < w.rows; ++i, ++tile) {
-                const uint32_t acc = tile % ACC_STAGES, aph = (tile / ACC_STAGES) & 1;
-                const int y = w.y0 + i;
+            for (int i = 0; i < s.rows; ++i, ++tile) {
+                const uint32_t acc = tile % ACC_SLOTS, aph = (tile / ACC_SLOTS) & 1;
+                const int y = s.y0 + i;
                 const size_t pix = static_cast<size_t>(y) * a.W + x;
                 uint4 rv[VEC];
                 if (res_img != nullptr && valid) {
@@ -241,23 +307,21 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
                 }
                 ptx::mbar_wait(bar_tfull + 8 * acc, aph, 5);
                 ptx::tc_fence_after();
-                uint32_t v[C::NT / 32][32];
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * C::NT;
-#pragma unroll
-                for (int h = 0; h < C::NT / 32; ++h) ptx::tmem_ld_x32(taddr + h * 32, v[h]);
+                uint32_t v[32];
+                ptx::tmem_ld_x32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * NT + hf * 32, v);
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * acc);
                 if (valid) {
-                    uint4* op = reinterpret_cast<uint4*>(a.out + (static_cast<size_t>(w.m) * a.H * a.W + pix) * a.cout + co0);
+                    uint4* op = reinterpret_cast<uint4*>(a.out + (static_cast<size_t>(s.m) * a.H * a.W + pix) * a.cout + co0);
 #pragma unroll
                     for (int vv = 0; vv < VEC; ++vv) {
                         float f[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             const int ch = vv * 8 + e;
-                            float val = __uint_as_float(v[ch / 32][ch % 32]) + bias_s[ch];
+                            float val = __uint_as_float(v[ch]) + bias_s[hf * 32 + ch];
                             if (a.has_prelu) val = val >= 0.0f ? val : a.prelu * val;
                             f[e] = val;
                         }
@@ -284,7 +348,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
-    if (warp == 2) ptx::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    if (warp == 2) ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 // ---------------------------------------------------------------- host side
@@ -320,33 +384,33 @@ int launch_impl(const ConvArgs& a, const CUtensorMap& map, const Geometry& g, in
     return 0;
 }
 
-inline int n_tile_for(int cin) { return cin == 64 ? 64 : 32; }
-
 }  // namespace
 
 int conv3x3_bytes_per_weight_image(int cin, int cout) { return 9 * cin * cout * 2; }
 
+// OIHW fp32 -> per 64-channel output part: [kx][chunk][block = 2 - ky][n = 64 co][k = 64 ci] bf16, each
+// (kx, chunk) tile being 192 K-major rows of 128 B whose 16-byte chunks are XOR-swizzled by (row % 8).
 void conv3x3_pack_weights(const float* oihw, int cin, int cout, uint8_t* dst) {
-    const int nt = n_tile_for(cin), chunks = cin / 64, parts = cout / nt;
-    const size_t tile_bytes = static_cast<size_t>(nt) * 128;
+    const int chunks = cin / 64, parts = cout / NT;
     for (int p = 0; p < parts; ++p)
-        for (int tap = 0; tap < 9; ++tap)
+        for (int kx = 0; kx < 3; ++kx)
             for (int c = 0; c < chunks; ++c) {
-                uint8_t* tile = dst + ((static_cast<size_t>(p) * 9 + tap) * chunks + c) * tile_bytes;
-                for (int n = 0; n < nt; ++n)
-                    for (int k = 0; k < 64; ++k) {
-                        const int co = p * nt + n, ci = c * 64 + k;
-                        const float w = oihw[(static_cast<size_t>(co) * cin + ci) * 9 + tap];
-                        const __nv_bfloat16 h = __float2bfloat16_rn(w);
-                        // K-major row of 64 bf16 = 128 B, 16-byte chunks XOR-swizzled by (row % 8): SWIZZLE_128B
-                        const size_t off = static_cast<size_t>(n) * 128 + (((k >> 3) ^ (n & 7)) << 4) + (k & 7) * 2;
-                        std::memcpy(tile + off, &h, 2);
-                    }
+                uint8_t* tile = dst + ((static_cast<size_t>(p) * 3 + kx) * chunks + c) * BTILE_BYTES;
+                for (int blk = 0; blk < 3; ++blk) {
+                    const int ky = 2 - blk;
+                    for (int n = 0; n < NT; ++n)
+                        for (int k = 0; k < 64; ++k) {
+                            const int co = p * NT + n, ci = c * 64 + k, row = blk * NT + n;
+                            const float w = oihw[(static_cast<size_t>(co) * cin + ci) * 9 + ky * 3 + kx];
+                            const __nv_bfloat16 h = __float2bfloat16_rn(w);
+                            const size_t off = static_cast<size_t>(row) * 128 + (((k >> 3) ^ (row & 7)) << 4) + (k & 7) * 2;
+                            std::memcpy(tile + off, &h, 2);
+                        }
+                }
             }
 }
 
-int conv3x3_launch(const ConvArgs& a_in, int sm_count, cudaStream_t stream) {
-    ConvArgs a = a_in;
+int conv3x3_launch(const ConvArgs& a, int sm_count, cudaStream_t stream) {
     if ((a.cin != 64 && a.cin != 128) || (a.cout != 64 && a.cout != 128)) {
         set_error("conv3x3: unsupported channels %d -> %d (need 64/128)", a.cin, a.cout);
         return -1;
@@ -360,22 +424,14 @@ int conv3x3_launch(const ConvArgs& a_in, int sm_count, cudaStream_t stream) {
         set_error("conv3x3: cuTensorMapEncodeTiled not available from the driver");
         return -1;
     }
-    const int nt = n_tile_for(a.cin);
     Geometry g;
-    g.n_parts = a.cout / nt;
+    g.n_parts = a.cout / NT;
     g.x_tiles = (a.W + TILE_M - 1) / TILE_M;
-    int ctas = std::max(g.n_parts, (sm_count / g.n_parts) * g.n_parts);
-    const int groups = ctas / g.n_parts;
-    if (a.strip_h <= 0) {
-        // enough strips that every CTA group sees several work items, but strips no shorter than 8 rows
-        const long long base_items = static_cast<long long>(a.n_img) * g.x_tiles;
-        long long want = (6LL * groups + base_items - 1) / base_items;
-        want = std::max(1LL, std::min<long long>(want, std::max(1, a.H / 8)));
-        a.strip_h = static_cast<int>((a.H + want - 1) / want);
-    }
-    g.strips = (a.H + a.strip_h - 1) / a.strip_h;
-    g.items_per_part = a.n_img * g.x_tiles * g.strips;
-    ctas = std::min(ctas, g.items_per_part * g.n_parts);
+    g.total_rows = static_cast<long long>(a.n_img) * g.x_tiles * a.H;
+    int ctas = a.max_ctas > 0 ? std::min(a.max_ctas, sm_count) : sm_count;
+    ctas = std::max(g.n_parts, (ctas / g.n_parts) * g.n_parts);
+    g.groups = static_cast<int>(std::min<long long>(ctas / g.n_parts, g.total_rows));
+    ctas = g.groups * g.n_parts;
 
     CUtensorMap map;
     const cuuint64_t dims[4] = {static_cast<cuuint64_t>(a.in_c), static_cast<cuuint64_t>(a.W),

@@ -34,13 +34,13 @@ struct ConvArgs {
     // geometry of the OUTPUT images (same H, W as the input: 3x3, pad 1)
     int n_img, H, W;
     int cin, cout;            // cin in {64, 128}; cout in {64, 128}
-    int strip_h;              // output rows handled per work item
+    int max_ctas;             // 0 = one CTA per SM; tests shrink it to force odd strip boundaries
     // A operand gather.  pair_mode: output image m = (b, i) reads chunk 0 from view i and chunk 1 from
     // view top-1-i of the 64-channel view stack (HRNet.py:114-119); otherwise chunk c = channels [64c, 64c+64).
     int pair_mode, half, src_views, top;
     const void* in;           // bf16 NHWC source tensor (for the TMA map)
     int in_images, in_c;      // its image count and channels per pixel
-    // B operand: pre-swizzled smem image, [cout / n_tile][9 taps][cin / 64][n_tile rows x 128 B]
+    // B operand: pre-swizzled smem image, [cout / 64][kx][cin / 64][3 ky-blocks x 64 rows x 128 B]
     const uint8_t* w_img;
     const float* bias;        // [cout]
     float prelu;
@@ -51,7 +51,6 @@ struct ConvArgs {
     const __nv_bfloat16* res; // RES_SAME: cout-channel tensor; RES_PAIR / RES_ALPHA: the 64-channel view stack
     const float* alphas;      // (B, alpha_stride) original alphas, RES_ALPHA only
     int alpha_stride;
-    int desc_base_offset_mode;   // bring-up knob: 0 = base_offset 0, 1 = (start >> 7) & 7
 };
 int conv3x3_bytes_per_weight_image(int cin, int cout);
 // Repack OIHW fp32 (cout, cin, 3, 3) host weights into the pre-swizzled bf16 smem image (host memory).

@@ -104,8 +104,8 @@ int32_t hrn_shift_cpsnr(const float* sr, const float* hr, const float* hr_map, i
 int32_t hrn_forward_dump(hrn_handle* h, const float* lrs, const float* alphas, int32_t B, int32_t L, int32_t H,
                          int32_t W, float* sr, int32_t stage, float* dump, void* stream);
 
-/* Bring-up knob for the tcgen05 shared-memory descriptors: 0 = matrix base offset 0 (default),
- * 1 = base offset (start_address >> 7) & 7. */
+/* Test knobs.  "max_ctas" = N > 0 limits the tcgen05 conv kernels to N CTAs (0 = one per SM), which moves
+ * the strip boundaries of the row partition; results must not change. */
 int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value);
 
 /* Per-launch device timing of HRNet.forward, by kernel class, with CUDA events recorded on the stream the

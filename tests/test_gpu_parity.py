@@ -155,6 +155,22 @@ def test_full_size_properties_c2(net, dev):
     assert err <= SR_GATE and err <= SR_REGRESSION_GATE, err
 
 
+def test_row_partition_does_not_change_results(hb, dev):
+    """The conv kernels split the flattened (image, row) space evenly over the CTAs; odd CTA counts put strip
+    boundaries in the middle of images (1-row strips included).  Results must be bit-identical."""
+    lrs, alphas = cases.hrnet_inputs("b2_l9_s16")
+    tl, ta = torch.from_numpy(lrs).to(dev), torch.from_numpy(alphas).to(dev)
+    outs = []
+    for ctas in (0, 1, 2, 7, 37, 146):
+        model = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval()
+        model.load_state_dict(hrnet_oracle.make_params(cases.WEIGHT_SEED))
+        model = model.to(dev)
+        model.debug_set(dev, "max_ctas", ctas)
+        outs.append(model(tl, ta))
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+
+
 def test_forward_host_equals_device_path(net, dev):
     lrs, alphas = cases.hrnet_inputs("b2_l4_s32")
     a = net(torch.from_numpy(lrs).to(dev), torch.from_numpy(alphas).to(dev)).cpu()

@@ -54,7 +54,7 @@ def _layer_ref(x, w, b, slope):
     return F.prelu(y, slope) if slope is not None else y
 
 
-def group_taps(bo_mode: int, size: int):
+def group_taps(max_ctas: int, size: int):
     """Isolate single taps of the first 64->64 tcgen05 conv (stage ENC(1))."""
     import numpy as np
     import torch
@@ -80,14 +80,14 @@ def group_taps(bo_mode: int, size: int):
         sd[key + ".weight"] = w
         net.load_state_dict(sd)
         net = net.to(dev)
-        net.debug_set(dev, "desc_base_offset_mode", bo_mode)
+        net.debug_set(dev, "max_ctas", max_ctas)
         _, x0 = net.forward_stage(lrs, alphas, hm.stage_enc(0), (1, 64, size, size))
         _, y1 = net.forward_stage(lrs, alphas, hm.stage_enc(1), (1, 64, size, size))
         torch.cuda.synchronize()
         wb = w.to(torch.bfloat16).to(torch.float32)
         ref = _layer_ref(x0.cpu(), wb, params[key + ".bias"], params["encode.res_layers.0.block.1.weight"])
         err = (y1.cpu() - ref).abs()
-        log(check="conv64_taps", bo_mode=bo_mode, size=size, taps=str(taps), max_err=float(err.max()),
+        log(check="conv64_taps", max_ctas=max_ctas, size=size, taps=str(taps), max_err=float(err.max()),
             ref_max=float(ref.abs().max()), bad_frac=float((err > 2e-2 * ref.abs().max()).float().mean()))
         del net
 
@@ -159,9 +159,9 @@ def group_speed():
 
 GROUPS = {
     "scoring": lambda: group_scoring(),
-    "taps_bo0_s16": lambda: group_taps(0, 16),
-    "taps_bo0_s128": lambda: group_taps(0, 128),
-    "taps_bo1_s16": lambda: group_taps(1, 16),
+    "taps_s16": lambda: group_taps(0, 16),
+    "taps_s128": lambda: group_taps(0, 128),
+    "taps_s128_ctas5": lambda: group_taps(5, 128),
     "forward_small": lambda: group_forward(["b1_l1_s16", "b2_l4_s32", "b1_l5_s24", "b1_l6_s16", "b2_l9_s16", "b1_l16_s16"]),
     "forward_big": lambda: group_forward(["b1_l2_s136", "c1_b2_l4_s128"]),
     "speed": lambda: group_speed(),
