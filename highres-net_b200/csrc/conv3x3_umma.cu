@@ -179,80 +179,56 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
     } else if (warp == 1) {
         // ===================================================== MMA issuer (whole warp loops, one lane issues)
         constexpr uint32_t idesc_base = ptx::umma_idesc_bf16(TILE_M, 0);
+        constexpr uint32_t idesc64 = ptx::umma_idesc_bf16(TILE_M, NT);
+        constexpr uint32_t BLK = NT * 128 / 16;                   // one 64-row ky block, in descriptor units (16 B)
+        const uint32_t a_lo0 = desc_lo(ring_s), b_lo0 = desc_lo(w_s);
         ptx::mbar_wait(bar_w, 0, 2);
         uint32_t it = 0, tile0 = 0;
         StripWalker walk(geo, group, a.H);
         Strip s;
         while (walk.next(s)) {
             for (int q = 0; q < s.rows + 2; ++q) {
-                // input row q feeds output rows o = q - ky; B block blk = 2 - ky <-> output o = q - 2 + blk
+                // Input row q feeds output rows o = q - ky.  B block (2 - ky) <-> output row q - ky, so the blocks
+                // [blk_lo, blk_lo + nblk) map to the consecutive accumulators (tiles) t_lo, t_lo + 1, ...
                 const int ky_lo = max(0, q - (s.rows - 1)), ky_hi = min(2, q);
-                const int blk_lo = 2 - ky_hi, blk_hi = 2 - ky_lo;
-                const uint32_t t_lo = tile0 + q - 2 + blk_lo;           // accumulator (tile) index of block blk_lo
-                const bool opens = (ky_lo == 0);                        // block 2 starts a new accumulator
+                const int blk_lo = 2 - ky_hi, nblk = ky_hi - ky_lo + 1;
+                const uint32_t t_lo = tile0 + q - ky_hi;
+                const uint32_t s_lo = t_lo % ACC_SLOTS;
+                const bool opens = (ky_lo == 0);                        // the last block starts a new accumulator
                 if (opens) {
                     const uint32_t t_new = tile0 + q;
                     ptx::mbar_wait(bar_tempty + 8 * (t_new % ACC_SLOTS), ((t_new / ACC_SLOTS) & 1) ^ 1, 4);
                 }
-                // split [blk_lo, blk_hi] into runs that are contiguous in TMEM (slot wrap) and, for the very first
-                // k-step, share the same accumulate flag (the new accumulator must be overwritten, not added to)
-                int run_blk[3], run_len[3], n_runs = 0;
-                int first_blk[3], first_len[3], first_acc[3], n_first = 0;
-                {
-                    int b0 = blk_lo;
-                    for (int b = blk_lo; b <= blk_hi; ++b) {
-                        const bool last = (b == blk_hi);
-                        const bool wrap_next = ((t_lo + (b - blk_lo)) % ACC_SLOTS) == ACC_SLOTS - 1;
-                        if (last || wrap_next) {
-                            run_blk[n_runs] = b0;
-                            run_len[n_runs++] = b - b0 + 1;
-                            b0 = b + 1;
-                        }
-                    }
-                    for (int r = 0; r < n_runs; ++r) {
-                        const int rb = run_blk[r], rl = run_len[r];
-                        if (opens && rb + rl - 1 == 2 && rl > 1) {
-                            first_blk[n_first] = rb;
-                            first_len[n_first] = rl - 1;
-                            first_acc[n_first++] = 1;
-                            first_blk[n_first] = 2;
-                            first_len[n_first] = 1;
-                            first_acc[n_first++] = 0;
-                        } else {
-                            first_blk[n_first] = rb;
-                            first_len[n_first] = rl;
-                            first_acc[n_first++] = (opens && rb == 2) ? 0 : 1;
-                        }
-                    }
-                }
+                // the accumulators are contiguous in TMEM except across the slot 7 -> 0 wrap: at most two segments
+                const int w0 = min(nblk, ACC_SLOTS - static_cast<int>(s_lo)), w1 = nblk - w0;
+                const uint32_t d0 = tmem_base + s_lo * NT, d1 = tmem_base;
+                const uint32_t id0 = idesc_base | (static_cast<uint32_t>(w0 * NT >> 3) << 17);
+                const uint32_t id1 = idesc_base | (static_cast<uint32_t>(w1 * NT >> 3) << 17);
 #pragma unroll
                 for (int c = 0; c < C::CHUNKS; ++c, ++it) {
                     const uint32_t slot = it % C::RING;
                     ptx::mbar_wait(bar_full + 8 * slot, (it / C::RING) & 1, 3);
                     ptx::tc_fence_after();
                     if (ptx::elect_one()) {
-                        const uint32_t a_lo = desc_lo(ring_s + slot * CHUNK_BYTES);
+                        const uint32_t a_lo = a_lo0 + slot * (CHUNK_BYTES / 16);
+                        const uint32_t b0 = b_lo0 + c * (BTILE_BYTES / 16) + blk_lo * BLK;
+                        const uint32_t b1 = b0 + w0 * BLK;
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx) {
-                            const uint32_t b_lo = desc_lo(w_s + (kx * C::CHUNKS + c) * BTILE_BYTES);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const uint64_t adesc = make_desc(a_lo + kx * 8 + j * 2);   // +128 B per kx, +32 B per k-step
+                                const uint32_t bofs = kx * (C::CHUNKS * BTILE_BYTES / 16) + j * 2;
                                 if (c == 0 && kx == 0 && j == 0) {
-                                    for (int r = 0; r < n_first; ++r) {
-                                        const uint32_t t = t_lo + (first_blk[r] - blk_lo);
-                                        ptx::umma_bf16(tmem_base + (t % ACC_SLOTS) * NT, adesc,
-                                                       make_desc(b_lo + first_blk[r] * (NT * 128 / 16) + j * 2),
-                                                       idesc_base | (static_cast<uint32_t>(first_len[r] * NT >> 3) << 17),
-                                                       first_acc[r]);
-                                    }
+                                    // first k-step of the row: block by block, so that the opening accumulator is
+                                    // overwritten (accumulate = 0) while the older ones keep accumulating
+                                    for (int b = 0; b < nblk; ++b)
+                                        ptx::umma_bf16(tmem_base + ((t_lo + b) % ACC_SLOTS) * NT, adesc,
+                                                       make_desc(b0 + b * BLK + bofs), idesc64,
+                                                       (opens && b == nblk - 1) ? 0u : 1u);
                                 } else {
-                                    for (int r = 0; r < n_runs; ++r) {
-                                        const uint32_t t = t_lo + (run_blk[r] - blk_lo);
-                                        ptx::umma_bf16(tmem_base + (t % ACC_SLOTS) * NT, adesc,
-                                                       make_desc(b_lo + run_blk[r] * (NT * 128 / 16) + j * 2),
-                                                       idesc_base | (static_cast<uint32_t>(run_len[r] * NT >> 3) << 17), 1);
-                                    }
+                                    ptx::umma_bf16(d0, adesc, make_desc(b0 + bofs), id0, 1u);
+                                    if (w1 > 0) ptx::umma_bf16(d1, adesc, make_desc(b1 + bofs), id1, 1u);
                                 }
                             }
                         }
