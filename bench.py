@@ -56,8 +56,9 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (samples outside the
+    [t0, t1] window handed to stop() are dropped)."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
@@ -66,13 +67,15 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0, t1):
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
@@ -83,21 +86,23 @@ class ClockSampler:
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for line in out.strip().splitlines():
             parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-                power.append(float(parts[2]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                vals = (float(parts[1]), float(parts[2]), float(parts[3]))
             except ValueError:
                 continue
-            for name, val in zip(names, parts[3:7]):
+            if ts < t0 or ts > t1:
+                continue
+            sm.append(vals[0])
+            mx.append(vals[1])
+            power.append(vals[2])
+            for name, val in zip(names, parts[4:8]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        # the busiest samples are the ones taken under load
-        sm_sorted = sorted(sm)
-        return {"sm_mhz": statistics.median(sm_sorted) if sm_sorted else None,
-                "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(power) if power else None,
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "power_w_median": statistics.median(power) if power else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
@@ -163,7 +168,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="imagesets per GPU per step")
@@ -210,23 +215,7 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    # ---------------- device-resident throughput ----------------
-    for i in range(args.warmup):
-        net(*dev_inputs[i % n_rot])
-    sync_all()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    launches0 = hb.kernel_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        sr = net(*dev_inputs[i % n_rot])
-    e1.record()
-    sync_all()
-    launches = hb.kernel_launch_count() - launches0
-    ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop() if sampler is not None else None
-
-    # ---------------- end to end through the host-buffer API ----------------
+    # ---------------- end to end through the host-buffer API (runs first: it also ramps the clocks) ----------------
     for i in range(2):
         net.forward_host(*host_inputs[i % len(host_inputs)], out_host=host_out, device=dev)
     sync_all()
@@ -237,6 +226,24 @@ def main():
     e3.record()
     sync_all()
     ms_e2e = e2.elapsed_time(e3)
+
+    # ---------------- device-resident throughput ----------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for i in range(args.warmup):
+        net(*dev_inputs[i % n_rot])
+    sync_all()
+    launches0 = hb.kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        sr = net(*dev_inputs[i % n_rot])
+    e1.record()
+    sync_all()
+    t_wall1 = time.time()
+    launches = hb.kernel_launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler is not None else None
 
     # ---------------- per-kernel-class timing for the roofline ----------------
     net.profile_begin(dev)

@@ -44,7 +44,8 @@ struct hrn_handle {
     float prelu_init = 0.0f;
     std::vector<hrn::ConvLayer> enc;   // 2 * num_layers residual convs + the final conv
     hrn::ConvLayer fuse[3];
-    float *wd = nullptr, *bd = nullptr, *wf = nullptr;
+    uint8_t* wd_img = nullptr;         // decoder_pack_weights() image
+    float *bd = nullptr, *wf = nullptr;
     float prelu_dec = 0.0f, bf = 0.0f;
     // workspace
     size_t act_cap = 0;                // bytes of each activation buffer
@@ -54,6 +55,7 @@ struct hrn_handle {
     size_t io_cap[3] = {0, 0, 0};
     float* io[3] = {nullptr, nullptr, nullptr};   // device staging for hrn_forward_host: lrs, alphas, sr
     int max_ctas = 0;                  // 0 = one CTA per SM (test knob)
+    int debug_flags = 0;
     // optional per-launch timing (hrn_profile_begin / hrn_profile_end)
     bool profiling = false;
     struct Span { cudaEvent_t e0, e1; int cls; double flops; };
@@ -162,6 +164,7 @@ int run_conv(hrn_handle* h, const hrn::ConvLayer& l, hrn::ConvArgs a, cudaStream
     a.prelu = l.prelu;
     a.has_prelu = l.has_prelu ? 1 : 0;
     a.max_ctas = h->max_ctas;
+    a.debug_flags = h->debug_flags;
     return hrn::conv3x3_launch(a, h->sm_count, s);
 }
 
@@ -300,7 +303,7 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
     // ---- decoder (HRNet.py:147-156)
     {
         SpanGuard guard(h, s, HRN_PROF_DECODER, 74880.0 * static_cast<double>(B) * hw);
-        if (hrn::decoder_launch(h->act[cur], B, H, W, h->wd, h->bd, h->prelu_dec, h->wf, h->bf, sr, s)) return -1;
+        if (hrn::decoder_umma_launch(h->act[cur], B, H, W, h->wd_img, h->bd, h->prelu_dec, h->wf, h->bf, sr, h->sm_count, s)) return -1;
     }
     if (dump != nullptr && !dump->hit) {
         set_error("hrn_forward_dump: stage 0x%x does not exist for L=%d", dump->stage, L);
@@ -384,7 +387,7 @@ void hrn_destroy(hrn_handle* h) {
         rel(l.w_img);
         rel(l.bias);
     }
-    rel(h->wd);
+    rel(h->wd_img);
     rel(h->bd);
     rel(h->wf);
     for (auto* p : h->act) rel(p);
@@ -436,13 +439,11 @@ int32_t hrn_set_weight(hrn_handle* h, const char* key, const float* data, const 
         rc = set_prelu(&h->fuse[2].prelu, &h->fuse[2].has_prelu, shape, ndim, data);
     } else if (k == "decode.deconv.0.weight") {
         if (shape_is(shape, ndim, {64, 64, 3, 3})) {
-            // ConvTranspose2d weight (ci, co, ky, kx) -> [pos = ky*3+kx][co][ci]
-            std::vector<float> packed(9 * 64 * 64);
-            for (int ci = 0; ci < 64; ++ci)
-                for (int co = 0; co < 64; ++co)
-                    for (int pos = 0; pos < 9; ++pos)
-                        packed[(static_cast<size_t>(pos) * 64 + co) * 64 + ci] = data[(static_cast<size_t>(ci) * 64 + co) * 9 + pos];
-            rc = upload(&h->wd, packed.data(), packed.size());
+            std::vector<uint8_t> img(hrn::decoder_weight_image_bytes());
+            hrn::decoder_pack_weights(data, img.data());
+            rc = 0;
+            if (h->wd_img == nullptr && cudaMalloc(reinterpret_cast<void**>(&h->wd_img), img.size()) != cudaSuccess) rc = -4;
+            if (rc == 0 && cudaMemcpy(h->wd_img, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) rc = -4;
         } else rc = -3;
     } else if (k == "decode.deconv.0.bias") {
         rc = shape_is(shape, ndim, {64}) ? upload(&h->bd, data, 64) : -3;
@@ -462,6 +463,10 @@ int32_t hrn_set_weight(hrn_handle* h, const char* key, const float* data, const 
     }
     if (rc == -3) {
         set_error("hrn_set_weight: wrong shape for '%s'", key);
+        return -1;
+    }
+    if (rc == -4) {
+        set_error("hrn_set_weight: CUDA allocation/copy failed for '%s'", key);
         return -1;
     }
     if (rc != 0) return -1;
@@ -579,6 +584,7 @@ int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value) {
         return -1;
     }
     if (strcmp(knob, "max_ctas") == 0) h->max_ctas = value;
+    else if (strcmp(knob, "debug_flags") == 0) h->debug_flags = value;
     else {
         set_error("hrn_debug_set: unknown knob '%s'", knob);
         return -1;

@@ -28,8 +28,7 @@
 // accumulator slots (all 512 columns), so epilogues overlap the MMAs of later rows.
 // Work is split evenly: each CTA (group) owns a contiguous range of the flattened
 // (image, column tile, row) space and walks it as per-image strips.
-#include "internal.h"
-#include "ptx.cuh"
+#include "umma_common.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -48,7 +47,6 @@ constexpr int TMEM_COLS = ACC_SLOTS * NT;
 constexpr int EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;
 constexpr int BTILE_BYTES = 3 * NT * 128;   // one (kx, chunk) B tile: 192 rows x 64 bf16
-constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
 
 template <int CIN>
 struct Cfg {
@@ -91,11 +89,6 @@ struct StripWalker {
         return true;
     }
 };
-
-__device__ __forceinline__ uint64_t make_desc(uint32_t lo) {
-    return (static_cast<uint64_t>(DESC_HI) << 32) | lo;
-}
-__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return (saddr >> 4) | (1u << 16); }
 
 template <int CIN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -142,93 +135,125 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
     const uint32_t tmem_base = *tmem_slot_gen;
 
     if (warp == 0) {
-        // ===================================================== TMA producer (whole warp loops, one lane issues)
+        // ===================================================== TMA producer: one elected thread
         if (ptx::elect_one()) {
             ptx::mbar_expect_tx(bar_w, C::W_BYTES);
             const uint8_t* wsrc = a.w_img + static_cast<size_t>(part) * C::W_BYTES;
             for (int off = 0; off < C::W_BYTES; off += 8192) ptx::bulk_copy_g2s(w_s + off, wsrc + off, 8192, bar_w);
-        }
-        uint32_t it = 0;
-        StripWalker walk(geo, group, a.H);
-        Strip s;
-        while (walk.next(s)) {
-            int img[2], ch[2];
-            if (a.pair_mode) {
-                const int b = s.m / a.half, i = s.m % a.half;
-                img[0] = b * a.src_views + i;
-                img[1] = b * a.src_views + (a.top - 1 - i);
-                ch[0] = ch[1] = 0;
-            } else {
-                img[0] = img[1] = s.m;
-                ch[0] = 0;
-                ch[1] = 64;
-            }
-            for (int q = 0; q < s.rows + 2; ++q) {
+            uint32_t it = 0;
+            StripWalker walk(geo, group, a.H);
+            Strip s;
+            while (walk.next(s)) {
+                int img[2], ch[2];
+                if (a.pair_mode) {
+                    const int b = s.m / a.half, i = s.m % a.half;
+                    img[0] = b * a.src_views + i;
+                    img[1] = b * a.src_views + (a.top - 1 - i);
+                    ch[0] = ch[1] = 0;
+                } else {
+                    img[0] = img[1] = s.m;
+                    ch[0] = 0;
+                    ch[1] = 64;
+                }
+                for (int q = 0; q < s.rows + 2; ++q) {
 #pragma unroll
-                for (int c = 0; c < C::CHUNKS; ++c, ++it) {
-                    const uint32_t slot = it % C::RING, ph = (it / C::RING) & 1;
-                    ptx::mbar_wait(bar_empty + 8 * slot, ph ^ 1, 1);
-                    if (ptx::elect_one()) {
-                        ptx::mbar_expect_tx(bar_full + 8 * slot, CHUNK_TX);
-                        ptx::tma_load_4d(ring_s + slot * CHUNK_BYTES, &in_map, ch[c], s.xt * TILE_M - 1, s.y0 - 1 + q,
-                                         img[c], bar_full + 8 * slot);
+                    for (int c = 0; c < C::CHUNKS; ++c, ++it) {
+                        const uint32_t slot = it % C::RING, ph = (it / C::RING) & 1;
+                        ptx::mbar_wait(bar_empty + 8 * slot, ph ^ 1, 1);
+                        if (a.debug_flags & 4) {
+                            ptx::mbar_arrive(bar_full + 8 * slot);
+                        } else {
+                            ptx::mbar_expect_tx(bar_full + 8 * slot, CHUNK_TX);
+                            ptx::tma_load_4d(ring_s + slot * CHUNK_BYTES, &in_map, ch[c], s.xt * TILE_M - 1,
+                                             s.y0 - 1 + q, img[c], bar_full + 8 * slot);
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================================================== MMA issuer (whole warp loops, one lane issues)
-        constexpr uint32_t idesc_base = ptx::umma_idesc_bf16(TILE_M, 0);
-        constexpr uint32_t idesc64 = ptx::umma_idesc_bf16(TILE_M, NT);
-        constexpr uint32_t BLK = NT * 128 / 16;                   // one 64-row ky block, in descriptor units (16 B)
-        const uint32_t a_lo0 = desc_lo(ring_s), b_lo0 = desc_lo(w_s);
-        ptx::mbar_wait(bar_w, 0, 2);
-        uint32_t it = 0, tile0 = 0;
-        StripWalker walk(geo, group, a.H);
-        Strip s;
-        while (walk.next(s)) {
-            for (int q = 0; q < s.rows + 2; ++q) {
-                // Input row q feeds output rows o = q - ky.  B block (2 - ky) <-> output row q - ky, so the blocks
-                // [blk_lo, blk_lo + nblk) map to the consecutive accumulators (tiles) t_lo, t_lo + 1, ...
-                const int ky_lo = max(0, q - (s.rows - 1)), ky_hi = min(2, q);
-                const int blk_lo = 2 - ky_hi, nblk = ky_hi - ky_lo + 1;
-                const uint32_t t_lo = tile0 + q - ky_hi;
-                const uint32_t s_lo = t_lo % ACC_SLOTS;
-                const bool opens = (ky_lo == 0);                        // the last block starts a new accumulator
-                if (opens) {
-                    const uint32_t t_new = tile0 + q;
-                    ptx::mbar_wait(bar_tempty + 8 * (t_new % ACC_SLOTS), ((t_new / ACC_SLOTS) & 1) ^ 1, 4);
-                }
-                // the accumulators are contiguous in TMEM except across the slot 7 -> 0 wrap: at most two segments
-                const int w0 = min(nblk, ACC_SLOTS - static_cast<int>(s_lo)), w1 = nblk - w0;
-                const uint32_t d0 = tmem_base + s_lo * NT, d1 = tmem_base;
-                const uint32_t id0 = idesc_base | (static_cast<uint32_t>(w0 * NT >> 3) << 17);
-                const uint32_t id1 = idesc_base | (static_cast<uint32_t>(w1 * NT >> 3) << 17);
+        // ===================================================== MMA issuer: ONE elected thread runs the whole role.
+        // The tensor pipe queues about six N=192 MMAs (~600 cycles, measured with tools/umma_probe.cu), so the
+        // per-item bookkeeping is hidden as long as it stays short: the barrier waits for the NEXT (row, chunk)
+        // item are therefore issued in the middle of the current item's MMA burst, when the queue is full anyway.
+        if (ptx::elect_one()) {
+            constexpr uint32_t idesc_base = ptx::umma_idesc_bf16(TILE_M, 0);
+            constexpr uint32_t idesc64 = ptx::umma_idesc_bf16(TILE_M, NT);
+            constexpr uint32_t BLK = NT * 128 / 16;               // one 64-row ky block, in descriptor units (16 B)
+            constexpr uint32_t B_KX = C::CHUNKS * BTILE_BYTES / 16 - 6;   // k-step 3 of kx -> k-step 0 of kx + 1
+            const uint32_t a_lo0 = desc_lo(ring_s), b_lo0 = desc_lo(w_s);
+            ptx::mbar_wait(bar_w, 0, 2);
+            uint32_t it = 0, tile0 = 0;
+            bool full_seen = false, tempty_seen = false;          // waits already done by the previous item
+            StripWalker walk(geo, group, a.H);
+            Strip s;
+            bool have = walk.next(s);
+            while (have) {
+                Strip nxt;
+                const bool have_next = walk.next(nxt);
+                for (int q = 0; q < s.rows + 2; ++q) {
+                    // Input row q feeds output rows o = q - ky.  B block (2 - ky) <-> output row q - ky, so the blocks
+                    // [blk_lo, blk_lo + nblk) map to the consecutive accumulators (tiles) t_lo, t_lo + 1, ...
+                    const int ky_lo = max(0, q - (s.rows - 1)), ky_hi = min(2, q);
+                    const int blk_lo = 2 - ky_hi, nblk = ky_hi - ky_lo + 1;
+                    const uint32_t t_lo = tile0 + q - ky_hi;
+                    const uint32_t s_lo = t_lo % ACC_SLOTS;
+                    const bool opens = (ky_lo == 0);                    // the last block starts a new accumulator
+                    if (opens && !tempty_seen && !(a.debug_flags & 16)) {
+                        const uint32_t t_new = tile0 + q;
+                        ptx::mbar_wait(bar_tempty + 8 * (t_new % ACC_SLOTS), ((t_new / ACC_SLOTS) & 1) ^ 1, 4);
+                    }
+                    tempty_seen = false;
+                    // the accumulators are contiguous in TMEM except across the slot 7 -> 0 wrap: at most two segments
+                    const int w0 = min(nblk, ACC_SLOTS - static_cast<int>(s_lo)), w1 = nblk - w0;
+                    const uint32_t d0 = tmem_base + s_lo * NT, d1 = tmem_base;
+                    const uint32_t id0 = idesc_base | (static_cast<uint32_t>(w0 * NT >> 3) << 17);
+                    const uint32_t id1 = idesc_base | (static_cast<uint32_t>(w1 * NT >> 3) << 17);
+                    // what follows this row (for the early waits)
+                    const bool last_row = (q == s.rows + 1);
+                    const bool more_rows = !last_row || have_next;
+                    const bool next_opens = last_row ? true : (q + 1 <= s.rows - 1);
+                    const uint32_t t_next = last_row ? tile0 + s.rows : tile0 + q + 1;
 #pragma unroll
-                for (int c = 0; c < C::CHUNKS; ++c, ++it) {
-                    const uint32_t slot = it % C::RING;
-                    ptx::mbar_wait(bar_full + 8 * slot, (it / C::RING) & 1, 3);
-                    ptx::tc_fence_after();
-                    if (ptx::elect_one()) {
-                        const uint32_t a_lo = a_lo0 + slot * (CHUNK_BYTES / 16);
-                        const uint32_t b0 = b_lo0 + c * (BTILE_BYTES / 16) + blk_lo * BLK;
-                        const uint32_t b1 = b0 + w0 * BLK;
+                    for (int c = 0; c < C::CHUNKS; ++c, ++it) {
+                        const uint32_t slot = it % C::RING;
+                        if (!full_seen && !(a.debug_flags & 16)) ptx::mbar_wait(bar_full + 8 * slot, (it / C::RING) & 1, 3);
+                        full_seen = false;
+                        ptx::tc_fence_after();
+                        // Running 64-bit descriptors advanced in place: +2 (32 B) per k-step, +8 (one pixel) per kx
+                        // for A; next (kx, chunk) tile for B.
+                        uint64_t ad = make_desc(a_lo0 + slot * (CHUNK_BYTES / 16));
+                        uint64_t bd0 = make_desc(b_lo0 + c * (BTILE_BYTES / 16) + blk_lo * BLK);
+                        uint64_t bd1 = bd0 + w0 * BLK;
+                        if (c == 0) {
+                            // first k-step of the row: block by block, so that the opening accumulator is
+                            // overwritten (accumulate = 0) while the older ones keep accumulating
+                            for (int b = 0; b < nblk; ++b)
+                                ptx::umma_bf16(tmem_base + ((t_lo + b) % ACC_SLOTS) * NT, ad, bd0 + b * BLK, idesc64,
+                                               (opens && b == nblk - 1) ? 0u : 1u);
+                        } else {
+                            ptx::umma_bf16(d0, ad, bd0, id0, 1u);
+                            if (w1 > 0) ptx::umma_bf16(d1, ad, bd1, id1, 1u);
+                        }
 #pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const uint64_t adesc = make_desc(a_lo + kx * 8 + j * 2);   // +128 B per kx, +32 B per k-step
-                                const uint32_t bofs = kx * (C::CHUNKS * BTILE_BYTES / 16) + j * 2;
-                                if (c == 0 && kx == 0 && j == 0) {
-                                    // first k-step of the row: block by block, so that the opening accumulator is
-                                    // overwritten (accumulate = 0) while the older ones keep accumulating
-                                    for (int b = 0; b < nblk; ++b)
-                                        ptx::umma_bf16(tmem_base + ((t_lo + b) % ACC_SLOTS) * NT, adesc,
-                                                       make_desc(b0 + b * BLK + bofs), idesc64,
-                                                       (opens && b == nblk - 1) ? 0u : 1u);
-                                } else {
-                                    ptx::umma_bf16(d0, adesc, make_desc(b0 + bofs), id0, 1u);
-                                    if (w1 > 0) ptx::umma_bf16(d1, adesc, make_desc(b1 + bofs), id1, 1u);
+                        for (int step = 1; step < 12; ++step) {
+                            ad += 2;
+                            bd0 += (step & 3) ? 2u : B_KX;
+                            bd1 += (step & 3) ? 2u : B_KX;
+                            ptx::umma_bf16(d0, ad, bd0, id0, 1u);
+                            if (w1 > 0) ptx::umma_bf16(d1, ad, bd1, id1, 1u);
+                            if (step == 7) {
+                                // early waits for the next item: its A buffer, and its new accumulator if it opens one
+                                const bool next_item = (c + 1 < C::CHUNKS) || more_rows;
+                                if (next_item && !(a.debug_flags & 16)) {
+                                    const uint32_t itn = it + 1;
+                                    ptx::mbar_wait(bar_full + 8 * (itn % C::RING), (itn / C::RING) & 1, 6);
+                                    full_seen = true;
+                                    if (c + 1 == C::CHUNKS && next_opens) {
+                                        ptx::mbar_wait(bar_tempty + 8 * (t_next % ACC_SLOTS),
+                                                       ((t_next / ACC_SLOTS) & 1) ^ 1, 7);
+                                        tempty_seen = true;
+                                    }
                                 }
                             }
                         }
@@ -236,10 +261,11 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
                         if (c == C::CHUNKS - 1 && ky_hi == 2)                   // output row q-2 has all 9 taps
                             ptx::umma_commit(bar_tfull + 8 * ((tile0 + q - 2) % ACC_SLOTS));
                     }
-                    __syncwarp();
                 }
+                tile0 += s.rows;
+                s = nxt;
+                have = have_next;
             }
-            tile0 += s.rows;
         }
     } else if (warp >= 4) {
         // ===================================================== epilogue: 8 warps, (lane quadrant) x (column half)
@@ -276,7 +302,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
                 const int y = s.y0 + i;
                 const size_t pix = static_cast<size_t>(y) * a.W + x;
                 uint4 rv[VEC];
-                if (res_img != nullptr && valid) {
+                if (res_img != nullptr && valid && !(a.debug_flags & 8)) {
                     const uint4* rp = reinterpret_cast<const uint4*>(res_img + pix * res_c);
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) rv[v] = __ldg(rp + v);
@@ -284,12 +310,17 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
                 ptx::mbar_wait(bar_tfull + 8 * acc, aph, 5);
                 ptx::tc_fence_after();
                 uint32_t v[32];
-                ptx::tmem_ld_x32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * NT + hf * 32, v);
-                ptx::tmem_ld_wait();
+                if (a.debug_flags & 1) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] = 0;
+                } else {
+                    ptx::tmem_ld_x32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * NT + hf * 32, v);
+                    ptx::tmem_ld_wait();
+                }
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * acc);
-                if (valid) {
+                if (valid && !(a.debug_flags & 2)) {
                     uint4* op = reinterpret_cast<uint4*>(a.out + (static_cast<size_t>(s.m) * a.H * a.W + pix) * a.cout + co0);
 #pragma unroll
                     for (int vv = 0; vv < VEC; ++vv) {
@@ -328,23 +359,6 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
 }
 
 // ---------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (fn == nullptr) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess)
-            return nullptr;
-        fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
 template <int CIN>
 int launch_impl(const ConvArgs& a, const CUtensorMap& map, const Geometry& g, int ctas, cudaStream_t stream) {
     using C = Cfg<CIN>;
@@ -395,11 +409,6 @@ int conv3x3_launch(const ConvArgs& a, int sm_count, cudaStream_t stream) {
         set_error("conv3x3: empty problem");
         return -1;
     }
-    EncodeTiledFn encode = get_encode_fn();
-    if (encode == nullptr) {
-        set_error("conv3x3: cuTensorMapEncodeTiled not available from the driver");
-        return -1;
-    }
     Geometry g;
     g.n_parts = a.cout / NT;
     g.x_tiles = (a.W + TILE_M - 1) / TILE_M;
@@ -410,20 +419,7 @@ int conv3x3_launch(const ConvArgs& a, int sm_count, cudaStream_t stream) {
     ctas = g.groups * g.n_parts;
 
     CUtensorMap map;
-    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(a.in_c), static_cast<cuuint64_t>(a.W),
-                                static_cast<cuuint64_t>(a.H), static_cast<cuuint64_t>(a.in_images)};
-    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(a.in_c) * 2, static_cast<cuuint64_t>(a.W) * a.in_c * 2,
-                                   static_cast<cuuint64_t>(a.H) * a.W * a.in_c * 2};
-    const cuuint32_t box[4] = {64, SLOT_PIX, 1, 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a.in), dims, strides, box,
-                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("conv3x3: cuTensorMapEncodeTiled failed with CUresult %d (dims %d x %d x %d x %d)", (int)r, a.in_c,
-                  a.W, a.H, a.in_images);
-        return -1;
-    }
+    if (encode_nhwc_map(&map, a.in, a.in_c, a.W, a.H, a.in_images, SLOT_PIX)) return -1;
     return a.cin == 64 ? launch_impl<64>(a, map, g, ctas, stream) : launch_impl<128>(a, map, g, ctas, stream);
 }
 

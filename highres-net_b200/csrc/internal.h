@@ -35,6 +35,7 @@ struct ConvArgs {
     int n_img, H, W;
     int cin, cout;            // cin in {64, 128}; cout in {64, 128}
     int max_ctas;             // 0 = one CTA per SM; tests shrink it to force odd strip boundaries
+    int debug_flags;          // perf triage only: 1 = no TMEM load, 2 = no stores, 4 = no TMA loads, 8 = no residual loads
     // A operand gather.  pair_mode: output image m = (b, i) reads chunk 0 from view i and chunk 1 from
     // view top-1-i of the 64-channel view stack (HRNet.py:114-119); otherwise chunk c = channels [64c, 64c+64).
     int pair_mode, half, src_views, top;
@@ -62,10 +63,12 @@ int median_anchor_launch(const float* lrs, int B, int L, int H, int W, float* an
 // conv 2->64 + PReLU on (view, anchor) pairs; writes bf16 NHWC (B*L, H, W, 64).  w: (64, 2, 3, 3) fp32 device.
 int conv_init_launch(const float* lrs, const float* anchor, int B, int L, int H, int W, const float* w,
                      const float* bias, float prelu, __nv_bfloat16* out, cudaStream_t s);
-// stride-3 deconv + PReLU + 1x1 conv, fused; in: bf16 NHWC (B, H, W, 64) -> out fp32 (B, 3H, 3W).
-// wd: (9, 64 co, 64 ci) fp32 device (repacked), bd (64), wf (64), bf scalar.
-int decoder_launch(const __nv_bfloat16* in, int B, int H, int W, const float* wd, const float* bd, float prelu,
-                   const float* wf, float bf, float* out, cudaStream_t s);
+// decoder_umma.cu: stride-3 deconv + PReLU + 1x1 conv fused on the tensor cores; in: bf16 NHWC (B, H, W, 64) ->
+// out fp32 (B, 3H, 3W).  w_img = decoder_pack_weights() image (device), bd (64), wf (64) fp32 device.
+int decoder_weight_image_bytes();
+void decoder_pack_weights(const float* w_ci_co_ky_kx, uint8_t* dst);
+int decoder_umma_launch(const __nv_bfloat16* in, int B, int H, int W, const uint8_t* w_img, const float* bd, float prelu,
+                        const float* wf, float bf, float* out, int sm_count, cudaStream_t s);
 int nhwc_bf16_to_nchw_f32_launch(const __nv_bfloat16* in, int n, int H, int W, int C, float* out, cudaStream_t s);
 
 // ------------------------------------------------------------------ scoring

@@ -1,9 +1,7 @@
 // CUDA-core kernels of the HRNet path that are HBM-bound (or tiny) rather than
 // dense contractions: the median anchor (HRNet.py:200), the 2->64 first conv on
-// (view, anchor) pairs with the repeat/cat of HRNet.py:201-204 fused away, the
-// decoder (stride-3 deconv + PReLU + 1x1 conv, HRNet.py:147-156, fused so that the
-// 64 x 3H x 3W tensor is never materialised) and a layout-conversion helper used
-// by the stage-dump test hook.
+// (view, anchor) pairs with the repeat/cat of HRNet.py:201-204 fused away, and a
+// layout-conversion helper used by the stage-dump test hook.
 #include "internal.h"
 
 namespace hrn {
@@ -111,71 +109,6 @@ conv_init_kernel(const float* __restrict__ lrs, const float* __restrict__ anchor
     }
 }
 
-// ------------------------------------------------------------------ decoder (CUDA-core version)
-// stride == kernel (3) => no overlap: every LR pixel produces its own 3x3 HR block:
-//   sr[3y+ky, 3x+kx] = bf + sum_co wf[co] * PReLU(bd[co] + sum_ci in[ci] * Wd[ci, co, ky, kx])
-// Block = 128 LR pixels (one per thread); the repacked deconv weight for ONE (ky, kx)
-// position at a time (64 x 64 fp32 = 16 KB) is staged in shared memory.
-constexpr int DEC_THREADS = 128;
-__global__ void __launch_bounds__(DEC_THREADS)
-decoder_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, size_t npix, const float* __restrict__ wd,
-               const float* __restrict__ bd, float prelu, const float* __restrict__ wf, float bf,
-               float* __restrict__ out) {
-    __shared__ __align__(16) float wsm[64][64];   // [co][ci] of the current position
-    __shared__ float bds[64], wfs[64];
-    const size_t pix = blockIdx.x * static_cast<size_t>(DEC_THREADS) + threadIdx.x;
-    const bool valid = pix < npix;
-    if (threadIdx.x < 64) {
-        bds[threadIdx.x] = __ldg(bd + threadIdx.x);
-        wfs[threadIdx.x] = __ldg(wf + threadIdx.x);
-    }
-    float xin[64];
-    if (valid) {
-        const uint4* ip = reinterpret_cast<const uint4*>(in + pix * 64);
-#pragma unroll
-        for (int v = 0; v < 8; ++v) {
-            const uint4 raw = __ldg(ip + v);
-            const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float2 f = __bfloat1622float2(r2[e]);
-                xin[v * 8 + 2 * e] = f.x;
-                xin[v * 8 + 2 * e + 1] = f.y;
-            }
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 64; ++i) xin[i] = 0.0f;
-    }
-    const size_t hw = static_cast<size_t>(H) * W;
-    const size_t b = valid ? pix / hw : 0;
-    const int y = valid ? static_cast<int>((pix % hw) / W) : 0, x = valid ? static_cast<int>(pix % W) : 0;
-    float* obase = out + b * 9 * hw + (static_cast<size_t>(3 * y) * (3 * W) + 3 * x);
-    for (int pos = 0; pos < 9; ++pos) {
-        __syncthreads();
-        const float4* wsrc = reinterpret_cast<const float4*>(wd + static_cast<size_t>(pos) * 4096);
-        float4* wdst = reinterpret_cast<float4*>(&wsm[0][0]);
-        for (int i = threadIdx.x; i < 1024; i += DEC_THREADS) wdst[i] = __ldg(wsrc + i);
-        __syncthreads();
-        float sr = bf;
-#pragma unroll 4
-        for (int co = 0; co < 64; ++co) {
-            float acc = bds[co];
-#pragma unroll
-            for (int c4 = 0; c4 < 16; ++c4) {
-                const float4 wv = *reinterpret_cast<const float4*>(&wsm[co][c4 * 4]);
-                acc = fmaf(xin[c4 * 4 + 0], wv.x, acc);
-                acc = fmaf(xin[c4 * 4 + 1], wv.y, acc);
-                acc = fmaf(xin[c4 * 4 + 2], wv.z, acc);
-                acc = fmaf(xin[c4 * 4 + 3], wv.w, acc);
-            }
-            acc = acc >= 0.0f ? acc : prelu * acc;
-            sr = fmaf(wfs[co], acc, sr);
-        }
-        if (valid) obase[static_cast<size_t>(pos / 3) * (3 * W) + (pos % 3)] = sr;
-    }
-}
-
 // ------------------------------------------------------------------ bf16 NHWC -> fp32 NCHW (test hook)
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, size_t hw, int C, size_t total,
                                     float* __restrict__ out) {
@@ -207,16 +140,6 @@ int conv_init_launch(const float* lrs, const float* anchor, int B, int L, int H,
     }
     dim3 grid((W + CI_TX - 1) / CI_TX, (H + CI_TY - 1) / CI_TY, static_cast<unsigned>(imgs));
     conv_init_kernel<<<grid, dim3(CI_TX, CI_TY), 0, s>>>(lrs, anchor, L, H, W, w, bias, prelu, out);
-    note_launches(1);
-    HRN_CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
-int decoder_launch(const __nv_bfloat16* in, int B, int H, int W, const float* wd, const float* bd, float prelu,
-                   const float* wf, float bf, float* out, cudaStream_t s) {
-    const size_t npix = static_cast<size_t>(B) * H * W;
-    decoder_kernel<<<static_cast<unsigned>((npix + DEC_THREADS - 1) / DEC_THREADS), DEC_THREADS, 0, s>>>(
-        in, H, W, npix, wd, bd, prelu, wf, bf, out);
     note_launches(1);
     HRN_CUDA_OK(cudaGetLastError());
     return 0;

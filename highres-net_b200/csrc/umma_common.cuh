@@ -1,0 +1,55 @@
+// Shared by the tcgen05 kernels (conv3x3_umma.cu, decoder_umma.cu): descriptor helpers and the host-side
+// TMA tensor-map encoder for bf16 NHWC activation tensors.
+#pragma once
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace hrn {
+
+// K-major SWIZZLE_128B shared-memory descriptor: only the low word (start address) varies.
+constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_desc(uint32_t lo) { return (static_cast<uint64_t>(DESC_HI) << 32) | lo; }
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return (saddr >> 4) | (1u << 16); }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 4-D map over a bf16 NHWC tensor (dims fastest first: C, W, H, N); box = 64 channels x box_pixels x 1 x 1,
+// SWIZZLE_128B, out-of-bounds elements read as zero (that is the conv padding).
+inline int encode_nhwc_map(CUtensorMap* map, const void* base, int channels, int W, int H, int images, int box_pixels) {
+    EncodeTiledFn encode = get_encode_fn();
+    if (encode == nullptr) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return -1;
+    }
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(channels), static_cast<cuuint64_t>(W),
+                                static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(images)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(channels) * 2, static_cast<cuuint64_t>(W) * channels * 2,
+                                   static_cast<cuuint64_t>(H) * W * channels * 2};
+    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_pixels), 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (dims %d x %d x %d x %d)", (int)r, channels, W, H, images);
+        return -1;
+    }
+    return 0;
+}
+
+}  // namespace hrn
