@@ -269,10 +269,16 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
         }
     } else if (warp >= 4) {
         // ===================================================== epilogue: 8 warps, (lane quadrant) x (column half)
+        // Per thread and output row: one pixel x 32 channels.  Bias and PReLU in fp32 on the accumulators, one
+        // rounding to bf16, then the residual / alpha merge as a packed bf16x2 FMA; 256-bit global loads/stores.
         const int wq = warp & 3;                 // TMEM lanes [32 wq, 32 wq + 32)
         const int hf = (warp - 4) >> 2;          // accumulator columns [32 hf, 32 hf + 32)
         const int co0 = part * NT + hf * 32;     // first output channel handled by this thread
-        constexpr int VEC = 4;                   // 4 x 16 B = 32 bf16 per pixel
+        float bias_r[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) bias_r[e] = bias_s[hf * 32 + e];
+        const bool has_prelu = a.has_prelu != 0;
+        const float slope_m1 = a.prelu - 1.0f;   // PReLU(v) = v + (slope - 1) * min(v, 0)
         uint32_t tile = 0;
         StripWalker walk(geo, group, a.H);
         Strip s;
@@ -297,15 +303,18 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
                 res_c = 64;
                 scale = a.alphas[b * a.alpha_stride + (a.top - 1 - i)];
             }
-            for (int i = 0; i < s.rows; ++i, ++tile) {
+            const bool use_res = res_img != nullptr && valid && !(a.debug_flags & 8);
+            const __nv_bfloat162 scale2 = __floats2bfloat162_rn(scale, scale);
+            const size_t pix0 = static_cast<size_t>(s.y0) * a.W + x;
+            const __nv_bfloat16* rp = res_img + pix0 * res_c;
+            __nv_bfloat16* op = a.out + (static_cast<size_t>(s.m) * a.H * a.W + pix0) * a.cout + co0;
+            const size_t r_step = static_cast<size_t>(a.W) * res_c, o_step = static_cast<size_t>(a.W) * a.cout;
+            for (int i = 0; i < s.rows; ++i, ++tile, rp += r_step, op += o_step) {
                 const uint32_t acc = tile % ACC_SLOTS, aph = (tile / ACC_SLOTS) & 1;
-                const int y = s.y0 + i;
-                const size_t pix = static_cast<size_t>(y) * a.W + x;
-                uint4 rv[VEC];
-                if (res_img != nullptr && valid && !(a.debug_flags & 8)) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(res_img + pix * res_c);
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) rv[v] = __ldg(rp + v);
+                uint32_t rv[2][8];
+                if (use_res) {
+                    ptx::ldg_nc_v8(rp, rv[0]);
+                    ptx::ldg_nc_v8(rp + 16, rv[1]);
                 }
                 ptx::mbar_wait(bar_tfull + 8 * acc, aph, 5);
                 ptx::tc_fence_after();
@@ -320,33 +329,22 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(bar_tempty + 8 * acc);
-                if (valid && !(a.debug_flags & 2)) {
-                    uint4* op = reinterpret_cast<uint4*>(a.out + (static_cast<size_t>(s.m) * a.H * a.W + pix) * a.cout + co0);
+                uint32_t o[2][8];
 #pragma unroll
-                    for (int vv = 0; vv < VEC; ++vv) {
-                        float f[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int ch = vv * 8 + e;
-                            float val = __uint_as_float(v[ch]) + bias_s[hf * 32 + ch];
-                            if (a.has_prelu) val = val >= 0.0f ? val : a.prelu * val;
-                            f[e] = val;
-                        }
-                        if (res_img != nullptr) {
-                            const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv[vv]);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float2 rf = __bfloat1622float2(r2[e]);
-                                f[2 * e] = rf.x + scale * f[2 * e];
-                                f[2 * e + 1] = rf.y + scale * f[2 * e + 1];
-                            }
-                        }
-                        uint4 o;
-                        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-                        op[vv] = o;
+                for (int e = 0; e < 16; ++e) {
+                    float x0 = __uint_as_float(v[2 * e]) + bias_r[2 * e];
+                    float x1 = __uint_as_float(v[2 * e + 1]) + bias_r[2 * e + 1];
+                    if (has_prelu) {
+                        x0 = fmaf(slope_m1, fminf(x0, 0.0f), x0);
+                        x1 = fmaf(slope_m1, fminf(x1, 0.0f), x1);
                     }
+                    __nv_bfloat162 y = __floats2bfloat162_rn(x0, x1);
+                    if (use_res) y = __hfma2(scale2, y, *reinterpret_cast<const __nv_bfloat162*>(&rv[e >> 3][e & 7]));
+                    o[e >> 3][e & 7] = *reinterpret_cast<const uint32_t*>(&y);
+                }
+                if (valid && !(a.debug_flags & 2)) {
+                    ptx::stg_v8(op, o[0]);
+                    ptx::stg_v8(op + 16, o[1]);
                 }
             }
         }

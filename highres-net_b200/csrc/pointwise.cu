@@ -37,26 +37,28 @@ __global__ void median_anchor_kernel(const float* __restrict__ lrs, int L, int k
 }
 
 // ------------------------------------------------------------------ conv 2 -> 64 + PReLU
-// Block = 32 x 8 output pixels of one (imageset, view).  Input channel 0 is the view,
-// channel 1 the per-imageset anchor.  fp32 math, bf16 NHWC store (128 B per pixel).
-constexpr int CI_TX = 32, CI_TY = 8;
+// Block = 64 x 8 output pixels of one (imageset, view), two horizontally adjacent pixels per thread so that every
+// weight vector fetched from shared memory feeds two pixels.  Input channel 0 is the view, channel 1 the
+// per-imageset anchor.  fp32 math, bf16 NHWC store (128 B per pixel, 256-bit stores).
+constexpr int CI_TX = 32, CI_TY = 8, CI_PX = 2;
 __global__ void __launch_bounds__(CI_TX* CI_TY)
 conv_init_kernel(const float* __restrict__ lrs, const float* __restrict__ anchor, int L, int H, int W,
                  const float* __restrict__ w, const float* __restrict__ bias, float prelu,
                  __nv_bfloat16* __restrict__ out) {
-    __shared__ float tile[2][CI_TY + 2][CI_TX + 2];
+    constexpr int TW = CI_TX * CI_PX;
+    __shared__ float tile[2][CI_TY + 2][TW + 2];
     __shared__ __align__(16) float ws[18][64];   // [ci*9 + tap][co]
     __shared__ float bs[64];
     const int m = blockIdx.z;                    // image index b * L + view
     const int b = m / L;
-    const int x0 = blockIdx.x * CI_TX, y0 = blockIdx.y * CI_TY;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * CI_TY;
     const int tid = threadIdx.y * CI_TX + threadIdx.x;
     const size_t hw = static_cast<size_t>(H) * W;
     const float* src0 = lrs + static_cast<size_t>(m) * hw;
     const float* src1 = anchor + static_cast<size_t>(b) * hw;
-    for (int i = tid; i < 2 * (CI_TY + 2) * (CI_TX + 2); i += CI_TX * CI_TY) {
-        const int c = i / ((CI_TY + 2) * (CI_TX + 2));
-        const int r = (i / (CI_TX + 2)) % (CI_TY + 2), q = i % (CI_TX + 2);
+    for (int i = tid; i < 2 * (CI_TY + 2) * (TW + 2); i += CI_TX * CI_TY) {
+        const int c = i / ((CI_TY + 2) * (TW + 2));
+        const int r = (i / (TW + 2)) % (CI_TY + 2), q = i % (TW + 2);
         const int y = y0 + r - 1, x = x0 + q - 1;
         float v = 0.0f;
         if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg((c ? src1 : src0) + static_cast<size_t>(y) * W + x);
@@ -68,44 +70,51 @@ conv_init_kernel(const float* __restrict__ lrs, const float* __restrict__ anchor
     }
     if (tid < 64) bs[tid] = __ldg(bias + tid);
     __syncthreads();
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    if (x >= W || y >= H) return;
-    float in[18];
+    const int xa = x0 + CI_PX * threadIdx.x, y = y0 + threadIdx.y;
+    if (xa >= W || y >= H) return;
+    float in[2][18];                                // [pixel][ci*9 + ky*3 + kx]
 #pragma unroll
     for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) in[c * 9 + ky * 3 + kx] = tile[c][threadIdx.y + ky][threadIdx.x + kx];
-    uint4* op = reinterpret_cast<uint4*>(out + (static_cast<size_t>(m) * hw + static_cast<size_t>(y) * W + x) * 64);
+            for (int kx = 0; kx < 4; ++kx) {
+                const float v = tile[c][threadIdx.y + ky][CI_PX * threadIdx.x + kx];
+                if (kx < 3) in[0][c * 9 + ky * 3 + kx] = v;
+                if (kx > 0) in[1][c * 9 + ky * 3 + kx - 1] = v;
+            }
+    const float slope_m1 = prelu - 1.0f;
+    __nv_bfloat16* op = out + (static_cast<size_t>(m) * hw + static_cast<size_t>(y) * W + xa) * 64;
+    const bool second = xa + 1 < W;
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
-        float acc[8];
+        float acc[2][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = bs[g * 8 + e];
+        for (int e = 0; e < 8; ++e) acc[0][e] = acc[1][e] = bs[g * 8 + e];
 #pragma unroll
         for (int k = 0; k < 18; ++k) {
             const float4 wa = *reinterpret_cast<const float4*>(&ws[k][g * 8]);
             const float4 wb = *reinterpret_cast<const float4*>(&ws[k][g * 8 + 4]);
-            acc[0] = fmaf(in[k], wa.x, acc[0]);
-            acc[1] = fmaf(in[k], wa.y, acc[1]);
-            acc[2] = fmaf(in[k], wa.z, acc[2]);
-            acc[3] = fmaf(in[k], wa.w, acc[3]);
-            acc[4] = fmaf(in[k], wb.x, acc[4]);
-            acc[5] = fmaf(in[k], wb.y, acc[5]);
-            acc[6] = fmaf(in[k], wb.z, acc[6]);
-            acc[7] = fmaf(in[k], wb.w, acc[7]);
-        }
-        uint4 o;
-        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+            const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float p0 = acc[2 * e], p1 = acc[2 * e + 1];
-            p0 = p0 >= 0.0f ? p0 : prelu * p0;
-            p1 = p1 >= 0.0f ? p1 : prelu * p1;
-            o2[e] = __floats2bfloat162_rn(p0, p1);
+            for (int e = 0; e < 8; ++e) {
+                acc[0][e] = fmaf(in[0][k], wv[e], acc[0][e]);
+                acc[1][e] = fmaf(in[1][k], wv[e], acc[1][e]);
+            }
         }
-        op[g] = o;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            uint4 o;
+            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float p0 = acc[p][2 * e], p1 = acc[p][2 * e + 1];
+                p0 = fmaf(slope_m1, fminf(p0, 0.0f), p0);      // PReLU(v) = v + (slope - 1) min(v, 0)
+                p1 = fmaf(slope_m1, fminf(p1, 0.0f), p1);
+                o2[e] = __floats2bfloat162_rn(p0, p1);
+            }
+            if (p == 0 || second) *reinterpret_cast<uint4*>(op + p * 64 + g * 8) = o;
+        }
     }
 }
 
@@ -138,7 +147,7 @@ int conv_init_launch(const float* lrs, const float* anchor, int B, int L, int H,
         set_error("conv_init: B*L = %lld exceeds the grid z limit (65535); split the batch", imgs);
         return -1;
     }
-    dim3 grid((W + CI_TX - 1) / CI_TX, (H + CI_TY - 1) / CI_TY, static_cast<unsigned>(imgs));
+    dim3 grid((W + CI_TX * CI_PX - 1) / (CI_TX * CI_PX), (H + CI_TY - 1) / CI_TY, static_cast<unsigned>(imgs));
     conv_init_kernel<<<grid, dim3(CI_TX, CI_TY), 0, s>>>(lrs, anchor, L, H, W, w, bias, prelu, out);
     note_launches(1);
     HRN_CUDA_OK(cudaGetLastError());
