@@ -92,6 +92,75 @@ lanczos_shift_kernel(const float* __restrict__ img, const float* __restrict__ sh
     }
 }
 
+// N = 7 specialisation (the only width the reference uses): 128 x 32 output tile per block, rows walked warp by
+// warp so that no index needs a division, x pass computes four outputs per thread from three 128-bit shared-memory
+// reads and stores them as one float4.
+constexpr int L7_TW = 128, L7_TH = 32, L7_THREADS = 256, L7_HALF = 3;
+constexpr int L7_INW = L7_TW + 2 * L7_HALF, L7_INH = L7_TH + 2 * L7_HALF, L7_PITCH = L7_INW + 2;   // 134, 38, 136
+
+__global__ void __launch_bounds__(L7_THREADS)
+lanczos_shift7_kernel(const float* __restrict__ img, const float* __restrict__ shift, int C, int H, int W, int p, int a,
+                      float* __restrict__ out) {
+    __shared__ __align__(16) float tile[L7_INH][L7_PITCH];
+    __shared__ __align__(16) float tmp[L7_TH][L7_PITCH];
+    __shared__ float taps[2][MAX_TAPS];
+    const int plane = blockIdx.z, c = plane % C;
+    const int x0 = blockIdx.x * L7_TW, y0 = blockIdx.y * L7_TH;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* src = img + static_cast<size_t>(plane) * H * W;
+    if (threadIdx.x < 2) lanczos_taps_device(shift[c * 2 + threadIdx.x], a, 7, taps[threadIdx.x]);
+    for (int r = warp; r < L7_INH; r += L7_THREADS / 32) {
+        bool oky;
+        const int yy = padded_index(y0 + r - L7_HALF, H, p, &oky);
+        const float* row = src + static_cast<size_t>(yy) * W;
+        for (int q = lane; q < L7_INW; q += 32) {
+            bool okx;
+            const int xx = padded_index(x0 + q - L7_HALF, W, p, &okx);
+            tile[r][q] = (oky && okx) ? __ldg(row + xx) : 0.0f;
+        }
+    }
+    __syncthreads();
+    float ky[7], kx[7];
+#pragma unroll
+    for (int t = 0; t < 7; ++t) {
+        ky[t] = taps[0][t];
+        kx[t] = taps[1][t];
+    }
+    for (int r = warp; r < L7_TH; r += L7_THREADS / 32) {            // y pass (dim 0 taps first, lanczos.py:90)
+        for (int q = lane; q < L7_INW; q += 32) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int t = 0; t < 7; ++t) acc = fmaf(ky[t], tile[r + t][q], acc);
+            tmp[r][q] = acc;
+        }
+    }
+    __syncthreads();
+    const bool vec_ok = (W & 3) == 0;
+    for (int r = warp; r < L7_TH; r += L7_THREADS / 32) {            // x pass (lanczos.py:94), 4 outputs per thread
+        const int y = y0 + r, x = x0 + 4 * lane;
+        if (y >= H || x >= W) continue;
+        float v[12];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) *reinterpret_cast<float4*>(&v[4 * k]) = *reinterpret_cast<const float4*>(&tmp[r][4 * lane + 4 * k]);
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int t = 0; t < 7; ++t) acc = fmaf(kx[t], v[e + t], acc);
+            o[e] = acc;
+        }
+        float* dst = out + static_cast<size_t>(plane) * H * W + static_cast<size_t>(y) * W + x;
+        if (vec_ok && x + 3 < W) {
+            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (x + e < W) dst[e] = o[e];
+        }
+    }
+}
+
 // ------------------------------------------------------------------ cPSNR shift search
 constexpr int CP_COLS = 32;       // crop columns per block (threadIdx.x)
 constexpr int CP_MAXS = 7;        // shifts per axis supported (border_w <= 3)
@@ -232,10 +301,16 @@ int lanczos_shift_launch(const float* img, const float* shift, int nb, int c, in
         set_error("lanczos_shift: %lld planes outside [1, 65535]", planes);
         return -1;
     }
-    const int half = ntaps / 2;
-    const size_t smem = (static_cast<size_t>(LZ_TH + 2 * half) + LZ_TH) * (LZ_TW + 2 * half) * sizeof(float);
-    dim3 grid((W + LZ_TW - 1) / LZ_TW, (H + LZ_TH - 1) / LZ_TH, static_cast<unsigned>(planes));
-    lanczos_shift_kernel<<<grid, LZ_THREADS, smem, s>>>(img, shift, c, H, W, p, a, ntaps, out);
+    if (ntaps == 7) {
+        // the width the reference uses everywhere (ShiftNet.py:87-89): compile-time tile geometry
+        dim3 grid((W + L7_TW - 1) / L7_TW, (H + L7_TH - 1) / L7_TH, static_cast<unsigned>(planes));
+        lanczos_shift7_kernel<<<grid, L7_THREADS, 0, s>>>(img, shift, c, H, W, p, a, out);
+    } else {
+        const int half = ntaps / 2;
+        const size_t smem = (static_cast<size_t>(LZ_TH + 2 * half) + LZ_TH) * (LZ_TW + 2 * half) * sizeof(float);
+        dim3 grid((W + LZ_TW - 1) / LZ_TW, (H + LZ_TH - 1) / LZ_TH, static_cast<unsigned>(planes));
+        lanczos_shift_kernel<<<grid, LZ_THREADS, smem, s>>>(img, shift, c, H, W, p, a, ntaps, out);
+    }
     note_launches(1);
     HRN_CUDA_OK(cudaGetLastError());
     return 0;
