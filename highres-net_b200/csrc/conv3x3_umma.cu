@@ -192,6 +192,80 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
                 Strip nxt;
                 const bool have_next = walk.next(nxt);
                 for (int q = 0; q < s.rows + 2; ++q) {
+                    if (q >= 2 && q <= s.rows - 1) {
+                        // ---- interior row (the bulk of the work): all three ky blocks are live and block 2 opens the
+                        // accumulator of output row q.  Everything is derived from the slot of the oldest tile.
+                        const uint32_t t_new = tile0 + q;
+                        const uint32_t sl = (t_new - 2) % ACC_SLOTS;             // slot of output row q - 2
+                        if (!tempty_seen)
+                            ptx::mbar_wait(bar_tempty + 8 * (t_new % ACC_SLOTS), ((t_new / ACC_SLOTS) & 1) ^ 1, 4);
+                        tempty_seen = false;
+                        const bool nxt_opens = (q + 1 <= s.rows - 1);
+#pragma unroll
+                        for (int c = 0; c < C::CHUNKS; ++c, ++it) {
+                            const uint32_t slot = it % C::RING;
+                            if (!full_seen) ptx::mbar_wait(bar_full + 8 * slot, (it / C::RING) & 1, 3);
+                            full_seen = false;
+                            ptx::tc_fence_after();
+                            uint64_t ad = make_desc(a_lo0 + slot * (CHUNK_BYTES / 16));
+                            uint64_t bd = make_desc(b_lo0 + c * (BTILE_BYTES / 16));
+                            const uint32_t dA = tmem_base + sl * NT;
+                            // early waits for the next item, issued after k-step 7 while the MMA queue is full
+                            auto early = [&]() {
+                                const uint32_t itn = it + 1;
+                                ptx::mbar_wait(bar_full + 8 * (itn % C::RING), (itn / C::RING) & 1, 6);
+                                full_seen = true;
+                                if (c + 1 == C::CHUNKS && nxt_opens) {
+                                    const uint32_t tn = t_new + 1;
+                                    ptx::mbar_wait(bar_tempty + 8 * (tn % ACC_SLOTS), ((tn / ACC_SLOTS) & 1) ^ 1, 7);
+                                    tempty_seen = true;
+                                }
+                            };
+                            if (sl <= ACC_SLOTS - 3) {
+                                // slots sl, sl+1, sl+2 are contiguous: one N = 192 MMA per k-step
+                                if (c == 0) {
+                                    ptx::umma_bf16(dA, ad, bd, idesc_base | ((2 * NT >> 3) << 17), 1u);
+                                    ptx::umma_bf16(dA + 2 * NT, ad, bd + 2 * BLK, idesc64, 0u);
+                                } else {
+                                    ptx::umma_bf16(dA, ad, bd, idesc_base | ((3 * NT >> 3) << 17), 1u);
+                                }
+#pragma unroll
+                                for (int step = 1; step < 12; ++step) {
+                                    ad += 2;
+                                    bd += (step & 3) ? 2u : B_KX;
+                                    ptx::umma_bf16(dA, ad, bd, idesc_base | ((3 * NT >> 3) << 17), 1u);
+                                    if (step == 7) early();
+                                }
+                            } else {
+                                // wrap: sl = 6 -> blocks {0,1} at slots 6,7 and block 2 at slot 0;
+                                //       sl = 7 -> block 0 at slot 7 and blocks {1,2} at slots 0,1
+                                const uint32_t n0 = (sl == ACC_SLOTS - 2) ? 2u : 1u, n1 = 3u - n0;
+                                const uint32_t id0 = idesc_base | ((n0 * NT >> 3) << 17), id1 = idesc_base | ((n1 * NT >> 3) << 17);
+                                uint64_t bd1 = bd + n0 * BLK;
+                                if (c == 0) {
+                                    ptx::umma_bf16(dA, ad, bd, id0, 1u);
+                                    if (n1 == 2) ptx::umma_bf16(tmem_base, ad, bd1, idesc64, 1u);
+                                    ptx::umma_bf16(tmem_base + (n1 - 1) * NT, ad, bd + 2 * BLK, idesc64, 0u);
+                                } else {
+                                    ptx::umma_bf16(dA, ad, bd, id0, 1u);
+                                    ptx::umma_bf16(tmem_base, ad, bd1, id1, 1u);
+                                }
+#pragma unroll
+                                for (int step = 1; step < 12; ++step) {
+                                    ad += 2;
+                                    bd += (step & 3) ? 2u : B_KX;
+                                    bd1 += (step & 3) ? 2u : B_KX;
+                                    ptx::umma_bf16(dA, ad, bd, id0, 1u);
+                                    ptx::umma_bf16(tmem_base, ad, bd1, id1, 1u);
+                                    if (step == 7) early();
+                                }
+                            }
+                            ptx::umma_commit(bar_empty + 8 * slot);
+                            if (c == C::CHUNKS - 1) ptx::umma_commit(bar_tfull + 8 * sl);
+                        }
+                        continue;
+                    }
+                    // ---- boundary rows of a strip (q = 0, 1, rows, rows + 1, or very short strips): generic path
                     // Input row q feeds output rows o = q - ky.  B block (2 - ky) <-> output row q - ky, so the blocks
                     // [blk_lo, blk_lo + nblk) map to the consecutive accumulators (tiles) t_lo, t_lo + 1, ...
                     const int ky_lo = max(0, q - (s.rows - 1)), ky_hi = min(2, q);

@@ -50,12 +50,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return done != 0;
 }
-// Bounded wait: a pipeline bug must surface as a CUDA error, never as a hung GPU.
+// Bounded wait: a pipeline bug must surface as a CUDA error, never as a hung GPU.  The retry loop lives out of
+// line so that the common case (barrier already complete) costs one TRYWAIT and one branch at the call site.
 #ifndef HRN_WAIT_LIMIT_CYCLES
 #define HRN_WAIT_LIMIT_CYCLES (4000000000LL)   // ~2 s at 1.9 GHz
 #endif
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
-    if (mbar_try_wait(bar, parity)) return;
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int tag) {
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > HRN_WAIT_LIMIT_CYCLES) {
@@ -64,6 +64,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
             __trap();
         }
     }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, tag);
 }
 
 // ---------------------------------------------------------------- TMA
