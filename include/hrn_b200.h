@@ -68,7 +68,8 @@ int32_t hrn_forward(hrn_handle* h, const float* lrs, const float* alphas, int32_
                     int32_t W, float* sr, void* stream);
 
 /* Same with HOST buffers (the train.py:200-208 / predict.py:36-40 pattern: H2D of
- * lrs/alphas, forward, D2H of sr), synchronous.  Pinned host memory is used as is. */
+ * lrs/alphas, forward, D2H of sr), synchronous.  The batch is cut into chunks whose copies overlap the
+ * kernels of the neighbouring chunks (pinned host memory is needed for that overlap; pageable works too). */
 int32_t hrn_forward_host(hrn_handle* h, const float* lrs_host, const float* alphas_host, int32_t B, int32_t L,
                          int32_t H, int32_t W, float* sr_host, void* stream);
 
@@ -105,7 +106,9 @@ int32_t hrn_forward_dump(hrn_handle* h, const float* lrs, const float* alphas, i
                          int32_t W, float* sr, int32_t stage, float* dump, void* stream);
 
 /* Test knobs.  "max_ctas" = N > 0 limits the tcgen05 conv kernels to N CTAs (0 = one per SM), which moves
- * the strip boundaries of the row partition; results must not change. */
+ * the strip boundaries of the row partition; results must not change.  "host_chunks" = pipeline depth of
+ * hrn_forward_host (0 = automatic, 1 = no overlap).  "debug_flags" disables parts of the conv kernel for
+ * performance triage (results are then garbage). */
 int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value);
 
 /* Per-launch device timing of HRNet.forward, by kernel class, with CUDA events recorded on the stream the

@@ -178,6 +178,21 @@ def test_forward_host_equals_device_path(net, dev):
     assert torch.equal(a, b)
 
 
+def test_forward_host_pipeline_depths(hb, dev):
+    """hrn_forward_host cuts the batch into chunks whose copies overlap compute; any depth gives identical output."""
+    model = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval()
+    model.load_state_dict(hrnet_oracle.make_params(cases.WEIGHT_SEED))
+    model = model.to(dev)
+    g = torch.Generator().manual_seed(8)
+    lrs, alphas = torch.rand(7, 4, 32, 32, generator=g).pin_memory(), torch.ones(7, 4).pin_memory()
+    ref = model(lrs.to(dev), alphas.to(dev)).cpu()
+    for depth in (1, 2, 3, 8):
+        model.debug_set(dev, "host_chunks", depth)
+        assert torch.equal(model.forward_host(lrs, alphas, device=dev), ref), depth
+    model.debug_set(dev, "host_chunks", 0)
+    assert torch.equal(model.forward_host(lrs.clone(), alphas.clone(), device=dev), ref)    # pageable host memory too
+
+
 def test_forward_rejects_bad_inputs(hb, net, dev):
     with pytest.raises(RuntimeError):
         net(torch.rand(1, 2, 16, 16), torch.ones(1, 2))                  # CPU tensors: no fallback
