@@ -40,7 +40,8 @@ struct hrn_handle {
     std::set<std::string> have;
     int expected = 0;
     // first conv (2 -> 64) and decoder parameters (fp32, device)
-    float *w_init = nullptr, *b_init = nullptr;
+    uint8_t* w_init_img = nullptr;     // conv_init_pack_weights() image
+    float* b_init = nullptr;
     float prelu_init = 0.0f;
     std::vector<hrn::ConvLayer> enc;   // 2 * num_layers residual convs + the final conv
     hrn::ConvLayer fuse[3];
@@ -217,7 +218,7 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
     }
     {
         SpanGuard guard(h, s, HRN_PROF_CONV_INIT, 2.0 * 18.0 * 64.0 * static_cast<double>(n_img) * hw);
-        if (hrn::conv_init_launch(lrs, h->anchor, B, L, H, W, h->w_init, h->b_init, h->prelu_init, h->act[0], s)) return -1;
+        if (hrn::conv_init_umma_launch(lrs, h->anchor, B, L, H, W, h->w_init_img, h->b_init, h->prelu_init, h->act[0], h->sm_count, s)) return -1;
     }
     int stage = 0;
     if (maybe_dump(dump, HRN_STAGE_ENC(stage), h->act[0], static_cast<int>(n_img), H, W, 64, s)) return -1;
@@ -380,7 +381,7 @@ void hrn_destroy(hrn_handle* h) {
     auto rel = [](void* p) {
         if (p != nullptr) cudaFree(p);
     };
-    rel(h->w_init);
+    rel(h->w_init_img);
     rel(h->b_init);
     for (auto& l : h->enc) {
         rel(l.w_img);
@@ -422,7 +423,13 @@ int32_t hrn_set_weight(hrn_handle* h, const char* key, const float* data, const 
     int r = 0, j = 0;
     char tail[16] = "";
     if (k == "encode.init_layer.0.weight") {
-        rc = shape_is(shape, ndim, {64, 2, 3, 3}) ? upload(&h->w_init, data, 64 * 18) : -3;
+        if (shape_is(shape, ndim, {64, 2, 3, 3})) {
+            std::vector<uint8_t> img(hrn::conv_init_weight_image_bytes());
+            hrn::conv_init_pack_weights(data, img.data());
+            rc = 0;
+            if (h->w_init_img == nullptr && cudaMalloc(reinterpret_cast<void**>(&h->w_init_img), img.size()) != cudaSuccess) rc = -4;
+            if (rc == 0 && cudaMemcpy(h->w_init_img, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) rc = -4;
+        } else rc = -3;
     } else if (k == "encode.init_layer.0.bias") {
         rc = shape_is(shape, ndim, {64}) ? upload(&h->b_init, data, 64) : -3;
     } else if (k == "encode.init_layer.1.weight") {

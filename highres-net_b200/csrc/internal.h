@@ -60,9 +60,12 @@ int conv3x3_launch(const ConvArgs& a, int sm_count, cudaStream_t stream);
 
 // ------------------------------------------------------------------ pointwise / CUDA-core kernels
 int median_anchor_launch(const float* lrs, int B, int L, int H, int W, float* anchor, cudaStream_t s);
-// conv 2->64 + PReLU on (view, anchor) pairs; writes bf16 NHWC (B*L, H, W, 64).  w: (64, 2, 3, 3) fp32 device.
-int conv_init_launch(const float* lrs, const float* anchor, int B, int L, int H, int W, const float* w,
-                     const float* bias, float prelu, __nv_bfloat16* out, cudaStream_t s);
+// conv_init_umma.cu: conv 2->64 + PReLU on (view, anchor) pairs on the tensor cores (A operand built in smem with a
+// hi/lo bf16 split of the fp32 inputs); writes bf16 NHWC (B*L, H, W, 64).  w_img = conv_init_pack_weights() (device).
+int conv_init_weight_image_bytes();
+void conv_init_pack_weights(const float* w_co_ci_ky_kx, uint8_t* dst);
+int conv_init_umma_launch(const float* lrs, const float* anchor, int B, int L, int H, int W, const uint8_t* w_img,
+                          const float* bias, float prelu, __nv_bfloat16* out, int sm_count, cudaStream_t s);
 // decoder_umma.cu: stride-3 deconv + PReLU + 1x1 conv fused on the tensor cores; in: bf16 NHWC (B, H, W, 64) ->
 // out fp32 (B, 3H, 3W).  w_img = decoder_pack_weights() image (device), bd (64), wf (64) fp32 device.
 int decoder_weight_image_bytes();
