@@ -45,6 +45,20 @@ def synthetic_batch(b, l, s, seed, device=None, pin=False):
     return lrs, alphas
 
 
+def ncu_traffic_per_launch(kernel_class):
+    """DRAM bytes (read + write) per launch of a kernel class, averaged over the launches of one forward step, from the
+    committed `ncu --set full` capture (profiles/r01_ncu_full_summary.json); None if the capture is not there."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")
+    if not os.path.exists(path):
+        return None
+    tag = kernel_class.replace("conv3x3_umma", "conv3x3_umma_kernel")
+    with open(path) as f:
+        rows = [r for r in json.load(f) if tag in r["name"]]
+    if not rows:
+        return None
+    return sum((float(r["rd"]) + float(r["wr"])) * 1e9 for r in rows) / len(rows)
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -270,7 +284,9 @@ def main():
         step_ms = sum(v["ms"] for v in prof.values()) / prof_steps
         roofline = {
             "bound": "tensor", "kernel": dom, "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": ach / peaks["bf16_tflops"], "peak_source": peaks["source"], "traffic": None,
+            "frac": ach / peaks["bf16_tflops"], "peak_source": peaks["source"], "traffic": ncu_traffic_per_launch(dom),
+            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the launches of this class in one "
+                            "forward step (profiles/r01_ncu_full_summary.json); equals the activation bytes read + written once",
             "avg_launch_ms": prof[dom]["ms"] / max(prof[dom]["launches"], 1),
             "share_of_step": prof[dom]["ms"] / prof_steps / max(step_ms, 1e-9),
             "per_class": {k: {"ms_per_step": v["ms"] / prof_steps, "launches_per_step": v["launches"] / prof_steps,

@@ -92,16 +92,17 @@ lanczos_shift_kernel(const float* __restrict__ img, const float* __restrict__ sh
     }
 }
 
-// N = 7 specialisation (the only width the reference uses): 128 x 32 output tile per block, rows walked warp by
-// warp so that no index needs a division, x pass computes four outputs per thread from three 128-bit shared-memory
-// reads and stores them as one float4.
-constexpr int L7_TW = 128, L7_TH = 32, L7_THREADS = 256, L7_HALF = 3;
-constexpr int L7_INW = L7_TW + 2 * L7_HALF, L7_INH = L7_TH + 2 * L7_HALF, L7_PITCH = L7_INW + 2;   // 134, 38, 136
+// N = 7 specialisation (the only width the reference uses).  128 x 32 output tile per block.  The y pass runs
+// straight from global memory: each thread owns one column of the (128 + 6)-wide strip and slides a 7-row register
+// window down 16 output rows (22 coalesced loads for 16 outputs, nothing staged in shared memory); the x pass then
+// computes four outputs per thread from three 128-bit shared-memory reads and stores one float4.
+constexpr int L7_TW = 128, L7_TH = 32, L7_THREADS = 288, L7_HALF = 3;   // 288 >= 134 columns x 2 segments: one y-pass round
+constexpr int L7_INW = L7_TW + 2 * L7_HALF, L7_PITCH = L7_INW + 2;   // 134, 136
+constexpr int L7_SEG = 16;                                            // output rows per y-pass work item
 
 __global__ void __launch_bounds__(L7_THREADS)
 lanczos_shift7_kernel(const float* __restrict__ img, const float* __restrict__ shift, int C, int H, int W, int p, int a,
                       float* __restrict__ out) {
-    __shared__ __align__(16) float tile[L7_INH][L7_PITCH];
     __shared__ __align__(16) float tmp[L7_TH][L7_PITCH];
     __shared__ float taps[2][MAX_TAPS];
     const int plane = blockIdx.z, c = plane % C;
@@ -109,16 +110,6 @@ lanczos_shift7_kernel(const float* __restrict__ img, const float* __restrict__ s
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* src = img + static_cast<size_t>(plane) * H * W;
     if (threadIdx.x < 2) lanczos_taps_device(shift[c * 2 + threadIdx.x], a, 7, taps[threadIdx.x]);
-    for (int r = warp; r < L7_INH; r += L7_THREADS / 32) {
-        bool oky;
-        const int yy = padded_index(y0 + r - L7_HALF, H, p, &oky);
-        const float* row = src + static_cast<size_t>(yy) * W;
-        for (int q = lane; q < L7_INW; q += 32) {
-            bool okx;
-            const int xx = padded_index(x0 + q - L7_HALF, W, p, &okx);
-            tile[r][q] = (oky && okx) ? __ldg(row + xx) : 0.0f;
-        }
-    }
     __syncthreads();
     float ky[7], kx[7];
 #pragma unroll
@@ -126,12 +117,26 @@ lanczos_shift7_kernel(const float* __restrict__ img, const float* __restrict__ s
         ky[t] = taps[0][t];
         kx[t] = taps[1][t];
     }
-    for (int r = warp; r < L7_TH; r += L7_THREADS / 32) {            // y pass (dim 0 taps first, lanczos.py:90)
-        for (int q = lane; q < L7_INW; q += 32) {
+    // y pass (dim 0 taps first, lanczos.py:90): work item = (column q of the strip, 16-row segment)
+    for (int item = threadIdx.x; item < L7_INW * (L7_TH / L7_SEG); item += L7_THREADS) {
+        const int q = item % L7_INW, seg = item / L7_INW;
+        bool okx;
+        const int xx = padded_index(x0 + q - L7_HALF, W, p, &okx);
+        const int r0 = seg * L7_SEG;
+        // all 22 loads are issued before the first use (memory-level parallelism), then 16 outputs are formed
+        float col[L7_SEG + 6];
+#pragma unroll
+        for (int t = 0; t < L7_SEG + 6; ++t) {
+            bool oky;
+            const int yy = padded_index(y0 + r0 + t - L7_HALF, H, p, &oky);
+            col[t] = (oky && okx) ? __ldg(src + static_cast<size_t>(yy) * W + xx) : 0.0f;
+        }
+#pragma unroll
+        for (int r = 0; r < L7_SEG; ++r) {
             float acc = 0.0f;
 #pragma unroll
-            for (int t = 0; t < 7; ++t) acc = fmaf(ky[t], tile[r + t][q], acc);
-            tmp[r][q] = acc;
+            for (int t = 0; t < 7; ++t) acc = fmaf(ky[t], col[r + t], acc);
+            tmp[r0 + r][q] = acc;
         }
     }
     __syncthreads();
