@@ -9,7 +9,8 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "csrc", "libhrn_b200.so")
+# HRN_B200_LIB lets tools/ab.py load another build of the same ABI for same-box A/B timing
+_LIB_PATH = os.environ.get("HRN_B200_LIB") or os.path.join(_HERE, "csrc", "libhrn_b200.so")
 
 
 class HrnConfig(ctypes.Structure):
