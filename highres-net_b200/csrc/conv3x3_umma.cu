@@ -127,6 +127,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
         ptx::fence_barrier_init();
         ptx::prefetch_tensormap(&in_map);
     }
+    ptx::pdl_launch_dependents();            // the next kernel's prologue may overlap our tail
     if (warp == 2) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
     if (threadIdx.x >= 128 && threadIdx.x < 128 + NT) bias_s[threadIdx.x - 128] = a.bias[part * NT + threadIdx.x - 128];
     ptx::tc_fence_before();
@@ -140,6 +141,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
             ptx::mbar_expect_tx(bar_w, C::W_BYTES);
             const uint8_t* wsrc = a.w_img + static_cast<size_t>(part) * C::W_BYTES;
             for (int off = 0; off < C::W_BYTES; off += 8192) ptx::bulk_copy_g2s(w_s + off, wsrc + off, 8192, bar_w);
+            ptx::pdl_wait();                 // weights are constants; the activations come from the previous kernel
             uint32_t it = 0;
             StripWalker walk(geo, group, a.H);
             Strip s;
@@ -353,6 +355,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
         for (int e = 0; e < 32; ++e) bias_r[e] = bias_s[hf * 32 + e];
         const bool has_prelu = a.has_prelu != 0;
         const float slope_m1 = a.prelu - 1.0f;   // PReLU(v) = v + (slope - 1) * min(v, 0)
+        ptx::pdl_wait();                         // residual reads and output writes touch the previous kernel's tensors
         uint32_t tile = 0;
         StripWalker walk(geo, group, a.H);
         Strip s;
@@ -440,9 +443,8 @@ int launch_impl(const ConvArgs& a, const CUtensorMap& map, const Geometry& g, in
                                          C::SMEM_BYTES));
         attr_set = true;
     }
-    conv3x3_umma_kernel<CIN><<<ctas, NUM_THREADS, C::SMEM_BYTES, stream>>>(map, a, g);
+    HRN_CUDA_OK(launch_pdl(conv3x3_umma_kernel<CIN>, ctas, NUM_THREADS, C::SMEM_BYTES, stream, map, a, g));
     note_launches(1);
-    HRN_CUDA_OK(cudaGetLastError());
     return 0;
 }
 

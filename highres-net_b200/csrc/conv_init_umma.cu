@@ -66,6 +66,7 @@ conv_init_umma_kernel(const InitArgs a) {
         }
         ptx::fence_barrier_init();
     }
+    ptx::pdl_launch_dependents();
     if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
     // weights (8 KB) and bias: plain loads, then made visible to the tensor-core (async) proxy
     for (int i = threadIdx.x; i < W_BYTES / 16; i += NUM_THREADS)
@@ -125,6 +126,7 @@ conv_init_umma_kernel(const InitArgs a) {
             }
         };
         float v[18];
+        ptx::pdl_wait();                 // the anchor comes from the previous kernel
         const long long first = static_cast<long long>(blockIdx.x) + static_cast<long long>(set) * gridDim.x;
         const long long stride = 2LL * gridDim.x;
         if (first < a.tiles) gather(first, v);
@@ -160,6 +162,7 @@ conv_init_umma_kernel(const InitArgs a) {
         float bias_r[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) bias_r[e] = bias_s[hf * 32 + e];
+        ptx::pdl_wait();                 // the output buffer may still be read by the previous forward's kernels
         uint32_t it = 0;
         for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
             int m, y, xt;
@@ -233,9 +236,8 @@ int conv_init_umma_launch(const float* lrs, const float* anchor, int B, int L, i
         attr_set = true;
     }
     const int ctas = static_cast<int>(a.tiles < sm_count ? a.tiles : sm_count);
-    conv_init_umma_kernel<<<ctas, NUM_THREADS, SMEM_BYTES, s>>>(a);
+    HRN_CUDA_OK(launch_pdl(conv_init_umma_kernel, ctas, NUM_THREADS, SMEM_BYTES, s, a));
     note_launches(1);
-    HRN_CUDA_OK(cudaGetLastError());
     return 0;
 }
 

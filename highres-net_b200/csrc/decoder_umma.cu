@@ -59,6 +59,7 @@ decoder_umma_kernel(const __grid_constant__ CUtensorMap in_map, const DecArgs a)
         ptx::fence_barrier_init();
         ptx::prefetch_tensormap(&in_map);
     }
+    ptx::pdl_launch_dependents();
     if (warp == 2) ptx::tmem_alloc<512>(tmem_slot);
     if (threadIdx.x >= 128 && threadIdx.x < 192) {
         bd_s[threadIdx.x - 128] = a.bd[threadIdx.x - 128];
@@ -73,6 +74,7 @@ decoder_umma_kernel(const __grid_constant__ CUtensorMap in_map, const DecArgs a)
         if (ptx::elect_one()) {
             ptx::mbar_expect_tx(bar_w, W_BYTES);
             for (int off = 0; off < W_BYTES; off += 8192) ptx::bulk_copy_g2s(w_s + off, a.w_img + off, 8192, bar_w);
+            ptx::pdl_wait();
             uint32_t it = 0;
             for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
                 const int xt = static_cast<int>(t % a.x_tiles);
@@ -116,6 +118,7 @@ decoder_umma_kernel(const __grid_constant__ CUtensorMap in_map, const DecArgs a)
         const int wq = warp & 3;            // TMEM lane quadrant
         const int set = (warp - 4) >> 2;    // 0: even groups, 1: odd groups
         const float slope_m1 = a.prelu - 1.0f;
+        ptx::pdl_wait();
         uint32_t grp = 0;
         for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x) {
             const int xt = static_cast<int>(t % a.x_tiles);
@@ -203,9 +206,8 @@ int decoder_umma_launch(const __nv_bfloat16* in, int B, int H, int W, const uint
         attr_set = true;
     }
     const int ctas = static_cast<int>(a.tiles < sm_count ? a.tiles : sm_count);
-    decoder_umma_kernel<<<ctas, NUM_THREADS, SMEM_BYTES, s>>>(map, a);
+    HRN_CUDA_OK(launch_pdl(decoder_umma_kernel, ctas, NUM_THREADS, SMEM_BYTES, s, map, a));
     note_launches(1);
-    HRN_CUDA_OK(cudaGetLastError());
     return 0;
 }
 

@@ -4,6 +4,8 @@
 #include "internal.h"
 #include "ptx.cuh"
 
+#include <utility>
+
 namespace hrn {
 
 // K-major SWIZZLE_128B shared-memory descriptor: only the low word (start address) varies.
@@ -50,6 +52,24 @@ inline int encode_nhwc_map(CUtensorMap* map, const void* base, int channels, int
         return -1;
     }
     return 0;
+}
+
+// Launch with programmatic dependent launch enabled: the kernel's prologue (barrier init, TMEM allocation, weight
+// loads) overlaps the tail of the previous kernel in the stream; the kernel itself calls ptx::pdl_wait() before it
+// reads or writes any tensor the previous kernel may still be using.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 }  // namespace hrn
