@@ -1,0 +1,99 @@
+"""Device-side mirror of the reference's inference caller (the "next" rows N1/N2 of SURVEY.md section 8f):
+
+  * ``collateFunction(min_L)``       -- src/utils.py:49-113: pad / truncate every imageset to ``min_L`` views
+                                        (zero views, alpha = 0) and stack the batch;
+  * ``get_sr_and_score(imset, model, min_L=16)`` -- src/predict.py:17-49: collate, HRNet forward, clip, shifted cPSNR.
+
+Same names, arguments and return values as the reference; the forward and the scoring run through the C ABI on
+the GPU and the SR never takes the D2H -> NumPy -> cPSNR detour of predict.py:40-45 (it is copied back once, only
+because the reference returns it).  ``get_sr_and_score_batch`` scores many imagesets in one forward."""
+from __future__ import annotations
+
+from collections.abc import Mapping
+
+import numpy as np
+import torch
+
+from .evaluator import shift_cPSNR
+
+
+class collateFunction:
+    """Util class to create padded batches of data (utils.py:49-113)."""
+
+    def __init__(self, min_L=32):
+        self.min_L = min_L
+
+    def __call__(self, batch):
+        return self.collateFunction(batch)
+
+    def collateFunction(self, batch):
+        """batch: list of imagesets (mappings with 'lr' (L, H, W), 'hr', 'hr_map', 'name') ->
+        (padded_lr_batch (B, min_L, H, W), alpha_batch (B, min_L), hr_batch, hm_batch, names)."""
+        lr_batch, alpha_batch, hr_batch, hm_batch, isn_batch = [], [], [], [], []
+        train_batch = True
+        for imageset in batch:
+            lrs = torch.as_tensor(imageset["lr"])
+            n_views, h, w = lrs.shape
+            if n_views >= self.min_L:                               # truncate (utils.py:89-91)
+                lr_batch.append(lrs[:self.min_L])
+                alpha_batch.append(torch.ones(self.min_L))
+            else:                                                   # zero-pad, alpha = 0 (utils.py:92-95)
+                pad = torch.zeros(self.min_L - n_views, h, w, dtype=lrs.dtype)
+                lr_batch.append(torch.cat([lrs, pad], dim=0))
+                alpha_batch.append(torch.cat([torch.ones(n_views), torch.zeros(self.min_L - n_views)], dim=0))
+            hr = imageset["hr"]
+            if train_batch and hr is not None:
+                hr_batch.append(torch.as_tensor(hr))
+            else:
+                train_batch = False
+            hm_batch.append(torch.as_tensor(imageset["hr_map"]) if imageset["hr_map"] is not None else None)
+            isn_batch.append(imageset["name"])
+        padded_lr_batch = torch.stack(lr_batch, dim=0)
+        alpha_batch = torch.stack(alpha_batch, dim=0)
+        if train_batch:
+            hr_batch = torch.stack(hr_batch, dim=0)
+            hm_batch = torch.stack(hm_batch, dim=0)
+        return padded_lr_batch, alpha_batch, hr_batch, hm_batch, isn_batch
+
+
+def _device_of(model):
+    return next(model.parameters()).device
+
+
+def get_sr_and_score(imset, model, min_L=16):
+    """predict.py:17-49.  imset: one imageset (mapping) or a tuple of batches (lrs, alphas, hrs, hr_maps, names).
+    Returns (sr: np.ndarray (3H, 3W) of the FIRST imageset, scPSNR: float or None)."""
+    if isinstance(imset, Mapping):
+        lrs, alphas, hrs, hr_maps, names = collateFunction(min_L=min_L)([imset])
+    elif isinstance(imset, tuple):
+        lrs, alphas, hrs, hr_maps, names = imset
+    else:
+        raise TypeError("imset must be an imageset mapping or a tuple of batches")
+    device = _device_of(model)
+    if device.type != "cuda":
+        raise RuntimeError("the model must live on a CUDA device: the B200 path has no CPU fallback")
+    sr_dev = model(lrs.float().to(device), alphas.float().to(device))[:, 0]
+    sr = sr_dev.detach().cpu().numpy()[0]
+    if len(hrs) > 0:
+        hr = torch.as_tensor(hrs)[0:1].float().to(device)
+        hm = torch.as_tensor(hr_maps)[0:1].float().to(device)
+        score = shift_cPSNR(sr_dev[0:1], hr, hm, border_w=3, clip_sr=True)       # np.clip(sr, 0, 1) fused (predict.py:43)
+        sc_psnr = np.float32(score[0].item())
+    else:
+        sc_psnr = None
+    return sr, sc_psnr
+
+
+def get_sr_and_score_batch(imsets, model, min_L=16):
+    """New capability: all imagesets in ONE forward + ONE scoring launch.
+    Returns (srs: np.ndarray (B, 3H, 3W), scores: np.ndarray (B,) float32 or None when there is no ground truth)."""
+    lrs, alphas, hrs, hr_maps, names = collateFunction(min_L=min_L)(list(imsets))
+    device = _device_of(model)
+    if device.type != "cuda":
+        raise RuntimeError("the model must live on a CUDA device: the B200 path has no CPU fallback")
+    sr_dev = model(lrs.float().to(device), alphas.float().to(device))[:, 0]
+    scores = None
+    if len(hrs) > 0:
+        scores = shift_cPSNR(sr_dev, hrs.float().to(device), hr_maps.float().to(device), border_w=3, clip_sr=True)
+        scores = scores.cpu().numpy().astype(np.float32)
+    return sr_dev.cpu().numpy(), scores

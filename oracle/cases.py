@@ -95,3 +95,18 @@ def cpsnr_inputs(name: str):
     else:
         raise KeyError(kind)
     return sr, hr, hm
+
+
+# name -> (number of real views, LR size, has ground truth); min_L = 16 (predict.py:17)
+PREDICT_CASES = {
+    "v5_s32": (5, 32, True),          # fewer views than min_L: zero padding, alpha = 0
+    "v20_s32": (20, 32, True),        # more views than min_L: truncated
+    "v16_s24_nohr": (16, 24, False),  # test-split imageset: no HR, score is None
+}
+PREDICT_MIN_L = 16
+
+
+def predict_lrs(name: str):
+    n, s, _ = PREDICT_CASES[name]
+    rng = np.random.RandomState(4000 + sorted(PREDICT_CASES).index(name))
+    return rng.rand(n, s, s).astype(np.float32)

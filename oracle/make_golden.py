@@ -32,9 +32,14 @@ from oracle import cases, hrnet_oracle, scoring_oracle  # noqa: E402
 def _import_reference():
     if not os.path.isdir(REF_SRC):
         raise SystemExit("reference sources not present; goldens can only be regenerated in the build container")
-    for name in ("skimage", "skimage.io"):
-        sys.modules.setdefault(name, types.ModuleType(name))
-    sys.modules["skimage"].io = sys.modules["skimage.io"]
+    class _Stub(types.ModuleType):          # plotting / image-IO packages the hot path never calls
+        def __getattr__(self, k):
+            if k.startswith("__"):
+                raise AttributeError(k)
+            return None
+    for name in ("skimage", "skimage.io", "matplotlib", "matplotlib.pyplot", "seaborn", "tensorboardX", "mpl_toolkits",
+                 "mpl_toolkits.axes_grid1"):
+        sys.modules.setdefault(name, _Stub(name))
     sys.path.insert(0, REF_SRC)
     from DeepNetworks.HRNet import HRNet  # type: ignore
     import lanczos  # type: ignore
@@ -109,6 +114,36 @@ def main():
         cp_out[name + "__sites"] = np.stack([p_[2] for p_ in per]).astype(np.float32)
         cp_out[name + "__argmax"] = np.array([p_[1] for p_ in per], dtype=np.int32)
     np.savez_compressed(os.path.join(out_dir, "cpsnr.npz"), **cp_out)
+
+    # ---------------- predict.get_sr_and_score (the caller) ----------------
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import predict as ref_predict  # type: ignore
+        from DataLoader import ImageSet  # type: ignore
+    from oracle import predict_oracle
+    pr_out = {}
+    rng = np.random.RandomState(77)
+    for name, (n, s, has_hr) in cases.PREDICT_CASES.items():
+        lr = cases.predict_lrs(name)
+        base = {"name": name, "lr": torch.from_numpy(lr), "hr": None, "hr_map": torch.ones(3 * s, 3 * s), "clearances": None}
+        with torch.no_grad():
+            sr0, _ = ref_predict.get_sr_and_score(ImageSet(base), model, min_L=cases.PREDICT_MIN_L)
+        if has_hr:      # HR built from the reference SR (roll + bias + noise) so that the score is well conditioned
+            hr = np.clip(np.roll(np.clip(sr0, 0, 1), (2, -1), (0, 1)) + 0.02 + 0.01 * rng.randn(*sr0.shape), 0, 1).astype(np.float32)
+            hm = (rng.rand(*sr0.shape) > 0.1).astype(np.float32)
+            base["hr"], base["hr_map"] = torch.from_numpy(hr), torch.from_numpy(hm)
+            pr_out[name + "__hr"], pr_out[name + "__hr_map"] = hr, hm
+        with torch.no_grad(), np.errstate(all="ignore"):
+            sr, score = ref_predict.get_sr_and_score(ImageSet(base), model, min_L=cases.PREDICT_MIN_L)
+        o_sr, o_score = predict_oracle.get_sr_and_score(
+            {"lr": lr, "hr": base["hr"].numpy() if has_hr else None, "hr_map": base["hr_map"].numpy()}, params, cases.PREDICT_MIN_L)
+        assert np.abs(o_sr - sr).max() <= 2e-6
+        assert (score is None and o_score is None) or abs(float(score) - float(o_score)) <= 1e-4
+        print(f"predict {name}: sr {sr.shape} score {score} oracle {o_score}")
+        pr_out[name + "__sr"] = sr.astype(np.float32)
+        pr_out[name + "__score"] = np.float32(np.nan if score is None else score)
+    np.savez_compressed(os.path.join(out_dir, "predict.npz"), **pr_out)
     print("goldens written to", out_dir)
 
 

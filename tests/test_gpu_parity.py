@@ -343,3 +343,25 @@ def test_full_scoring_path_against_oracle(hb, net, dev):
     for i in range(b):
         assert abs(best[i] - ref_scores[i][0]) <= CPSNR_GATE_DB
         assert xy[i, 0] * 7 + xy[i, 1] == ref_scores[i][1] == (3 + rolls[i, 0]) * 7 + (3 + rolls[i, 1])
+
+
+# ---------------------------------------------------------------------------- the caller
+@pytest.mark.parametrize("name", list(cases.PREDICT_CASES))
+def test_get_sr_and_score_matches_reference_golden(net, golden, name):
+    """predict.get_sr_and_score (predict.py:17-49): collate to min_L = 16, forward, clip, shifted cPSNR."""
+    from highres_net_b200.predict import get_sr_and_score, get_sr_and_score_batch
+    g = golden["predict"]
+    n, s, has_hr = cases.PREDICT_CASES[name]
+    imset = {"name": name, "lr": torch.from_numpy(cases.predict_lrs(name)),
+             "hr": torch.from_numpy(g[name + "__hr"]) if has_hr else None,
+             "hr_map": torch.from_numpy(g[name + "__hr_map"]) if has_hr else torch.ones(3 * s, 3 * s)}
+    sr, score = get_sr_and_score(imset, net, min_L=cases.PREDICT_MIN_L)
+    assert isinstance(sr, np.ndarray) and sr.shape == (3 * s, 3 * s)
+    assert np.abs(sr - g[name + "__sr"]).max() <= SR_REGRESSION_GATE
+    if has_hr:
+        assert abs(float(score) - float(g[name + "__score"])) <= CPSNR_GATE_DB
+        srs, scores = get_sr_and_score_batch([imset, imset], net, min_L=cases.PREDICT_MIN_L)
+        assert srs.shape == (2, 3 * s, 3 * s) and np.array_equal(srs[0], sr) and np.array_equal(srs[1], sr)
+        assert scores.shape == (2,) and abs(float(scores[1]) - float(score)) <= 1e-5
+    else:
+        assert score is None

@@ -108,3 +108,38 @@ def test_cpsnr_known_shift_convention():
     sr = np.roll(hr, (1, -2), axis=(0, 1))
     mx, am, _ = scoring_oracle.shift_cpsnr(sr, hr, np.ones_like(hr))
     assert int(am) == 19 and np.isinf(mx)
+
+
+@pytest.mark.parametrize("name", list(cases.PREDICT_CASES))
+def test_predict_oracle_matches_reference_golden(golden, name):
+    """predict.get_sr_and_score (predict.py:17-49) restated on the oracle pieces vs the reference run."""
+    from oracle import predict_oracle
+    g = golden["predict"]
+    n, s, has_hr = cases.PREDICT_CASES[name]
+    imset = {"lr": cases.predict_lrs(name), "hr": g[name + "__hr"] if has_hr else None,
+             "hr_map": g[name + "__hr_map"] if has_hr else None}
+    sr, score = predict_oracle.get_sr_and_score(imset, hrnet_oracle.make_params(cases.WEIGHT_SEED), cases.PREDICT_MIN_L)
+    assert np.abs(sr - g[name + "__sr"]).max() <= 2e-6
+    if has_hr:
+        assert abs(float(score) - float(g[name + "__score"])) <= 1e-4
+    else:
+        assert score is None and np.isnan(g[name + "__score"])
+
+
+def test_collate_mirror_matches_oracle():
+    """Host logic of the product's collateFunction (utils.py:63-113 mirror) against the oracle restatement."""
+    import torch
+    from highres_net_b200.predict import collateFunction
+    from oracle import predict_oracle
+    rng = np.random.RandomState(9)
+    imsets = [{"name": f"s{i}", "lr": torch.from_numpy(rng.rand(n, 8, 8).astype(np.float32)),
+               "hr": torch.from_numpy(rng.rand(24, 24).astype(np.float32)), "hr_map": torch.ones(24, 24)}
+              for i, n in enumerate((3, 16, 21))]
+    lrs, alphas, hrs, hms, names = collateFunction(min_L=16)(imsets)
+    o_lrs, o_alphas = predict_oracle.collate(imsets, 16)
+    assert lrs.shape == (3, 16, 8, 8) and np.array_equal(lrs.numpy(), o_lrs) and np.array_equal(alphas.numpy(), o_alphas)
+    assert hrs.shape == (3, 24, 24) and hms.shape == (3, 24, 24) and names == ["s0", "s1", "s2"]
+    assert alphas[0].tolist() == [1.0] * 3 + [0.0] * 13 and float(lrs[0, 3:].abs().max()) == 0.0
+    imsets[1]["hr"] = None                      # a test-split imageset: hr batch stays a (partial) list like the reference
+    _, _, hrs2, hms2, _ = collateFunction(min_L=16)(imsets)
+    assert isinstance(hrs2, list) and len(hrs2) == 1 and isinstance(hms2, list)
