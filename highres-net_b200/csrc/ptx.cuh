@@ -59,7 +59,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // Bounded wait: a pipeline bug must surface as a CUDA error, never as a hung GPU.  The retry loop lives out of
 // line so that the common case (barrier already complete) costs one TRYWAIT and one branch at the call site.
 #ifndef HRN_WAIT_LIMIT_CYCLES
-#define HRN_WAIT_LIMIT_CYCLES (4000000000LL)   // ~2 s at 1.9 GHz
+#define HRN_WAIT_LIMIT_CYCLES (20000000000LL)   // ~10-15 s: far beyond any legitimate wait, still bounded
 #endif
 static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int tag) {
     const long long t0 = clock64();
