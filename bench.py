@@ -229,17 +229,14 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    # ---------------- end to end through the host-buffer API (runs first: it also ramps the clocks) ----------------
-    for i in range(2):
-        net.forward_host(*host_inputs[i % len(host_inputs)], out_host=host_out, device=dev)
-    sync_all()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    for i in range(args.steps):
-        net.forward_host(*host_inputs[i % len(host_inputs)], out_host=host_out, device=dev)
-    e3.record()
-    sync_all()
-    ms_e2e = e2.elapsed_time(e3)
+    # ---------------- clock / power ramp (untimed) ----------------
+    # The board idles at 120 MHz and, once loaded, needs about a second to settle at its power-capped clock
+    # (sw_power_cap, ~900-1000 W).  Everything below is measured in that settled state.
+    t_ramp = time.time()
+    while time.time() - t_ramp < 2.0:
+        for i in range(5):
+            net(*dev_inputs[i % n_rot])
+        torch.cuda.synchronize(dev)
 
     # ---------------- device-resident throughput ----------------
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -258,6 +255,18 @@ def main():
     launches = hb.kernel_launch_count() - launches0
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop(t_wall0, t_wall1) if sampler is not None else None
+
+    # ---------------- end to end through the host-buffer API ----------------
+    for i in range(2):
+        net.forward_host(*host_inputs[i % len(host_inputs)], out_host=host_out, device=dev)
+    sync_all()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(args.steps):
+        net.forward_host(*host_inputs[i % len(host_inputs)], out_host=host_out, device=dev)
+    e3.record()
+    sync_all()
+    ms_e2e = e2.elapsed_time(e3)
 
     # ---------------- per-kernel-class timing for the roofline ----------------
     net.profile_begin(dev)
