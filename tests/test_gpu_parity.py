@@ -113,6 +113,23 @@ def test_conv64_single_taps(hb, dev, taps):
     assert (y1.cpu() - ref).abs().max() <= 4e-3 * max(1.0, float(ref.abs().max()))
 
 
+@pytest.mark.parametrize("b,l,size", [(1, 2, 1), (2, 3, 2), (1, 4, 3), (3, 7, 5), (1, 32, 8), (2, 2, 130), (1, 3, 257)])
+def test_hrnet_edge_shapes_match_oracle(net, dev, b, l, size):
+    """Tiny images (a strip of 1-3 rows, one ragged 128-pixel tile), deep recursion (L = 32: five fusion levels) and
+    widths just past one / two column tiles, against the oracle computed on the fly."""
+    rng = np.random.RandomState(100 * b + 10 * l + size)
+    lrs = rng.rand(b, l, size, size).astype(np.float32)
+    alphas = np.ones((b, l), dtype=np.float32)
+    if l > 2:
+        lrs[0, -1] = 0.0
+        alphas[0, -1] = 0.0
+    ref = hrnet_oracle.hrnet_forward(hrnet_oracle.make_params(cases.WEIGHT_SEED), lrs, alphas).numpy()
+    sr = net(torch.from_numpy(lrs).to(dev), torch.from_numpy(alphas).to(dev))
+    assert tuple(sr.shape) == (b, 1, 3 * size, 3 * size)
+    err = np.abs(sr.cpu().numpy() - ref).max()
+    assert err <= SR_GATE and err <= 2e-3, err          # L = 32 accumulates five levels of bf16 rounding: ~1.1e-3
+
+
 def test_alpha_zero_views_are_skipped(net, dev):
     """utils.py:89-95 contract: a padded view (alpha = 0) must not change the fused state (HRNet.py:123-128)."""
     rng = np.random.RandomState(3)
