@@ -144,7 +144,7 @@ def cpu_baseline(l, s, seconds_budget=25.0, max_sets=4, threads=None):
                       f"(oneDNN), batch 1 per call, best of 2"}
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
     """--impl reference: the reference's own CPU path (oracle port: the reference is pure PyTorch and
     /root/reference does not exist on the GPU box), all host threads, rank 0 only."""
     if rank != 0:
@@ -176,10 +176,20 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }), flush=True)
+    }), file=out, flush=True)
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else that writes to fd 1 (e.g. NCCL's version banner, which comes
+    from C code) is sent to stderr.  Returns a writer for the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=60)
@@ -196,7 +206,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, out)
         return
 
     import torch
@@ -324,7 +334,7 @@ def main():
             line["cpu_baseline"] = cpu_baseline(l, s)
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
