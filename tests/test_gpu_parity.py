@@ -210,6 +210,22 @@ def test_forward_host_pipeline_depths(hb, dev):
     assert torch.equal(model.forward_host(lrs.clone(), alphas.clone(), device=dev), ref)    # pageable host memory too
 
 
+def test_forward_on_side_stream(net, dev):
+    """All work is enqueued on the caller's current stream (torch.cuda.current_stream)."""
+    lrs, alphas = cases.hrnet_inputs("b2_l4_s32")
+    tl, ta = torch.from_numpy(lrs).to(dev), torch.from_numpy(alphas).to(dev)
+    ref = net(tl, ta)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(side):
+        big = torch.rand(4096, 4096, device=dev) @ torch.rand(4096, 4096, device=dev)      # keep the side stream busy first
+        out = net(tl, ta)
+        done = torch.cuda.Event()
+        done.record(side)
+    done.synchronize()
+    assert torch.equal(out, ref) and big.shape == (4096, 4096)
+
+
 def test_forward_rejects_bad_inputs(hb, net, dev):
     with pytest.raises(RuntimeError):
         net(torch.rand(1, 2, 16, 16), torch.ones(1, 2))                  # CPU tensors: no fallback
