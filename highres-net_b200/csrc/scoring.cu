@@ -205,24 +205,40 @@ cpsnr_pass_kernel(const float* __restrict__ sr, const float* __restrict__ hr, co
         b[y] = (PASS == 2 && y < g.S) ? bias[(set * g.S + x) * g.S + y] : 0.0f;
     }
     if (j < g.size) {
-        for (int i = i0; i < i1; ++i) {
-            float s = __ldg(srp + static_cast<size_t>(i + g.border) * g.W + j + g.border);
-            if (clip_sr) s = fminf(fmaxf(s, 0.0f), 1.0f);
-            const float* hrow = hrp + static_cast<size_t>(i + x) * g.W + j;
-            const float* mrow = hmp + static_cast<size_t>(i + x) * g.W + j;
+        // Rows are taken four at a time: the per-element arithmetic is the reference's fp32 arithmetic, the four
+        // row terms of a site are added in fp32 (the reference sums everything in fp32) and only that partial sum
+        // is folded into the fp64 accumulator, which quarters the fp64 conversions and adds.
+        for (int i = i0; i < i1; i += 4) {
+            float p0[CP_MAXS], p1[CP_MAXS];
 #pragma unroll
-            for (int y = 0; y < CP_MAXS; ++y) {
-                if (y < g.S) {
-                    const float m = __ldg(mrow + y);
-                    const float d = __ldg(hrow + y) - s;           // diff = hr - sr            (Evaluator.py:35)
-                    if (PASS == 1) {
-                        s0[y] += static_cast<double>(m);           // n_clear                   (Evaluator.py:34)
-                        s1[y] += static_cast<double>(d * m);       // sum(diff * hr_map)        (Evaluator.py:36)
-                    } else {
-                        const float t = (d - b[y]) * m;            // (diff - bias) * hr_map    (Evaluator.py:37)
-                        s0[y] += static_cast<double>(t * t);
+            for (int y = 0; y < CP_MAXS; ++y) p0[y] = p1[y] = 0.0f;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (i + r < i1) {
+                    float s = __ldg(srp + static_cast<size_t>(i + r + g.border) * g.W + j + g.border);
+                    if (clip_sr) s = fminf(fmaxf(s, 0.0f), 1.0f);
+                    const float* hrow = hrp + static_cast<size_t>(i + r + x) * g.W + j;
+                    const float* mrow = hmp + static_cast<size_t>(i + r + x) * g.W + j;
+#pragma unroll
+                    for (int y = 0; y < CP_MAXS; ++y) {
+                        if (y < g.S) {
+                            const float m = __ldg(mrow + y);
+                            const float d = __ldg(hrow + y) - s;       // diff = hr - sr            (Evaluator.py:35)
+                            if (PASS == 1) {
+                                p0[y] += m;                            // n_clear                   (Evaluator.py:34)
+                                p1[y] += d * m;                        // sum(diff * hr_map)        (Evaluator.py:36)
+                            } else {
+                                const float t = (d - b[y]) * m;        // (diff - bias) * hr_map    (Evaluator.py:37)
+                                p0[y] += t * t;
+                            }
+                        }
                     }
                 }
+            }
+#pragma unroll
+            for (int y = 0; y < CP_MAXS; ++y) {
+                s0[y] += static_cast<double>(p0[y]);
+                if (PASS == 1) s1[y] += static_cast<double>(p1[y]);
             }
         }
     }
