@@ -57,6 +57,7 @@ struct hrn_handle {
     float* io[3] = {nullptr, nullptr, nullptr};   // device staging for hrn_forward_host: lrs, alphas, sr
     int max_ctas = 0;                  // 0 = one CTA per SM (test knob)
     int host_chunks = 0;               // hrn_forward_host pipeline depth (0 = automatic)
+    long long workspace_mb = 65536;    // cap on the activation workspace; larger batches are run in slices
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of hrn_forward_host
     cudaEvent_t ev_in[8] = {}, ev_done[8] = {};
     int debug_flags = 0;
@@ -492,9 +493,30 @@ int32_t hrn_set_weight(hrn_handle* h, const char* key, const float* data, const 
     return 0;
 }
 
+// Imagesets are independent, so a batch whose activation workspace (5 buffers of B*L*H*W*128 bytes) would exceed the
+// cap is run as consecutive slices on the same stream; results are identical to one big call.
+static int forward_sliced(hrn_handle* h, const float* lrs, const float* alphas, int B, int L, int H, int W, float* sr,
+                          cudaStream_t s) {
+    if (h == nullptr) {
+        set_error("null handle");
+        return -1;
+    }
+    if (B <= 0 || L <= 0 || H <= 0 || W <= 0) return forward_impl(h, lrs, alphas, B, L, H, W, sr, s, nullptr);
+    const double per_set = 5.0 * L * static_cast<double>(H) * W * 128.0;
+    const double budget = static_cast<double>(h->workspace_mb) * 1048576.0;
+    long long slice = static_cast<long long>(budget / per_set);
+    slice = slice < 1 ? 1 : (slice > B ? B : slice);
+    const size_t set_in = static_cast<size_t>(L) * H * W, set_out = static_cast<size_t>(9) * H * W;
+    for (long long b0 = 0; b0 < B; b0 += slice) {
+        const int nb = static_cast<int>(b0 + slice <= B ? slice : B - b0);
+        if (forward_impl(h, lrs + b0 * set_in, alphas + b0 * L, nb, L, H, W, sr + b0 * set_out, s, nullptr)) return -1;
+    }
+    return 0;
+}
+
 int32_t hrn_forward(hrn_handle* h, const float* lrs, const float* alphas, int32_t B, int32_t L, int32_t H, int32_t W,
                     float* sr, void* stream) {
-    return forward_impl(h, lrs, alphas, B, L, H, W, sr, static_cast<cudaStream_t>(stream), nullptr);
+    return forward_sliced(h, lrs, alphas, B, L, H, W, sr, static_cast<cudaStream_t>(stream));
 }
 
 int32_t hrn_forward_dump(hrn_handle* h, const float* lrs, const float* alphas, int32_t B, int32_t L, int32_t H,
@@ -550,8 +572,8 @@ int32_t hrn_forward_host(hrn_handle* h, const float* lrs_host, const float* alph
         const int b0 = k * per, nb = (b0 + per <= B ? per : B - b0);
         if (nb <= 0) break;
         HRN_CUDA_OK(cudaStreamWaitEvent(s, h->ev_in[k], 0));
-        if (forward_impl(h, h->io[0] + b0 * set_in, h->io[1] + static_cast<size_t>(b0) * L, nb, L, H, W,
-                         h->io[2] + b0 * set_out, s, nullptr))
+        if (forward_sliced(h, h->io[0] + b0 * set_in, h->io[1] + static_cast<size_t>(b0) * L, nb, L, H, W,
+                           h->io[2] + b0 * set_out, s))
             return -1;
         HRN_CUDA_OK(cudaEventRecord(h->ev_done[k], s));
         HRN_CUDA_OK(cudaStreamWaitEvent(h->copy_out, h->ev_done[k], 0));
@@ -639,6 +661,7 @@ int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value) {
     if (strcmp(knob, "max_ctas") == 0) h->max_ctas = value;
     else if (strcmp(knob, "debug_flags") == 0) h->debug_flags = value;
     else if (strcmp(knob, "host_chunks") == 0) h->host_chunks = value;
+    else if (strcmp(knob, "workspace_mb") == 0) h->workspace_mb = value > 0 ? value : 65536;
     else {
         set_error("hrn_debug_set: unknown knob '%s'", knob);
         return -1;

@@ -117,6 +117,7 @@ lanczos_shift7_kernel(const float* __restrict__ img, const float* __restrict__ s
         ky[t] = taps[0][t];
         kx[t] = taps[1][t];
     }
+    const bool y_interior = (y0 - L7_HALF >= 0) && (y0 + L7_TH + L7_HALF <= H);
     // y pass (dim 0 taps first, lanczos.py:90): work item = (column q of the strip, 16-row segment)
     for (int item = threadIdx.x; item < L7_INW * (L7_TH / L7_SEG); item += L7_THREADS) {
         const int q = item % L7_INW, seg = item / L7_INW;
@@ -125,11 +126,17 @@ lanczos_shift7_kernel(const float* __restrict__ img, const float* __restrict__ s
         const int r0 = seg * L7_SEG;
         // all 22 loads are issued before the first use (memory-level parallelism), then 16 outputs are formed
         float col[L7_SEG + 6];
+        if (y_interior) {                       // no reflection needed in y for this block (10 of 12 row tiles at 384)
+            const float* base_ptr = src + static_cast<size_t>(y0 + r0 - L7_HALF) * W + xx;
 #pragma unroll
-        for (int t = 0; t < L7_SEG + 6; ++t) {
-            bool oky;
-            const int yy = padded_index(y0 + r0 + t - L7_HALF, H, p, &oky);
-            col[t] = (oky && okx) ? __ldg(src + static_cast<size_t>(yy) * W + xx) : 0.0f;
+            for (int t = 0; t < L7_SEG + 6; ++t) col[t] = okx ? __ldg(base_ptr + static_cast<size_t>(t) * W) : 0.0f;
+        } else {
+#pragma unroll
+            for (int t = 0; t < L7_SEG + 6; ++t) {
+                bool oky;
+                const int yy = padded_index(y0 + r0 + t - L7_HALF, H, p, &oky);
+                col[t] = (oky && okx) ? __ldg(src + static_cast<size_t>(yy) * W + xx) : 0.0f;
+            }
         }
 #pragma unroll
         for (int r = 0; r < L7_SEG; ++r) {

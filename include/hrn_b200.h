@@ -63,7 +63,8 @@ int32_t hrn_missing_weights(const hrn_handle* h);
 
 /* Replaces HRNet.forward (HRNet.py:186-211).  DEVICE pointers:
  *   lrs (B, L, H, W) fp32 contiguous, alphas (B, L) fp32, sr (B, 1, 3H, 3W) fp32 out.
- * Square inputs only (H == W), as the reference's view() at HRNet.py:204 requires. */
+ * Square inputs only (H == W), as the reference's view() at HRNet.py:204 requires.  The handle keeps 5 activation
+ * buffers of B*L*H*W*128 bytes (bf16 NHWC), capped at 64 GiB by slicing the batch. */
 int32_t hrn_forward(hrn_handle* h, const float* lrs, const float* alphas, int32_t B, int32_t L, int32_t H,
                     int32_t W, float* sr, void* stream);
 
@@ -107,7 +108,8 @@ int32_t hrn_forward_dump(hrn_handle* h, const float* lrs, const float* alphas, i
 
 /* Test knobs.  "max_ctas" = N > 0 limits the tcgen05 conv kernels to N CTAs (0 = one per SM), which moves
  * the strip boundaries of the row partition; results must not change.  "host_chunks" = pipeline depth of
- * hrn_forward_host (0 = automatic, 1 = no overlap).  "debug_flags" disables parts of the conv kernel for
+ * hrn_forward_host (0 = automatic, 1 = no overlap).  "workspace_mb" caps the activation workspace (default 65536 MB);
+ * batches that need more are run as consecutive slices with identical results.  "debug_flags" disables parts of the conv kernel for
  * performance triage (results are then garbage). */
 int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value);
 

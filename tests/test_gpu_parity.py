@@ -210,6 +210,20 @@ def test_forward_host_pipeline_depths(hb, dev):
     assert torch.equal(model.forward_host(lrs.clone(), alphas.clone(), device=dev), ref)    # pageable host memory too
 
 
+def test_workspace_cap_slices_the_batch(hb, dev):
+    """A batch whose activation workspace exceeds the cap is run in slices; the output must not change."""
+    model = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval()
+    model.load_state_dict(hrnet_oracle.make_params(cases.WEIGHT_SEED))
+    model = model.to(dev)
+    g = torch.Generator().manual_seed(21)
+    lrs, alphas = torch.rand(7, 4, 48, 48, generator=g).to(dev), torch.ones(7, 4, device=dev)
+    ref = model(lrs, alphas)
+    model.debug_set(dev, "workspace_mb", 12)      # one imageset needs 5 * 4 * 48 * 48 * 128 B = 5.6 MB -> slices of 2
+    assert torch.equal(model(lrs, alphas), ref)
+    model.debug_set(dev, "workspace_mb", 1)       # smaller than one imageset: falls back to one imageset per slice
+    assert torch.equal(model(lrs, alphas), ref)
+
+
 def test_forward_on_side_stream(net, dev):
     """All work is enqueued on the caller's current stream (torch.cuda.current_stream)."""
     lrs, alphas = cases.hrnet_inputs("b2_l4_s32")
