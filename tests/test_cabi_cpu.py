@@ -37,12 +37,18 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.hrn_kernel_launch_count() == 0
 
 
-def test_library_is_in_tree_and_built_for_sm100a():
+def test_library_is_in_tree_and_built_for_sm100a(lib):
+    import shutil
+    import subprocess
     import highres_net_b200 as hb
     path = hb.library_path()
-    assert path.startswith(ROOT) and os.path.exists(path)
-    log = open(os.path.join(os.path.dirname(path), "build.log")).read()
-    assert "sm_100a" in log
+    assert path.startswith(ROOT) and os.path.exists(path)                 # in-tree, not site-packages
+    build_py = open(os.path.join(ROOT, "highres-net_b200", "build.py")).read()
+    assert "arch=compute_100a,code=sm_100a" in build_py and "-lineinfo" in build_py
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if os.path.exists(cuobjdump):
+        elfs = subprocess.run([cuobjdump, "-lelf", path], capture_output=True, text=True).stdout
+        assert "sm_100a" in elfs and "sm_90" not in elfs                  # one target only: no multi-arch fat binary
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
