@@ -32,7 +32,6 @@
 
 #include <algorithm>
 #include <cstring>
-#include <vector>
 
 namespace hrn {
 namespace {

@@ -154,20 +154,13 @@ __device__ __forceinline__ void stg_v8(void* p, const uint32_t (&r)[8]) {
 }
 
 // ---------------------------------------------------------------- descriptors
-// Shared-memory matrix descriptor, K-major, 128-byte swizzle (sm_100 format):
+// Shared-memory matrix descriptor, K-major, 128-byte swizzle (sm_100 format; built in umma_common.cuh):
 //   [0,14)  start address >> 4        [16,30) leading byte offset >> 4 (unused for SW128 K-major: 1)
 //   [32,46) stride byte offset >> 4 (8-row group pitch = 1024 B -> 64)
-//   [46,48) version = 1               [49,52) matrix base offset        [61,64) layout: 2 = SWIZZLE_128B
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t base_offset) {
-    uint64_t d = 0;
-    d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
-    d |= static_cast<uint64_t>(1) << 16;
-    d |= static_cast<uint64_t>(1024 >> 4) << 32;
-    d |= static_cast<uint64_t>(1) << 46;
-    d |= static_cast<uint64_t>(base_offset & 7) << 49;
-    d |= static_cast<uint64_t>(2) << 61;
-    return d;
-}
+//   [46,48) version = 1               [49,52) matrix base offset = 0    [61,64) layout: 2 = SWIZZLE_128B
+// The swizzle is a function of the shared-memory ADDRESS bits, so a start address shifted by whole 128-byte rows
+// (the kx taps of the conv) needs no base offset -- verified on hardware (profiles/r01_bringup1.log: base offset
+// (start >> 7) & 7 gives wrong results, 0 is right).
 // Instruction descriptor for kind::f16: D fp32, A/B bf16, both K-major.
 //   [4,6) c_format = 1 (F32)   [7,10) a_format = 1 (BF16)   [10,13) b_format = 1 (BF16)
 //   [15] a_major = 0 (K)       [16] b_major = 0 (K)         [17,23) N >> 3          [24,29) M >> 4
