@@ -130,6 +130,36 @@ def test_hrnet_edge_shapes_match_oracle(net, dev, b, l, size):
     assert err <= SR_GATE and err <= 2e-3, err          # L = 32 accumulates five levels of bf16 rounding: ~1.1e-3
 
 
+@pytest.mark.parametrize("num_layers,alpha_residual", [(0, True), (1, True), (3, True), (2, False)])
+def test_config_variants_match_oracle(hb, dev, num_layers, alpha_residual):
+    """config.json knobs the kernels are not specialised away from: encoder depth and recursive.alpha_residual."""
+    import copy
+    cfg = copy.deepcopy(hrnet_oracle.DEFAULT_NETWORK_CONFIG)
+    cfg["encoder"]["num_layers"] = num_layers
+    cfg["recursive"]["alpha_residual"] = alpha_residual
+    params = hrnet_oracle.make_params(5, cfg)
+    model = hb.HRNet(cfg).eval()
+    model.load_state_dict(params)
+    model = model.to(dev)
+    rng = np.random.RandomState(31 + num_layers)
+    lrs = rng.rand(2, 4, 24, 24).astype(np.float32)
+    alphas = np.array([[1, 1, 1, 1], [1, 1, 1, 0]], dtype=np.float32)
+    lrs[1, 3] = 0.0
+    ref = hrnet_oracle.hrnet_forward(params, lrs, alphas, cfg).numpy()
+    sr = model(torch.from_numpy(lrs).to(dev), torch.from_numpy(alphas).to(dev)).cpu().numpy()
+    assert np.abs(sr - ref).max() <= SR_REGRESSION_GATE
+
+
+def test_unsupported_config_is_rejected(hb, dev):
+    import copy
+    cfg = copy.deepcopy(hrnet_oracle.DEFAULT_NETWORK_CONFIG)
+    cfg["encoder"]["channel_size"] = 32
+    cfg["recursive"]["in_channels"] = 32
+    model = hb.HRNet(cfg).eval().to(dev)
+    with pytest.raises(RuntimeError, match="unsupported network config"):
+        model(torch.rand(1, 2, 16, 16, device=dev), torch.ones(1, 2, device=dev))
+
+
 def test_alpha_zero_views_are_skipped(net, dev):
     """utils.py:89-95 contract: a padded view (alpha = 0) must not change the fused state (HRNet.py:123-128)."""
     rng = np.random.RandomState(3)
