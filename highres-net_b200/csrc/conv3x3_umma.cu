@@ -56,6 +56,7 @@ struct Cfg {
     static constexpr int BIAS_OFFSET = BAR_OFFSET + 512;
     static constexpr int SMEM_BYTES = BIAS_OFFSET + NT * 4 + 1024;
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+    static_assert(16 * RING + 16 * ACC_SLOTS + 8 + 8 <= 512, "barrier block overflows into the bias array");
 };
 
 struct Geometry {

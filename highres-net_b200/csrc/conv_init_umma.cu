@@ -23,8 +23,9 @@ constexpr int W_BYTES = 64 * 128;
 constexpr int ACC_SLOTS = 8;
 constexpr int NUM_THREADS = 128 + 256 + 256;    // warp 0: MMA, warp 1: TMEM alloc, warps 4-11: builders (two sets), warps 12-19: epilogue
 constexpr int BAR_OFFSET = W_BYTES + A_RING * A_BYTES;
-constexpr int BIAS_OFFSET = BAR_OFFSET + 256;
+constexpr int BIAS_OFFSET = BAR_OFFSET + 512;   // barriers: (2 * A_RING + 2 * ACC_SLOTS) * 8 B + TMEM slot
 constexpr int SMEM_BYTES = BIAS_OFFSET + 64 * 4 + 1024;
+static_assert((2 * A_RING + 2 * ACC_SLOTS) * 8 + 8 <= 512, "barrier block overflows into the bias array");
 
 struct InitArgs {
     const float* lrs;       // (B, L, H, W)

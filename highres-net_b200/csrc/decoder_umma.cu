@@ -22,6 +22,7 @@ constexpr int NUM_THREADS = 384;
 constexpr int BAR_OFFSET = W_BYTES + A_RING * A_BYTES;
 constexpr int PARAM_OFFSET = BAR_OFFSET + 256; // bd[64], wf[64]
 constexpr int SMEM_BYTES = PARAM_OFFSET + 128 * 4 + 1024;
+static_assert(16 * A_RING + 16 + 16 + 8 + 8 <= 256, "barrier block overflows into the parameter array");
 
 struct DecArgs {
     int B, H, W, x_tiles;
