@@ -37,6 +37,7 @@ SYMBOLS = {
     "hrn_lanczos_taps": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "hrn_shift_cpsnr": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hrn_clear_loss": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "hrn_forward_dump": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                    c_int32, c_void_p, c_void_p]),
     "hrn_profile_begin": (c_int32, [c_void_p]),

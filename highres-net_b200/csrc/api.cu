@@ -613,6 +613,15 @@ int32_t hrn_shift_cpsnr(const float* sr, const float* hr, const float* hr_map, i
                                    static_cast<cudaStream_t>(stream));
 }
 
+int32_t hrn_clear_loss(const float* sr, const float* hr, const float* hr_map, int32_t B, int32_t H, int32_t W,
+                       int32_t metric, float* loss, void* stream) {
+    if (sr == nullptr || hr == nullptr || hr_map == nullptr || loss == nullptr) {
+        set_error("hrn_clear_loss: null pointer");
+        return -1;
+    }
+    return hrn::clear_loss_launch(sr, hr, hr_map, B, H, W, metric, loss, static_cast<cudaStream_t>(stream));
+}
+
 int32_t hrn_profile_begin(hrn_handle* h) {
     if (h == nullptr) {
         set_error("null handle");

@@ -78,6 +78,8 @@ int nhwc_bf16_to_nchw_f32_launch(const __nv_bfloat16* in, int n, int H, int W, i
 int lanczos_shift_launch(const float* img, const float* shift, int nb, int c, int H, int W, int p, int a,
                          int ntaps, float* out, cudaStream_t s);
 int lanczos_taps_launch(const float* d, int n, int a, int ntaps, float* out, cudaStream_t s);
+int clear_loss_launch(const float* sr, const float* hr, const float* hm, int B, int H, int W, int metric, float* out,
+                      cudaStream_t s);
 int shift_cpsnr_launch(const float* sr, const float* hr, const float* hm, int B, int H, int W, int border,
                        int clip_sr, float* best_db, int32_t* best_site, float* site_db, cudaStream_t s);
 

@@ -308,6 +308,77 @@ __global__ void cpsnr_finalize_kernel(const double* __restrict__ partial, CpGeom
     }
 }
 
+// ------------------------------------------------------------------ clear loss (train.py:66-87 without autograd)
+// metric 0: masked_MSE = mean over ALL pixels of (m*sr - m*hr)^2
+// metric 1: cMSE       = sum(m * (sr + b - hr)^2) / sum(m),  b = sum(m * (hr - sr)) / sum(m)   (weight m, not m^2)
+// metric 2: cPSNR      = -10 log10(cMSE)
+constexpr int CL_BLOCKS = 16, CL_THREADS = 256;
+
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+    v = warp_sum(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < CL_THREADS / 32; ++w) r += scratch[w];       // fixed order: deterministic
+    return r;
+}
+
+// PASS 0: sum((m*sr - m*hr)^2).  PASS 1: sum(m), sum(m * (hr - sr)).  PASS 2: sum(m * ((sr + b) - hr)^2).
+template <int PASS>
+__global__ void __launch_bounds__(CL_THREADS)
+clear_loss_pass_kernel(const float* __restrict__ sr, const float* __restrict__ hr, const float* __restrict__ hm,
+                       size_t hw, const float* __restrict__ bias, double* __restrict__ partial) {
+    __shared__ double scratch[CL_THREADS / 32];
+    const int img = blockIdx.y;
+    const float *s = sr + img * hw, *h = hr + img * hw, *m = hm + img * hw;
+    const float b = PASS == 2 ? bias[img] : 0.0f;
+    double a0 = 0.0, a1 = 0.0;
+    for (size_t i = blockIdx.x * static_cast<size_t>(CL_THREADS) + threadIdx.x; i < hw; i += static_cast<size_t>(CL_BLOCKS) * CL_THREADS) {
+        const float sv = __ldg(s + i), hv = __ldg(h + i), mv = __ldg(m + i);
+        if (PASS == 0) {
+            const float e = mv * sv - mv * hv;
+            a0 += static_cast<double>(e * e);
+        } else if (PASS == 1) {
+            a0 += static_cast<double>(mv);
+            a1 += static_cast<double>(mv * (hv - sv));
+        } else {
+            const float e = (sv + b) - hv;
+            a0 += static_cast<double>(mv * (e * e));
+        }
+    }
+    const double r0 = block_sum(a0, scratch);
+    const double r1 = PASS == 1 ? block_sum(a1, scratch) : 0.0;
+    if (threadIdx.x == 0) {
+        partial[(static_cast<size_t>(img) * CL_BLOCKS + blockIdx.x) * 2] = r0;
+        partial[(static_cast<size_t>(img) * CL_BLOCKS + blockIdx.x) * 2 + 1] = r1;
+    }
+}
+
+// MODE 0: masked_MSE out.  MODE 1: bias + n_clear.  MODE 2: cMSE / cPSNR out.
+template <int MODE>
+__global__ void clear_loss_finalize_kernel(const double* __restrict__ partial, int B, double n_pix, int metric,
+                                           float* __restrict__ bias, double* __restrict__ nclear, float* __restrict__ out) {
+    const int img = blockIdx.x * blockDim.x + threadIdx.x;
+    if (img >= B) return;
+    double a0 = 0.0, a1 = 0.0;
+    for (int k = 0; k < CL_BLOCKS; ++k) {
+        a0 += partial[(static_cast<size_t>(img) * CL_BLOCKS + k) * 2];
+        a1 += partial[(static_cast<size_t>(img) * CL_BLOCKS + k) * 2 + 1];
+    }
+    if (MODE == 0) {
+        out[img] = static_cast<float>(a0 / n_pix);
+    } else if (MODE == 1) {
+        nclear[img] = a0;
+        bias[img] = static_cast<float>(a1 / a0);
+    } else {
+        const double cmse = a0 / nclear[img];
+        out[img] = metric == 1 ? static_cast<float>(cmse) : static_cast<float>(-10.0 * log10(cmse));
+    }
+}
+
 }  // namespace
 
 int lanczos_shift_launch(const float* img, const float* shift, int nb, int c, int H, int W, int p, int a, int ntaps,
@@ -394,6 +465,41 @@ int shift_cpsnr_launch(const float* sr, const float* hr, const float* hm, int B,
     cpsnr_pass_kernel<2><<<grid, block, 0, s>>>(sr, hr, hm, g, clip_sr, bias, partial);
     cpsnr_finalize_kernel<2><<<B, 64, 0, s>>>(partial, g, bias, nclear, best_db, best_site, site_db);
     note_launches(4);
+    HRN_CUDA_OK(cudaGetLastError());
+    HRN_CUDA_OK(cudaFreeAsync(ws, s));
+    return 0;
+}
+
+int clear_loss_launch(const float* sr, const float* hr, const float* hm, int B, int H, int W, int metric, float* out,
+                      cudaStream_t s) {
+    if (metric < 0 || metric > 2) {
+        set_error("clear_loss: metric %d unknown (0 = masked_MSE, 1 = cMSE, 2 = cPSNR)", metric);
+        return -1;
+    }
+    if (B <= 0 || B > 65535 || H <= 0 || W <= 0) {
+        set_error("clear_loss: bad sizes (B=%d H=%d W=%d)", B, H, W);
+        return -1;
+    }
+    const size_t hw = static_cast<size_t>(H) * W;
+    const size_t partial_bytes = static_cast<size_t>(B) * CL_BLOCKS * 2 * sizeof(double);
+    uint8_t* ws = nullptr;
+    HRN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&ws), partial_bytes + B * sizeof(double) + B * sizeof(float), s));
+    double* partial = reinterpret_cast<double*>(ws);
+    double* nclear = reinterpret_cast<double*>(ws + partial_bytes);
+    float* bias = reinterpret_cast<float*>(ws + partial_bytes + B * sizeof(double));
+    dim3 grid(CL_BLOCKS, B);
+    const int fb = (B + 127) / 128;
+    if (metric == 0) {
+        clear_loss_pass_kernel<0><<<grid, CL_THREADS, 0, s>>>(sr, hr, hm, hw, nullptr, partial);
+        clear_loss_finalize_kernel<0><<<fb, 128, 0, s>>>(partial, B, static_cast<double>(hw), metric, nullptr, nullptr, out);
+        note_launches(2);
+    } else {
+        clear_loss_pass_kernel<1><<<grid, CL_THREADS, 0, s>>>(sr, hr, hm, hw, nullptr, partial);
+        clear_loss_finalize_kernel<1><<<fb, 128, 0, s>>>(partial, B, 0.0, metric, bias, nclear, nullptr);
+        clear_loss_pass_kernel<2><<<grid, CL_THREADS, 0, s>>>(sr, hr, hm, hw, bias, partial);
+        clear_loss_finalize_kernel<2><<<fb, 128, 0, s>>>(partial, B, 0.0, metric, bias, nclear, out);
+        note_launches(4);
+    }
     HRN_CUDA_OK(cudaGetLastError());
     HRN_CUDA_OK(cudaFreeAsync(ws, s));
     return 0;

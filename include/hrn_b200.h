@@ -93,6 +93,15 @@ int32_t hrn_shift_cpsnr(const float* sr, const float* hr, const float* hr_map, i
                         int32_t border_w, int32_t clip_sr, float* best_db, int32_t* best_site, float* site_db,
                         void* stream);
 
+/* Replaces train.get_loss (src/train.py:66-87) without autograd: one value per image.  DEVICE pointers: sr, hr, hr_map
+ * (B, H, W) fp32, loss (B) fp32.  metric 0 = masked_MSE, 1 = cMSE (brightness-bias corrected, weighted by hr_map),
+ * 2 = cPSNR = -10 log10(cMSE). */
+#define HRN_LOSS_MASKED_MSE 0
+#define HRN_LOSS_CMSE 1
+#define HRN_LOSS_CPSNR 2
+int32_t hrn_clear_loss(const float* sr, const float* hr, const float* hr_map, int32_t B, int32_t H, int32_t W,
+                       int32_t metric, float* loss, void* stream);
+
 /* ---- test / profiling hooks (not part of the reference surface) ---- */
 
 /* Stage identifiers for hrn_forward_dump. */

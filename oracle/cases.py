@@ -110,3 +110,30 @@ def predict_lrs(name: str):
     n, s, _ = PREDICT_CASES[name]
     rng = np.random.RandomState(4000 + sorted(PREDICT_CASES).index(name))
     return rng.rand(n, s, s).astype(np.float32)
+
+
+# train.get_loss cases: name -> (B, S, kind of mask)
+LOSS_CASES = {
+    "binary_4_48": (4, 48, "binary"),
+    "soft_3_33": (3, 33, "soft"),              # non-binary weights, odd size
+    "cropped_2_96": (2, 96, "cropped"),        # hr_map * get_crop_mask(32, 3), as train.py:178-181 uses it
+    "full_2_384": (2, 384, "binary"),          # Proba-V HR size
+}
+LOSS_METRICS = ("masked_MSE", "cMSE", "cPSNR")
+
+
+def loss_inputs(name: str):
+    b, s, kind = LOSS_CASES[name]
+    rng = np.random.RandomState(5000 + sorted(LOSS_CASES).index(name))
+    sr = rng.rand(b, s, s).astype(np.float32)
+    hr = np.clip(sr + 0.03 + 0.05 * rng.randn(b, s, s), 0, 1).astype(np.float32)
+    if kind == "soft":
+        hm = rng.rand(b, s, s).astype(np.float32)
+    else:
+        hm = (rng.rand(b, s, s) > 0.15).astype(np.float32)
+    if kind == "cropped":
+        hm[:, :3, :] = 0
+        hm[:, -3:, :] = 0
+        hm[:, :, :3] = 0
+        hm[:, :, -3:] = 0
+    return sr, hr, hm

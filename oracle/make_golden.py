@@ -144,6 +144,26 @@ def main():
         pr_out[name + "__sr"] = sr.astype(np.float32)
         pr_out[name + "__score"] = np.float32(np.nan if score is None else score)
     np.savez_compressed(os.path.join(out_dir, "predict.npz"), **pr_out)
+
+    # ---------------- train.get_loss / get_crop_mask ----------------
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import train as ref_train  # type: ignore
+    ls_out = {}
+    for name in cases.LOSS_CASES:
+        sr, hr, hm = cases.loss_inputs(name)
+        for metric in cases.LOSS_METRICS:
+            ref = ref_train.get_loss(torch.from_numpy(sr), torch.from_numpy(hr), torch.from_numpy(hm), metric=metric).numpy()
+            mine = scoring_oracle.clear_loss(sr, hr, hm, metric)
+            rel = float(np.abs(mine / ref - 1).max())
+            print(f"loss {name} {metric}: {ref} oracle-vs-ref rel={rel:.2e}")
+            assert rel <= 2e-5, rel
+            ls_out[f"{name}__{metric}"] = ref.astype(np.float32)
+    for ps, cs in ((32, 3), (4, 1), (64, 6)):
+        ref = ref_train.get_crop_mask(ps, cs).numpy()
+        assert np.array_equal(ref, scoring_oracle.crop_mask(ps, cs))
+        ls_out[f"crop_{ps}_{cs}"] = ref.astype(np.float32)
+    np.savez_compressed(os.path.join(out_dir, "loss.npz"), **ls_out)
     print("goldens written to", out_dir)
 
 

@@ -113,3 +113,31 @@ def shift_cpsnr(sr: np.ndarray, hr: np.ndarray, hr_map: np.ndarray, border_w: in
             sites.append(cpsnr(src, hr[..., x:x + size, y:y + size], hr_map[..., x:x + size, y:y + size]))
     sites = np.array(sites)
     return np.max(sites, axis=0), np.argmax(sites, axis=0), sites
+
+
+def clear_loss(srs: np.ndarray, hrs: np.ndarray, hr_maps: np.ndarray, metric: str = "cMSE") -> np.ndarray:
+    """train.py:66-87 (get_loss) restated in float32 numpy: per-image masked_MSE, cMSE or cPSNR.  Note the weights:
+    masked_MSE averages (m*sr - m*hr)^2 over ALL pixels (train.py:78-80); cMSE weights the squared error by m (not m^2,
+    unlike Evaluator.cPSNR) and divides by sum(m) (train.py:81-85)."""
+    srs, hrs, hr_maps = (np.asarray(x, dtype=np.float32) for x in (srs, hrs, hr_maps))
+    if metric == "masked_MSE":
+        e = hr_maps * srs - hr_maps * hrs
+        return np.mean(e * e, axis=(1, 2), dtype=np.float32)
+    nclear = np.sum(hr_maps, axis=(1, 2), dtype=np.float32)
+    bright = (np.sum(hr_maps * (hrs - srs), axis=(1, 2), dtype=np.float32) / nclear).astype(np.float32)
+    e = (srs + bright[:, None, None]) - hrs
+    cmse = np.sum(hr_maps * (e * e), axis=(1, 2), dtype=np.float32) / nclear
+    if metric == "cMSE":
+        return cmse.astype(np.float32)
+    return (-10.0 * np.log10(cmse)).astype(np.float32)
+
+
+def crop_mask(patch_size: int, crop_size: int) -> np.ndarray:
+    """train.py:90-106 (get_crop_mask)."""
+    n = 3 * patch_size
+    m = np.ones((1, 1, n, n), dtype=np.float32)
+    m[0, 0, :crop_size, :] = 0
+    m[0, 0, -crop_size:, :] = 0
+    m[0, 0, :, :crop_size] = 0
+    m[0, 0, :, -crop_size:] = 0
+    return m

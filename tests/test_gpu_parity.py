@@ -442,3 +442,43 @@ def test_get_sr_and_score_matches_reference_golden(net, golden, name):
         assert scores.shape == (2,) and abs(float(scores[1]) - float(score)) <= 1e-5
     else:
         assert score is None
+
+
+# ---------------------------------------------------------------------------- train.get_loss twin
+LOSS_REL_GATE = 1e-5      # fp32 element ops as in the reference, fp64 sums
+
+
+@pytest.mark.parametrize("name", list(cases.LOSS_CASES))
+@pytest.mark.parametrize("metric", cases.LOSS_METRICS)
+def test_get_loss_matches_reference_golden(hb, dev, golden, name, metric):
+    sr, hr, hm = (torch.from_numpy(x).to(dev) for x in cases.loss_inputs(name))
+    got = hb.get_loss(sr, hr, hm, metric=metric)
+    assert got.shape == (sr.shape[0],) and got.dtype == torch.float32 and got.is_cuda
+    ref = golden["loss"][f"{name}__{metric}"]
+    assert np.abs(got.cpu().numpy() / ref - 1).max() <= LOSS_REL_GATE
+    assert np.abs(got.cpu().numpy() / scoring_oracle.clear_loss(*cases.loss_inputs(name), metric) - 1).max() <= LOSS_REL_GATE
+
+
+def test_get_loss_agrees_with_evaluator_on_binary_masks(hb, dev):
+    """For a 0/1 mask m == m^2, so train.get_loss('cPSNR') equals Evaluator.cPSNR (Evaluator.py:15-37) image by image."""
+    sr, hr, hm = (torch.from_numpy(x).to(dev) for x in cases.loss_inputs("full_2_384"))
+    loss = hb.get_loss(sr, hr, hm, metric="cPSNR").cpu().numpy()
+    for i in range(sr.shape[0]):
+        assert abs(loss[i] - float(hb.cPSNR(sr[i], hr[i], hm[i]))) <= 1e-4
+    again = hb.get_loss(sr, hr, hm, metric="cPSNR").cpu().numpy()
+    assert np.array_equal(loss, again)                                          # fixed-order reduction: deterministic
+
+
+def test_get_loss_degenerate_and_errors(hb, dev):
+    sr = torch.rand(2, 24, 24, device=dev)
+    zero = torch.zeros_like(sr)
+    assert torch.isnan(hb.get_loss(sr, sr * 0.5, zero, metric="cMSE")).all()    # 0 / 0 like the reference
+    assert torch.isinf(hb.get_loss(sr, sr, torch.ones_like(sr), metric="cPSNR")).all()
+    assert (hb.get_loss(sr, sr, torch.ones_like(sr), metric="masked_MSE") == 0).all()
+    with pytest.raises(Exception):
+        hb.get_loss(sr.cpu(), sr.cpu(), zero.cpu())                             # no CPU fallback
+
+
+def test_get_crop_mask_matches_reference_golden(hb, golden):
+    for ps, cs in ((32, 3), (4, 1), (64, 6)):
+        assert np.array_equal(hb.get_crop_mask(ps, cs).numpy(), golden["loss"][f"crop_{ps}_{cs}"])

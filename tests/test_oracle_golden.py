@@ -143,3 +143,19 @@ def test_collate_mirror_matches_oracle():
     imsets[1]["hr"] = None                      # a test-split imageset: hr batch stays a (partial) list like the reference
     _, _, hrs2, hms2, _ = collateFunction(min_L=16)(imsets)
     assert isinstance(hrs2, list) and len(hrs2) == 1 and isinstance(hms2, list)
+
+
+# ---------------------------------------------------------------------------- train.get_loss
+@pytest.mark.parametrize("name", list(cases.LOSS_CASES))
+@pytest.mark.parametrize("metric", cases.LOSS_METRICS)
+def test_clear_loss_oracle_matches_reference_golden(golden, name, metric):
+    sr, hr, hm = cases.loss_inputs(name)
+    mine = scoring_oracle.clear_loss(sr, hr, hm, metric)
+    ref = golden["loss"][f"{name}__{metric}"]
+    assert mine.shape == ref.shape
+    assert np.abs(mine / ref - 1).max() <= 2e-5            # fp32 summation order only
+
+
+def test_crop_mask_oracle_matches_reference_golden(golden):
+    for ps, cs in ((32, 3), (4, 1), (64, 6)):
+        assert np.array_equal(scoring_oracle.crop_mask(ps, cs), golden["loss"][f"crop_{ps}_{cs}"])
