@@ -42,3 +42,21 @@ def lanczos_shift(img, shift, p=3, a=3, N=7):
                                                  out.data_ptr(), _lib.current_stream_ptr(img.device)),
                    "hrn_lanczos_shift")
     return out.to(img.dtype)
+
+
+def transform(theta, I, device=None):
+    """ShiftNet.transform (ShiftNet.py:77-90): shift image b of I (B, 1, H, W) by theta[b] = (dx, dy) with Lanczos
+    interpolation (a = 3, p = 5) -> (1, 1, B, H, W), exactly the reference's (odd) result shape.  ``device`` is accepted
+    for signature compatibility and ignored: the work happens on I.device."""
+    _lib.require_cuda_tensor(I, "I")
+    theta = torch.as_tensor(theta, device=I.device)
+    return lanczos_shift(I.transpose(0, 1), theta.flip(-1), p=5, a=3)[:, None]
+
+
+def apply_shifts(shiftNet, images, thetas, device=None):
+    """train.apply_shifts (train.py:47-63): images (B, V, H, W), thetas (B, V, 2) = (dx, dy) -> warped (B, V, H, W).
+    ``shiftNet`` is only used by the reference to reach ``transform``; pass None (or any object) here."""
+    batch_size, n_views, height, width = images.shape
+    flat = images.reshape(-1, 1, height, width)
+    new_images = transform(thetas.reshape(-1, 2), flat, device=device)
+    return new_images.view(-1, n_views, height, width)

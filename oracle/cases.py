@@ -137,3 +137,15 @@ def loss_inputs(name: str):
         hm[:, :, :3] = 0
         hm[:, :, -3:] = 0
     return sr, hr, hm
+
+
+# train.apply_shifts / ShiftNet.transform cases: name -> (B, V, S)
+APPLY_SHIFTS_CASES = {"b2_v3_24": (2, 3, 24), "b1_v1_384": (1, 1, 384), "b3_v16_40": (3, 16, 40)}
+
+
+def apply_shifts_inputs(name: str):
+    b, v, s = APPLY_SHIFTS_CASES[name]
+    rng = np.random.RandomState(6000 + sorted(APPLY_SHIFTS_CASES).index(name))
+    images = rng.rand(b, v, s, s).astype(np.float32)
+    thetas = rng.uniform(-1.5, 1.5, size=(b, v, 2)).astype(np.float32)
+    return images, thetas

@@ -164,6 +164,21 @@ def main():
         assert np.array_equal(ref, scoring_oracle.crop_mask(ps, cs))
         ls_out[f"crop_{ps}_{cs}"] = ref.astype(np.float32)
     np.savez_compressed(os.path.join(out_dir, "loss.npz"), **ls_out)
+
+    # ---------------- train.apply_shifts / ShiftNet.transform ----------------
+    from DeepNetworks.ShiftNet import ShiftNet  # type: ignore
+    shim = types.SimpleNamespace()                       # transform only touches self.theta; no 34 M-parameter net needed
+    shim.transform = lambda theta, I, device="cpu": ShiftNet.transform(shim, theta, I, device=device)
+    as_out = {}
+    for name in cases.APPLY_SHIFTS_CASES:
+        images, thetas = cases.apply_shifts_inputs(name)
+        ref = ref_train.apply_shifts(shim, torch.from_numpy(images), torch.from_numpy(thetas), "cpu").numpy()
+        mine = scoring_oracle.apply_shifts(images, thetas)
+        err = float(np.abs(mine - ref).max())
+        print(f"apply_shifts {name}: {ref.shape} oracle-vs-ref max|d|={err:.3e}")
+        assert ref.shape == images.shape and err <= 2e-6, err
+        as_out[name] = ref.astype(np.float32)
+    np.savez_compressed(os.path.join(out_dir, "apply_shifts.npz"), **as_out)
     print("goldens written to", out_dir)
 
 

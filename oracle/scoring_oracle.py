@@ -77,6 +77,15 @@ def lanczos_shift(img: np.ndarray, shift: np.ndarray, p: int = 3, a: int = 3, n:
     return out
 
 
+def apply_shifts(images: np.ndarray, thetas: np.ndarray) -> np.ndarray:
+    """train.py:47-63 + ShiftNet.py:77-90: images (B, V, H, W), thetas (B, V, 2) = (dx, dy); every view becomes one
+    channel of a single (1, B*V, H, W) image, the shift is flipped to (dy, dx), a = 3, p = 5."""
+    b, v, h, w = images.shape
+    flat = np.asarray(images, dtype=np.float32).reshape(1, b * v, h, w)
+    shift = np.asarray(thetas, dtype=np.float32).reshape(-1, 2)[:, ::-1]
+    return lanczos_shift(flat, shift, p=5, a=3).reshape(b, v, h, w)
+
+
 # ----------------------------------------------------------------------------
 # cPSNR and the 7x7 shift search
 # ----------------------------------------------------------------------------

@@ -482,3 +482,22 @@ def test_get_loss_degenerate_and_errors(hb, dev):
 def test_get_crop_mask_matches_reference_golden(hb, golden):
     for ps, cs in ((32, 3), (4, 1), (64, 6)):
         assert np.array_equal(hb.get_crop_mask(ps, cs).numpy(), golden["loss"][f"crop_{ps}_{cs}"])
+
+
+# ---------------------------------------------------------------------------- train.apply_shifts / ShiftNet.transform (8a10)
+@pytest.mark.parametrize("name", list(cases.APPLY_SHIFTS_CASES))
+def test_apply_shifts_matches_reference_golden(hb, dev, golden, name):
+    images, thetas = cases.apply_shifts_inputs(name)
+    out = hb.apply_shifts(None, torch.from_numpy(images).to(dev), torch.from_numpy(thetas).to(dev), dev)
+    assert out.shape == images.shape and out.is_cuda
+    assert np.abs(out.cpu().numpy() - golden["apply_shifts"][name]).max() <= LANCZOS_GATE
+
+
+def test_apply_shifts_integer_theta_is_a_roll(hb, dev):
+    """theta = (dx, dy) = (1, -2): every interior pixel moves by exactly that many pixels (taps collapse to a delta)."""
+    img = torch.rand(1, 2, 32, 32, device=dev)
+    theta = torch.tensor([[[1.0, -2.0], [0.0, 0.0]]], device=dev)
+    out = hb.apply_shifts(None, img, theta, dev)
+    assert torch.allclose(out[0, 1], img[0, 1], atol=2e-6)
+    ref = scoring_oracle.apply_shifts(img.cpu().numpy(), theta.cpu().numpy())
+    assert np.abs(out.cpu().numpy() - ref).max() <= LANCZOS_GATE

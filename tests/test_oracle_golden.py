@@ -159,3 +159,10 @@ def test_clear_loss_oracle_matches_reference_golden(golden, name, metric):
 def test_crop_mask_oracle_matches_reference_golden(golden):
     for ps, cs in ((32, 3), (4, 1), (64, 6)):
         assert np.array_equal(scoring_oracle.crop_mask(ps, cs), golden["loss"][f"crop_{ps}_{cs}"])
+
+
+@pytest.mark.parametrize("name", list(cases.APPLY_SHIFTS_CASES))
+def test_apply_shifts_oracle_matches_reference_golden(golden, name):
+    images, thetas = cases.apply_shifts_inputs(name)
+    out = scoring_oracle.apply_shifts(images, thetas)
+    assert np.abs(out - golden["apply_shifts"][name]).max() <= 2e-6
