@@ -195,10 +195,12 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Block = (32 lanes x 4 crop columns) x (S row-shifts x).  A thread loads 10 consecutive hr / map values of one row (three
 // aligned float4 each) and 4 sr values, and feeds 4 columns x S column-shifts y from them: 11 load instructions per
 // 28 (pixel, site) terms instead of 15 per 7, which moves the kernel from the load pipe to the fp32 pipe.
-template <int PASS>
+// SFIX = 7 is the border_w = 3 search with every per-site loop bound known at compile time; SFIX = 0 takes S from g.
+template <int PASS, int SFIX>
 __global__ void __launch_bounds__(CP_LANES* CP_MAXS)
 cpsnr_pass_kernel(const float* __restrict__ sr, const float* __restrict__ hr, const float* __restrict__ hm,
                   CpGeom g, int clip_sr, const float* __restrict__ bias, double* __restrict__ partial) {
+    const int S = SFIX ? SFIX : g.S;
     const int set = blockIdx.y;
     const int band = blockIdx.x / g.col_blocks, cb = blockIdx.x % g.col_blocks;
     const int j0 = cb * CP_COLS + threadIdx.x * CP_TCOLS;      // first crop column of this thread
@@ -210,13 +212,14 @@ cpsnr_pass_kernel(const float* __restrict__ sr, const float* __restrict__ hr, co
     const float* hmp = hm + set * plane;
     const int i0 = band * g.band_rows, i1 = min(g.size, i0 + g.band_rows);
     const bool vec = g.vec_ok && j0 + CP_WIN <= g.W;
+    const bool full = ncol == CP_TCOLS;
     double s0[CP_MAXS], s1[CP_MAXS];
     float b[CP_MAXS];
 #pragma unroll
     for (int y = 0; y < CP_MAXS; ++y) {
         s0[y] = 0.0;
         s1[y] = 0.0;
-        b[y] = (PASS == 2 && y < g.S) ? bias[(set * g.S + x) * g.S + y] : 0.0f;
+        b[y] = (PASS == 2 && y < S) ? bias[(set * S + x) * S + y] : 0.0f;
     }
     if (ncol > 0) {
         // Rows are taken four at a time: the per-element arithmetic is the reference's fp32 arithmetic, the 16 terms of a
@@ -256,10 +259,10 @@ cpsnr_pass_kernel(const float* __restrict__ sr, const float* __restrict__ hr, co
                     }
 #pragma unroll
                     for (int c = 0; c < CP_TCOLS; ++c) {
-                        if (c < ncol) {
+                        if (full || c < ncol) {
 #pragma unroll
                             for (int y = 0; y < CP_MAXS; ++y) {
-                                if (y < g.S) {
+                                if (y < S) {
                                     const float m = mw[c + y];
                                     const float d = hw[c + y] - sv[c];     // diff = hr - sr            (Evaluator.py:35)
                                     if (PASS == 1) {
@@ -283,10 +286,10 @@ cpsnr_pass_kernel(const float* __restrict__ sr, const float* __restrict__ hr, co
         }
     }
     // fixed-order block reduction over the 32 lanes (one warp per x), then one partial per block
-    double* dst = partial + ((static_cast<size_t>(set) * g.blocks_per_set + blockIdx.x) * g.S + x) * g.S * 2;
+    double* dst = partial + ((static_cast<size_t>(set) * g.blocks_per_set + blockIdx.x) * S + x) * S * 2;
 #pragma unroll
     for (int y = 0; y < CP_MAXS; ++y) {
-        if (y < g.S) {
+        if (y < S) {
             const double r0 = warp_sum(s0[y]);
             const double r1 = PASS == 1 ? warp_sum(s1[y]) : 0.0;
             if (threadIdx.x == 0) {
@@ -497,9 +500,15 @@ int shift_cpsnr_launch(const float* sr, const float* hr, const float* hm, int B,
     double* nclear = reinterpret_cast<double*>(ws + partial_bytes);
     float* bias = reinterpret_cast<float*>(ws + partial_bytes + nclear_bytes);
     dim3 grid(g.blocks_per_set, B), block(CP_LANES, g.S);
-    cpsnr_pass_kernel<1><<<grid, block, 0, s>>>(sr, hr, hm, g, clip_sr, nullptr, partial);
+    if (g.S == 7)
+        cpsnr_pass_kernel<1, 7><<<grid, block, 0, s>>>(sr, hr, hm, g, clip_sr, nullptr, partial);
+    else
+        cpsnr_pass_kernel<1, 0><<<grid, block, 0, s>>>(sr, hr, hm, g, clip_sr, nullptr, partial);
     cpsnr_finalize_kernel<1><<<B, 64, 0, s>>>(partial, g, bias, nclear, nullptr, nullptr, nullptr);
-    cpsnr_pass_kernel<2><<<grid, block, 0, s>>>(sr, hr, hm, g, clip_sr, bias, partial);
+    if (g.S == 7)
+        cpsnr_pass_kernel<2, 7><<<grid, block, 0, s>>>(sr, hr, hm, g, clip_sr, bias, partial);
+    else
+        cpsnr_pass_kernel<2, 0><<<grid, block, 0, s>>>(sr, hr, hm, g, clip_sr, bias, partial);
     cpsnr_finalize_kernel<2><<<B, 64, 0, s>>>(partial, g, bias, nclear, best_db, best_site, site_db);
     note_launches(4);
     HRN_CUDA_OK(cudaGetLastError());
