@@ -53,6 +53,10 @@ struct hrn_handle {
     __nv_bfloat16* act[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t anchor_cap = 0;
     float* anchor = nullptr;
+    size_t lists_cap = 0, live_scratch_cap = 0;
+    int* lists = nullptr;              // live-work lists of the current forward call (pointwise.cu: live_lists_kernel)
+    uint8_t* live_scratch = nullptr;
+    int skip_dead = 1;                 // 0: process every view and pair even when it cannot reach the output (test knob)
     size_t io_cap[3] = {0, 0, 0};
     float* io[3] = {nullptr, nullptr, nullptr};   // device staging for hrn_forward_host: lrs, alphas, sr
     int max_ctas = 0;                  // 0 = one CTA per SM (test knob)
@@ -132,10 +136,11 @@ struct Dump {
     bool hit;
 };
 
-int maybe_dump(Dump* d, int stage, const __nv_bfloat16* t, int n, int H, int W, int C, cudaStream_t s) {
+int maybe_dump(Dump* d, int stage, const __nv_bfloat16* t, int n, int H, int W, int C, cudaStream_t s, int group = 1,
+               int stride = 1) {
     if (d == nullptr || d->stage != stage) return 0;
     d->hit = true;
-    return hrn::nhwc_bf16_to_nchw_f32_launch(t, n, H, W, C, d->dst, s);
+    return hrn::nhwc_bf16_to_nchw_f32_launch(t, n, H, W, C, group, stride, d->dst, s);
 }
 
 // Brackets one kernel launch with CUDA events on its own stream when profiling is on.
@@ -207,6 +212,17 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
     }
     if (grow(reinterpret_cast<void**>(&h->anchor), &h->anchor_cap, static_cast<size_t>(B) * hw * sizeof(float))) return -1;
 
+    // ---- live-work lists: views / pairs that cannot reach the output (alpha = 0 padding) are not computed at all.
+    // The stage-dump hook asks for dense lists so that every intermediate tensor is defined.  Must stay the first
+    // launch of the pass (see live_lists_launch).
+    if (grow(reinterpret_cast<void**>(&h->lists), &h->lists_cap, hrn::live_lists_ints(B, L) * sizeof(int))) return -1;
+    if (grow(reinterpret_cast<void**>(&h->live_scratch), &h->live_scratch_cap, hrn::live_scratch_bytes(B, L))) return -1;
+    if (hrn::live_lists_launch(alphas, B, L, (dump == nullptr && h->skip_dead) ? 1 : 0, h->cfg.rec_alpha_residual ? 1 : 0,
+                               h->live_scratch, h->lists, s))
+        return -1;
+    const int* enc_list = h->lists + 16;
+    const int* enc_count = h->lists;
+
     // ---- anchor + first conv (HRNet.py:200-204, 51-53)
     {
         SpanGuard guard(h, s, HRN_PROF_MEDIAN, 0.0);
@@ -219,7 +235,7 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
     }
     {
         SpanGuard guard(h, s, HRN_PROF_CONV_INIT, 2.0 * 18.0 * 64.0 * static_cast<double>(n_img) * hw);
-        if (hrn::conv_init_umma_launch(lrs, h->anchor, B, L, H, W, h->w_init_img, h->b_init, h->prelu_init, h->act[0], h->sm_count, s)) return -1;
+        if (hrn::conv_init_umma_launch(lrs, h->anchor, B, L, H, W, h->w_init_img, h->b_init, h->prelu_init, h->act[0], enc_list, enc_count, h->sm_count, s)) return -1;
     }
     int stage = 0;
     if (maybe_dump(dump, HRN_STAGE_ENC(stage), h->act[0], static_cast<int>(n_img), H, W, 64, s)) return -1;
@@ -231,6 +247,8 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
     base.W = W;
     base.in_images = static_cast<int>(n_img);
     base.in_c = 64;
+    base.live_list = enc_list;
+    base.live_count = enc_count;
     int cur = 0;
     for (int r = 0; r < h->cfg.enc_num_layers; ++r) {
         const int t1 = (cur + 1) % 3, t2 = (cur + 2) % 3;
@@ -258,23 +276,27 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
         if (maybe_dump(dump, HRN_STAGE_ENC(++stage), h->act[cur], base.n_img, H, W, 64, s)) return -1;
     }
 
-    // ---- recursive fusion (HRNet.py:99-134)
+    // ---- recursive fusion (HRNet.py:99-134), in place: the 64-channel view stack keeps its stride of L images per
+    // imageset at every level and the merged pair (b, i) overwrites alice's slot b * L + i.  A pair that is not live
+    // (alpha_bob = 0) therefore needs no work at all: alice is already where the next level expects it.
     int n = L, level = 0;
-    __nv_bfloat16 *t1 = h->act[3], *t2 = h->act[4];
+    __nv_bfloat16 *stack = h->act[cur], *t1 = h->act[3], *t2 = h->act[4];
+    const int* pair_list = h->lists + 16 + n_img;
     while (n / 2 > 0) {
         const int half = n / 2, top = n - (n % 2);
-        const int next = (cur + 1) % 3;
         hrn::ConvArgs a{};
         a.n_img = B * half;
         a.H = H;
         a.W = W;
         a.half = half;
-        a.src_views = n;
+        a.src_views = L;
         a.top = top;
+        a.live_list = pair_list;
+        a.live_count = h->lists + 1 + level;
         // conv 1 of the residual block on cat(alice, bob): the concat is two K chunks from two views
         a.pair_mode = 1;
-        a.in = h->act[cur];
-        a.in_images = B * n;
+        a.in = stack;
+        a.in_images = B * L;
         a.in_c = 64;
         a.out = t1;
         a.res_mode = hrn::RES_NONE;
@@ -287,28 +309,29 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
         a.in_c = 128;
         a.out = t2;
         a.res_mode = hrn::RES_PAIR;
-        a.res = h->act[cur];
+        a.res = stack;
         if (run_conv(h, h->fuse[1], a, s)) return -1;
         if (maybe_dump(dump, HRN_STAGE_FUSE(level, 1), t2, B * half, H, W, 128, s)) return -1;
-        // conv 128 -> 64 + PReLU, then alice + alpha_bob * x
+        // conv 128 -> 64 + PReLU, then alice + alpha_bob * x, written over alice
         a.in = t2;
-        a.out = h->act[next];
+        a.out = stack;
+        a.out_in_stack = 1;
         a.res_mode = h->cfg.rec_alpha_residual ? hrn::RES_ALPHA : hrn::RES_NONE;
-        a.res = h->act[cur];
+        a.res = stack;
         a.alphas = alphas;
         a.alpha_stride = L;
         if (run_conv(h, h->fuse[2], a, s)) return -1;
-        if (maybe_dump(dump, HRN_STAGE_FUSE(level, 2), h->act[next], B * half, H, W, 64, s)) return -1;
-        cur = next;
+        if (maybe_dump(dump, HRN_STAGE_FUSE(level, 2), stack, B * half, H, W, 64, s, half, L)) return -1;
+        pair_list += B * half;
         n = half;
         ++level;
     }
     // torch.mean over the single remaining view (HRNet.py:134) is the identity: the loop always ends at n == 1.
 
-    // ---- decoder (HRNet.py:147-156)
+    // ---- decoder (HRNet.py:147-156) on view 0 of every imageset
     {
         SpanGuard guard(h, s, HRN_PROF_DECODER, 74880.0 * static_cast<double>(B) * hw);
-        if (hrn::decoder_umma_launch(h->act[cur], B, H, W, h->wd_img, h->bd, h->prelu_dec, h->wf, h->bf, sr, h->sm_count, s)) return -1;
+        if (hrn::decoder_umma_launch(stack, B, L, H, W, h->wd_img, h->bd, h->prelu_dec, h->wf, h->bf, sr, h->sm_count, s)) return -1;
     }
     if (dump != nullptr && !dump->hit) {
         set_error("hrn_forward_dump: stage 0x%x does not exist for L=%d", dump->stage, L);
@@ -397,6 +420,8 @@ void hrn_destroy(hrn_handle* h) {
     rel(h->wf);
     for (auto* p : h->act) rel(p);
     rel(h->anchor);
+    rel(h->lists);
+    rel(h->live_scratch);
     for (auto* p : h->io) rel(p);
     if (h->copy_in != nullptr) {
         cudaStreamDestroy(h->copy_in);
@@ -671,6 +696,7 @@ int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value) {
     else if (strcmp(knob, "debug_flags") == 0) h->debug_flags = value;
     else if (strcmp(knob, "host_chunks") == 0) h->host_chunks = value;
     else if (strcmp(knob, "workspace_mb") == 0) h->workspace_mb = value > 0 ? value : 65536;
+    else if (strcmp(knob, "skip_dead_views") == 0) h->skip_dead = value != 0;
     else {
         set_error("hrn_debug_set: unknown knob '%s'", knob);
         return -1;

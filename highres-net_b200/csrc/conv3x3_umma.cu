@@ -70,13 +70,19 @@ struct Strip {
     int m, xt, y0, rows;
 };
 
-// The range of flattened rows owned by CTA group gi, cut into per-image strips.
+// The range of flattened rows owned by CTA group gi, cut into per-image strips.  With a live-work list the flattened
+// space covers only the *live_count listed images (the count is known on the device only, so every CTA derives its
+// own share from it) and Strip::m is looked up in the list; the MMA role never needs m and passes want_m = false.
 struct StripWalker {
     long long g, g_end;
     int H, x_tiles;
-    __device__ StripWalker(const Geometry& geo, int gi, int H_) : H(H_), x_tiles(geo.x_tiles) {
-        g = geo.total_rows * gi / geo.groups;
-        g_end = geo.total_rows * (gi + 1) / geo.groups;
+    const int* list;
+    __device__ StripWalker(const Geometry& geo, const ConvArgs& a, int gi, bool want_m = true)
+        : H(a.H), x_tiles(geo.x_tiles), list(want_m ? a.live_list : nullptr) {
+        long long total = geo.total_rows;
+        if (a.live_count != nullptr) total = static_cast<long long>(*a.live_count) * geo.x_tiles * a.H;
+        g = total * gi / geo.groups;
+        g_end = total * (gi + 1) / geo.groups;
     }
     __device__ bool next(Strip& s) {
         if (g >= g_end) return false;
@@ -84,6 +90,7 @@ struct StripWalker {
         s.y0 = static_cast<int>(g % H);
         s.rows = static_cast<int>(min(static_cast<long long>(H - s.y0), g_end - g));
         s.m = static_cast<int>(col / x_tiles);
+        if (list != nullptr) s.m = list[s.m];
         s.xt = static_cast<int>(col % x_tiles);
         g += s.rows;
         return true;
@@ -143,7 +150,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
             for (int off = 0; off < C::W_BYTES; off += 8192) ptx::bulk_copy_g2s(w_s + off, wsrc + off, 8192, bar_w);
             ptx::pdl_wait();                 // weights are constants; the activations come from the previous kernel
             uint32_t it = 0;
-            StripWalker walk(geo, group, a.H);
+            StripWalker walk(geo, a, group);
             Strip s;
             while (walk.next(s)) {
                 int img[2], ch[2];
@@ -187,7 +194,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
             ptx::mbar_wait(bar_w, 0, 2);
             uint32_t it = 0, tile0 = 0;
             bool full_seen = false, tempty_seen = false;          // waits already done by the previous item
-            StripWalker walk(geo, group, a.H);
+            StripWalker walk(geo, a, group, false);
             Strip s;
             bool have = walk.next(s);
             while (have) {
@@ -357,7 +364,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
         const float slope_m1 = a.prelu - 1.0f;   // PReLU(v) = v + (slope - 1) * min(v, 0)
         ptx::pdl_wait();                         // residual reads and output writes touch the previous kernel's tensors
         uint32_t tile = 0;
-        StripWalker walk(geo, group, a.H);
+        StripWalker walk(geo, a, group);
         Strip s;
         while (walk.next(s)) {
             const int x = s.xt * TILE_M + wq * 32 + lane;
@@ -384,7 +391,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
             const __nv_bfloat162 scale2 = __floats2bfloat162_rn(scale, scale);
             const size_t pix0 = static_cast<size_t>(s.y0) * a.W + x;
             const __nv_bfloat16* rp = res_img + pix0 * res_c;
-            __nv_bfloat16* op = a.out + (static_cast<size_t>(s.m) * a.H * a.W + pix0) * a.cout + co0;
+            const int out_img = a.out_in_stack ? (s.m / a.half) * a.src_views + s.m % a.half : s.m;
+            __nv_bfloat16* op = a.out + (static_cast<size_t>(out_img) * a.H * a.W + pix0) * a.cout + co0;
             const size_t r_step = static_cast<size_t>(a.W) * res_c, o_step = static_cast<size_t>(a.W) * a.cout;
             for (int i = 0; i < s.rows; ++i, ++tile, rp += r_step, op += o_step) {
                 const uint32_t acc = tile % ACC_SLOTS, aph = (tile / ACC_SLOTS) & 1;

@@ -36,12 +36,15 @@ struct InitArgs {
     const float* bias;
     float prelu;
     __nv_bfloat16* out;     // (B * L, H, W, 64)
+    const int* live_list;   // live-work list (pointwise.cu): images live_list[0 .. *live_count), nullptr = all B * L
+    const int* live_count;
 };
 
 __device__ __forceinline__ void decode_tile(long long t, const InitArgs& a, int& m, int& y, int& xt) {
     xt = static_cast<int>(t % a.x_tiles);
     y = static_cast<int>((t / a.x_tiles) % a.H);
     m = static_cast<int>(t / (static_cast<long long>(a.x_tiles) * a.H));
+    if (a.live_list != nullptr) m = a.live_list[m];
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -56,6 +59,7 @@ conv_init_umma_kernel(const InitArgs a) {
     float* bias_s = reinterpret_cast<float*>(smem_gen + BIAS_OFFSET);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long tiles = a.live_count != nullptr ? static_cast<long long>(*a.live_count) * a.H * a.x_tiles : a.tiles;
     if (threadIdx.x == 0) {
         for (int i = 0; i < A_RING; ++i) {
             ptx::mbar_init(bar_full + 8 * i, 128);       // every builder thread arrives
@@ -85,7 +89,7 @@ conv_init_umma_kernel(const InitArgs a) {
             constexpr uint32_t idesc = ptx::umma_idesc_bf16(TILE_M, 64);
             const uint32_t a_lo0 = desc_lo(ring_s), b_lo0 = desc_lo(w_s);
             uint32_t it = 0;
-            for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
+            for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
                 const uint32_t slot = it % A_RING, acc = it % ACC_SLOTS;
                 ptx::mbar_wait(bar_tempty + 8 * acc, ((it / ACC_SLOTS) & 1) ^ 1, 4);
                 ptx::mbar_wait(bar_full + 8 * slot, (it / A_RING) & 1, 3);
@@ -130,9 +134,9 @@ conv_init_umma_kernel(const InitArgs a) {
         ptx::pdl_wait();                 // the anchor comes from the previous kernel
         const long long first = static_cast<long long>(blockIdx.x) + static_cast<long long>(set) * gridDim.x;
         const long long stride = 2LL * gridDim.x;
-        if (first < a.tiles) gather(first, v);
+        if (first < tiles) gather(first, v);
         uint32_t it = set;
-        for (long long t = first; t < a.tiles; t += stride, it += 2) {
+        for (long long t = first; t < tiles; t += stride, it += 2) {
             // k = 0..17 hi parts, 18..35 lo parts, 36..47 zero
             __align__(16) __nv_bfloat16 row[48];
 #pragma unroll
@@ -143,7 +147,7 @@ conv_init_umma_kernel(const InitArgs a) {
             }
 #pragma unroll
             for (int k = 36; k < 48; ++k) row[k] = __float2bfloat16_rn(0.0f);
-            if (t + stride < a.tiles) gather(t + stride, v);
+            if (t + stride < tiles) gather(t + stride, v);
             const uint32_t slot = it % A_RING;
             ptx::mbar_wait(bar_empty + 8 * slot, ((it / A_RING) & 1) ^ 1, 1);
             uint8_t* dst = smem_gen + W_BYTES + slot * A_BYTES + px * 128;
@@ -165,7 +169,7 @@ conv_init_umma_kernel(const InitArgs a) {
         for (int e = 0; e < 32; ++e) bias_r[e] = bias_s[hf * 32 + e];
         ptx::pdl_wait();                 // the output buffer may still be read by the previous forward's kernels
         uint32_t it = 0;
-        for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
+        for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
             int m, y, xt;
             decode_tile(t, a, m, y, xt);
             const int x = xt * TILE_M + wq * 32 + lane;
@@ -218,7 +222,8 @@ void conv_init_pack_weights(const float* w, uint8_t* dst) {
 }
 
 int conv_init_umma_launch(const float* lrs, const float* anchor, int B, int L, int H, int W, const uint8_t* w_img,
-                          const float* bias, float prelu, __nv_bfloat16* out, int sm_count, cudaStream_t s) {
+                          const float* bias, float prelu, __nv_bfloat16* out, const int* live_list, const int* live_count,
+                          int sm_count, cudaStream_t s) {
     InitArgs a;
     a.lrs = lrs;
     a.anchor = anchor;
@@ -227,6 +232,8 @@ int conv_init_umma_launch(const float* lrs, const float* anchor, int B, int L, i
     a.W = W;
     a.x_tiles = (W + TILE_M - 1) / TILE_M;
     a.tiles = static_cast<long long>(B) * L * H * a.x_tiles;
+    a.live_list = live_list;
+    a.live_count = live_count;
     a.w_img = w_img;
     a.bias = bias;
     a.prelu = prelu;

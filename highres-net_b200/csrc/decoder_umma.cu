@@ -185,8 +185,8 @@ void decoder_pack_weights(const float* w, uint8_t* dst) {
             }
 }
 
-int decoder_umma_launch(const __nv_bfloat16* in, int B, int H, int W, const uint8_t* w_img, const float* bd, float prelu,
-                        const float* wf, float bf, float* out, int sm_count, cudaStream_t s) {
+int decoder_umma_launch(const __nv_bfloat16* in, int B, int image_stride, int H, int W, const uint8_t* w_img, const float* bd,
+                        float prelu, const float* wf, float bf, float* out, int sm_count, cudaStream_t s) {
     DecArgs a;
     a.B = B;
     a.H = H;
@@ -200,7 +200,7 @@ int decoder_umma_launch(const __nv_bfloat16* in, int B, int H, int W, const uint
     a.bf = bf;
     a.out = out;
     CUtensorMap map;
-    if (encode_nhwc_map(&map, in, 64, W, H, B, TILE_M)) return -1;
+    if (encode_nhwc_map(&map, in, 64, W, H, B, TILE_M, image_stride)) return -1;
     static bool attr_set = false;
     if (!attr_set) {
         HRN_CUDA_OK(cudaFuncSetAttribute(decoder_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

@@ -38,6 +38,8 @@ struct ConvArgs {
     int debug_flags;          // perf triage only: 1 = no TMEM load, 2 = no stores, 4 = no TMA loads, 8 = no residual loads
     // A operand gather.  pair_mode: output image m = (b, i) reads chunk 0 from view i and chunk 1 from
     // view top-1-i of the 64-channel view stack (HRNet.py:114-119); otherwise chunk c = channels [64c, 64c+64).
+    // src_views is the STRIDE of the view stack in images per imageset (the original L at every level: the fusion
+    // writes each level in place over the alice slots), top the number of views the level pairs up.
     int pair_mode, half, src_views, top;
     const void* in;           // bf16 NHWC source tensor (for the TMA map)
     int in_images, in_c;      // its image count and channels per pixel
@@ -52,6 +54,11 @@ struct ConvArgs {
     const __nv_bfloat16* res; // RES_SAME: cout-channel tensor; RES_PAIR / RES_ALPHA: the 64-channel view stack
     const float* alphas;      // (B, alpha_stride) original alphas, RES_ALPHA only
     int alpha_stride;
+    int out_in_stack;         // 1: output image m = (b, i) is written to slot b * src_views + i of the view stack
+    // live-work list (pointwise.cu: live_lists_kernel): the kernel processes images live_list[0 .. *live_count) instead
+    // of 0 .. n_img; both device pointers, nullptr = dense
+    const int* live_list;
+    const int* live_count;
 };
 int conv3x3_bytes_per_weight_image(int cin, int cout);
 // Repack OIHW fp32 (cout, cin, 3, 3) host weights into the pre-swizzled bf16 smem image (host memory).
@@ -65,14 +72,23 @@ int median_anchor_launch(const float* lrs, int B, int L, int H, int W, float* an
 int conv_init_weight_image_bytes();
 void conv_init_pack_weights(const float* w_co_ci_ky_kx, uint8_t* dst);
 int conv_init_umma_launch(const float* lrs, const float* anchor, int B, int L, int H, int W, const uint8_t* w_img,
-                          const float* bias, float prelu, __nv_bfloat16* out, int sm_count, cudaStream_t s);
+                          const float* bias, float prelu, __nv_bfloat16* out, const int* live_list, const int* live_count,
+                          int sm_count, cudaStream_t s);
 // decoder_umma.cu: stride-3 deconv + PReLU + 1x1 conv fused on the tensor cores; in: bf16 NHWC (B, H, W, 64) ->
 // out fp32 (B, 3H, 3W).  w_img = decoder_pack_weights() image (device), bd (64), wf (64) fp32 device.
 int decoder_weight_image_bytes();
 void decoder_pack_weights(const float* w_ci_co_ky_kx, uint8_t* dst);
-int decoder_umma_launch(const __nv_bfloat16* in, int B, int H, int W, const uint8_t* w_img, const float* bd, float prelu,
-                        const float* wf, float bf, float* out, int sm_count, cudaStream_t s);
-int nhwc_bf16_to_nchw_f32_launch(const __nv_bfloat16* in, int n, int H, int W, int C, float* out, cudaStream_t s);
+// image_stride: imageset b is image b * image_stride of `in` (view 0 of the in-place view stack).
+int decoder_umma_launch(const __nv_bfloat16* in, int B, int image_stride, int H, int W, const uint8_t* w_img, const float* bd,
+                        float prelu, const float* wf, float bf, float* out, int sm_count, cudaStream_t s);
+int nhwc_bf16_to_nchw_f32_launch(const __nv_bfloat16* in, int n, int H, int W, int C, int group, int stride, float* out,
+                                 cudaStream_t s);
+// live-work lists (see pointwise.cu)
+int live_levels(int L);
+size_t live_scratch_bytes(int B, int L);
+size_t live_lists_ints(int B, int L);
+int live_lists_launch(const float* alphas, int B, int L, int skip, int alpha_residual, uint8_t* scratch, int* lists,
+                      cudaStream_t s);
 
 // ------------------------------------------------------------------ scoring
 int lanczos_shift_launch(const float* img, const float* shift, int nb, int c, int H, int W, int p, int a,

@@ -35,14 +35,93 @@ __global__ void median_anchor_kernel(const float* __restrict__ lrs, int L, int k
 }
 
 // ------------------------------------------------------------------ bf16 NHWC -> fp32 NCHW (test hook)
-__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, size_t hw, int C, size_t total,
-                                    float* __restrict__ out) {
+// Image n of the dump is image (n / group) * stride + n % group of the source (group == stride: contiguous).
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, size_t hw, int C, size_t total, int group,
+                                    int stride, float* __restrict__ out) {
     const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;   // over n * C * hw (NCHW order)
     if (idx >= total) return;
     const size_t p = idx % hw;
     const size_t c = (idx / hw) % C;
     const size_t n = idx / (hw * C);
-    out[idx] = __bfloat162float(in[(n * hw + p) * C + c]);
+    const size_t src = (n / group) * stride + n % group;
+    out[idx] = __bfloat162float(in[(src * hw + p) * C + c]);
+}
+
+// ------------------------------------------------------------------ live-work lists
+// Which views and view pairs can reach the output?  HRNet.py:123-128 merges a pair as alice + alpha_bob * fuse(alice, bob),
+// so a pair whose bob has alpha = 0 contributes nothing but alice, and everything that only feeds such pairs (the
+// encoder work of zero-padded views, utils.py:89-95, and whole sub-trees of the fusion) never reaches the super-resolved
+// image.  One thread per imageset walks the fusion tree backwards from view 0 of the last level:
+//     need[l + 1][i]                        =>  need[l][i]                       (alice always survives)
+//     need[l + 1][i] and alpha[top-1-i] != 0 =>  pair (l, i) is live, need[l][top-1-i]
+// then the block compacts the flags into index lists (ascending, deterministic).  Layout of `lists`:
+//     [0, 16)                     counts: [0] = live encoder views, [1 + l] = live pairs of level l
+//     [16, 16 + B*L)              encoder list (image index b*L + v)
+//     then per level l            pair list (pair index b*half_l + i), B*half_l entries
+// With skip == 0 every flag is set (dense lists; used by the stage-dump hook).
+constexpr int LIVE_THREADS = 1024;
+
+__device__ void block_compact(const uint8_t* __restrict__ flag, int n, int* __restrict__ list, int* __restrict__ count) {
+    __shared__ int warp_tot[LIVE_THREADS / 32];
+    __shared__ int base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int start = 0; start < n; start += LIVE_THREADS) {
+        const int i = start + threadIdx.x;
+        const bool f = i < n && flag[i] != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        int off = base;
+        for (int w = 0; w < warp; ++w) off += warp_tot[w];
+        if (f) list[off + __popc(bal & ((1u << lane) - 1u))] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < LIVE_THREADS / 32; ++w) tot += warp_tot[w];
+            base += tot;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = base;
+}
+
+__global__ void __launch_bounds__(LIVE_THREADS)
+live_lists_kernel(const float* __restrict__ alphas, int B, int L, int levels, int skip, int alpha_residual,
+                  uint8_t* __restrict__ scratch, int* __restrict__ lists) {
+    // scratch: need[l] at l * B * L (B * n_l entries), pair flags of level l at (levels + 1) * B * L + l * B * L
+    const size_t BL = static_cast<size_t>(B) * L;
+    uint8_t* pair_flags = scratch + (levels + 1) * BL;
+    for (int b = threadIdx.x; b < B; b += LIVE_THREADS) {
+        int n_of[17];
+        n_of[0] = L;
+        for (int l = 0; l < levels; ++l) n_of[l + 1] = n_of[l] / 2;
+        scratch[levels * BL + static_cast<size_t>(b) * n_of[levels]] = 1;        // n_levels == 1: the surviving view
+        for (int l = levels - 1; l >= 0; --l) {
+            const int n = n_of[l], half = n / 2, top = n - (n & 1);
+            uint8_t* need = scratch + l * BL + static_cast<size_t>(b) * n;
+            const uint8_t* need_up = scratch + (l + 1) * BL + static_cast<size_t>(b) * half;
+            uint8_t* pf = pair_flags + l * BL + static_cast<size_t>(b) * half;
+            for (int i = 0; i < n; ++i) need[i] = skip ? 0 : 1;
+            for (int i = 0; i < half; ++i) {
+                const bool wanted = !skip || need_up[i] != 0;
+                const bool live = wanted && (!skip || !alpha_residual || alphas[static_cast<size_t>(b) * L + top - 1 - i] != 0.0f);
+                pf[i] = live ? 1 : 0;
+                if (wanted) need[i] = 1;
+                if (live) need[top - 1 - i] = 1;
+            }
+        }
+    }
+    __syncthreads();
+    block_compact(scratch, static_cast<int>(BL), lists + 16, lists);
+    int off = 16 + static_cast<int>(BL), n = L;
+    for (int l = 0; l < levels; ++l) {
+        const int half = n / 2;
+        block_compact(pair_flags + l * BL, B * half, lists + off, lists + 1 + l);
+        off += B * half;
+        n = half;
+    }
 }
 
 }  // namespace
@@ -56,9 +135,34 @@ int median_anchor_launch(const float* lrs, int B, int L, int H, int W, float* an
     return 0;
 }
 
-int nhwc_bf16_to_nchw_f32_launch(const __nv_bfloat16* in, int n, int H, int W, int C, float* out, cudaStream_t s) {
+int nhwc_bf16_to_nchw_f32_launch(const __nv_bfloat16* in, int n, int H, int W, int C, int group, int stride, float* out,
+                                 cudaStream_t s) {
     const size_t hw = static_cast<size_t>(H) * W, total = hw * C * n;
-    nhwc_to_nchw_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, hw, C, total, out);
+    nhwc_to_nchw_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, hw, C, total, group, stride, out);
+    note_launches(1);
+    HRN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int live_levels(int L) {
+    int levels = 0;
+    for (int n = L; n / 2 > 0; n /= 2) ++levels;
+    return levels;
+}
+
+size_t live_scratch_bytes(int B, int L) { return (2 * static_cast<size_t>(live_levels(L)) + 1) * B * L; }
+size_t live_lists_ints(int B, int L) { return 16 + 2 * static_cast<size_t>(B) * L; }
+
+int live_lists_launch(const float* alphas, int B, int L, int skip, int alpha_residual, uint8_t* scratch, int* lists,
+                      cudaStream_t s) {
+    const int levels = live_levels(L);
+    if (levels > 15) {
+        set_error("hrn_forward: L=%d views need more than 15 fusion levels", L);
+        return -1;
+    }
+    // A plain launch on purpose (no programmatic dependent launch): every later kernel of the forward pass reads the
+    // lists without waiting, which is safe because the kernel after this one only starts once this one has finished.
+    live_lists_kernel<<<1, LIVE_THREADS, 0, s>>>(alphas, B, L, levels, skip, alpha_residual, scratch, lists);
     note_launches(1);
     HRN_CUDA_OK(cudaGetLastError());
     return 0;

@@ -111,14 +111,17 @@ int32_t hrn_clear_loss(const float* sr, const float* hr, const float* hr_map, in
                                       /* j = 0: (B*half, 128, H, W) after block conv 1; 1: after the residual block;
                                          2: (B*half, 64, H, W) merged views of the next level */
 /* Runs the forward like hrn_forward and additionally copies the named intermediate,
- * converted to fp32 NCHW, into `dump` (device, caller-sized).  Returns -1 if the stage does not exist. */
+ * converted to fp32 NCHW, into `dump` (device, caller-sized).  Returns -1 if the stage does not exist.
+ * This hook always computes every view and pair (no dead-view skipping), so all intermediates are defined. */
 int32_t hrn_forward_dump(hrn_handle* h, const float* lrs, const float* alphas, int32_t B, int32_t L, int32_t H,
                          int32_t W, float* sr, int32_t stage, float* dump, void* stream);
 
 /* Test knobs.  "max_ctas" = N > 0 limits the tcgen05 conv kernels to N CTAs (0 = one per SM), which moves
  * the strip boundaries of the row partition; results must not change.  "host_chunks" = pipeline depth of
  * hrn_forward_host (0 = automatic, 1 = no overlap).  "workspace_mb" caps the activation workspace (default 65536 MB);
- * batches that need more are run as consecutive slices with identical results.  "debug_flags" disables parts of the conv kernel for
+ * batches that need more are run as consecutive slices with identical results.  "skip_dead_views" = 0 makes the forward
+ * compute every view and pair even when alpha = 0 padding keeps it from reaching the output (default 1: skipped; the
+ * super-resolved image is bit-identical either way).  "debug_flags" disables parts of the conv kernel for
  * performance triage (results are then garbage). */
 int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value);
 

@@ -175,6 +175,62 @@ def test_alpha_zero_views_are_skipped(net, dev):
     assert np.abs(sr_on - sr).max() > 1e-4         # the alpha mask really is consulted
 
 
+@pytest.mark.parametrize("l,pattern", [
+    (4, [[1, 0, 1, 1], [0, 1, 1, 0]]),                       # holes: a dead alice next to a live bob must still be right
+    (8, [[1, 1, 1, 0, 0, 1, 0, 1], [1, 0, 0, 0, 0, 0, 0, 0]]),
+    (7, [[1, 1, 1, 1, 1, 0, 0], [0, 0, 0, 0, 0, 0, 1]]),     # odd L (last view dropped) and alpha[0] = 0
+    (16, [[1] * 9 + [0] * 7, [1] * 16]),                     # Proba-V style trailing padding
+    (3, [[0, 0, 0], [1, 0, 1]]),
+])
+def test_dead_view_skipping_is_exact(hb, dev, l, pattern):
+    """Views / pairs that cannot reach the output are not computed (live-work lists).  Whatever the alpha pattern, the
+    result must equal the oracle (which computes everything and multiplies by alpha, HRNet.py:123-128) and must be
+    bit-identical to the dense run of the same kernels."""
+    params = hrnet_oracle.make_params(cases.WEIGHT_SEED)
+    model = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval()
+    model.load_state_dict(params)
+    model = model.to(dev)
+    rng = np.random.RandomState(l)
+    lrs = rng.rand(len(pattern), l, 24, 24).astype(np.float32)
+    alphas = np.array(pattern, dtype=np.float32)
+    tl, ta = torch.from_numpy(lrs).to(dev), torch.from_numpy(alphas).to(dev)
+    # poison the workspace first, so that a skipped view that is read anyway shows up
+    model(torch.full_like(tl, 1e4), torch.ones_like(ta))
+    sr = model(tl, ta).cpu().numpy()
+    ref = hrnet_oracle.hrnet_forward(params, lrs, alphas).numpy()
+    assert np.isfinite(sr).all()
+    assert np.abs(sr - ref).max() <= SR_REGRESSION_GATE
+    model.debug_set(dev, "skip_dead_views", 0)
+    dense = model(tl, ta).cpu().numpy()
+    assert np.array_equal(sr, dense)
+
+
+def test_dead_view_skipping_saves_time(hb, net, dev):
+    """B8 L32 64x64 with 12 real views per imageset (config.json n_views = 32, Proba-V scenes average 19 views): the
+    padded run must be clearly cheaper than the all-real run."""
+    lrs = torch.rand(8, 32, 64, 64, device=dev)
+    full = torch.ones(8, 32, device=dev)
+    padded = full.clone()
+    padded[:, 12:] = 0
+    lrs_p = lrs.clone()
+    lrs_p[:, 12:] = 0
+
+    def timed(x, a):
+        for _ in range(3):
+            net(x, a)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            net(x, a)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 10
+
+    t_full, t_pad = timed(lrs, full), timed(lrs_p, padded)
+    assert t_pad < 0.7 * t_full, (t_full, t_pad)
+
+
 def test_full_size_properties_c2(net, dev):
     """BASELINE.json configs[1] size (B32 L16 128x128): size-independent properties.
     Imagesets are independent => each batch row equals the same imageset run alone (bit-exact:
