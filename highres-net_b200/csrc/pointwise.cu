@@ -61,7 +61,8 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, size_t
 // With skip == 0 every flag is set (dense lists; used by the stage-dump hook).
 constexpr int LIVE_THREADS = 1024;
 
-__device__ void block_compact(const uint8_t* __restrict__ flag, int n, int* __restrict__ list, int* __restrict__ count) {
+// `flag` may point to shared or global memory: a generic pointer, deliberately without __restrict__ / read-only hints.
+__device__ void block_compact(const uint8_t* flag, int n, int* list, int* count) {
     __shared__ int warp_tot[LIVE_THREADS / 32];
     __shared__ int base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -89,8 +90,11 @@ __device__ void block_compact(const uint8_t* __restrict__ flag, int n, int* __re
 
 __global__ void __launch_bounds__(LIVE_THREADS)
 live_lists_kernel(const float* __restrict__ alphas, int B, int L, int levels, int skip, int alpha_residual,
-                  uint8_t* __restrict__ scratch, int* __restrict__ lists) {
-    // scratch: need[l] at l * B * L (B * n_l entries), pair flags of level l at (levels + 1) * B * L + l * B * L
+                  uint8_t* __restrict__ scratch_global, int use_smem, int* __restrict__ lists) {
+    // scratch: need[l] at l * B * L (B * n_l entries), pair flags of level l at (levels + 1) * B * L + l * B * L;
+    // kept in shared memory whenever it fits (always for Proba-V sized batches)
+    extern __shared__ uint8_t scratch_smem[];
+    uint8_t* scratch = use_smem ? scratch_smem : scratch_global;
     const size_t BL = static_cast<size_t>(B) * L;
     uint8_t* pair_flags = scratch + (levels + 1) * BL;
     for (int b = threadIdx.x; b < B; b += LIVE_THREADS) {
@@ -162,7 +166,10 @@ int live_lists_launch(const float* alphas, int B, int L, int skip, int alpha_res
     }
     // A plain launch on purpose (no programmatic dependent launch): every later kernel of the forward pass reads the
     // lists without waiting, which is safe because the kernel after this one only starts once this one has finished.
-    live_lists_kernel<<<1, LIVE_THREADS, 0, s>>>(alphas, B, L, levels, skip, alpha_residual, scratch, lists);
+    const size_t bytes = live_scratch_bytes(B, L);
+    const int use_smem = bytes <= 40 * 1024;
+    live_lists_kernel<<<1, LIVE_THREADS, use_smem ? bytes : 0, s>>>(alphas, B, L, levels, skip, alpha_residual, scratch,
+                                                                    use_smem, lists);
     note_launches(1);
     HRN_CUDA_OK(cudaGetLastError());
     return 0;

@@ -64,7 +64,10 @@ int32_t hrn_missing_weights(const hrn_handle* h);
 /* Replaces HRNet.forward (HRNet.py:186-211).  DEVICE pointers:
  *   lrs (B, L, H, W) fp32 contiguous, alphas (B, L) fp32, sr (B, 1, 3H, 3W) fp32 out.
  * Square inputs only (H == W), as the reference's view() at HRNet.py:204 requires.  The handle keeps 5 activation
- * buffers of B*L*H*W*128 bytes (bf16 NHWC), capped at 64 GiB by slicing the batch. */
+ * buffers of B*L*H*W*128 bytes (bf16 NHWC), capped at 64 GiB by slicing the batch.
+ * Views and view pairs that cannot reach the output because of alpha = 0 (HRNet.py:123-128: alice + alpha_bob * x) are
+ * not computed; the result is the one the reference produces for finite inputs.  Everything is enqueued on `stream`,
+ * nothing synchronises with the host. */
 int32_t hrn_forward(hrn_handle* h, const float* lrs, const float* alphas, int32_t B, int32_t L, int32_t H,
                     int32_t W, float* sr, void* stream);
 

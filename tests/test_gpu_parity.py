@@ -205,6 +205,22 @@ def test_dead_view_skipping_is_exact(hb, dev, l, pattern):
     assert np.array_equal(sr, dense)
 
 
+def test_dead_view_lists_large_batch(net, dev):
+    """B * L large enough that the liveness scratch leaves shared memory (global-memory path of live_lists_kernel):
+    every imageset of the batch must equal the same imageset run alone."""
+    rng = np.random.RandomState(11)
+    b, l = 300, 32
+    lrs = torch.from_numpy(rng.rand(b, l, 16, 16).astype(np.float32)).to(dev)
+    real = rng.randint(1, l + 1, size=b)
+    alphas = torch.zeros(b, l, device=dev)
+    for i, n in enumerate(real):
+        alphas[i, :n] = 1
+        lrs[i, n:] = 0
+    sr = net(lrs, alphas)
+    for i in (0, 1, 57, 150, 299):
+        assert torch.equal(sr[i:i + 1], net(lrs[i:i + 1], alphas[i:i + 1])), i
+
+
 def test_dead_view_skipping_saves_time(hb, net, dev):
     """B8 L32 64x64 with 12 real views per imageset (config.json n_views = 32, Proba-V scenes average 19 views): the
     padded run must be clearly cheaper than the all-real run."""
