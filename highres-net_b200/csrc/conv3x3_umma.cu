@@ -148,11 +148,14 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
             ptx::mbar_expect_tx(bar_w, C::W_BYTES);
             const uint8_t* wsrc = a.w_img + static_cast<size_t>(part) * C::W_BYTES;
             for (int off = 0; off < C::W_BYTES; off += 8192) ptx::bulk_copy_g2s(w_s + off, wsrc + off, 8192, bar_w);
-            ptx::pdl_wait();                 // weights are constants; the activations come from the previous kernel
-            uint32_t it = 0;
+            // The live-work list was finished long before the previous kernel started (live_lists_launch), so the
+            // first strip is resolved while that kernel may still be running.
             StripWalker walk(geo, a, group);
             Strip s;
-            while (walk.next(s)) {
+            bool have = walk.next(s);
+            ptx::pdl_wait();                 // weights are constants; the activations come from the previous kernel
+            uint32_t it = 0;
+            for (; have; have = walk.next(s)) {
                 int img[2], ch[2];
                 if (a.pair_mode) {
                     const int b = s.m / a.half, i = s.m % a.half;
@@ -362,11 +365,12 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
         for (int e = 0; e < 32; ++e) bias_r[e] = bias_s[hf * 32 + e];
         const bool has_prelu = a.has_prelu != 0;
         const float slope_m1 = a.prelu - 1.0f;   // PReLU(v) = v + (slope - 1) * min(v, 0)
-        ptx::pdl_wait();                         // residual reads and output writes touch the previous kernel's tensors
-        uint32_t tile = 0;
         StripWalker walk(geo, a, group);
         Strip s;
-        while (walk.next(s)) {
+        bool have = walk.next(s);
+        ptx::pdl_wait();                         // residual reads and output writes touch the previous kernel's tensors
+        uint32_t tile = 0;
+        for (; have; have = walk.next(s)) {
             const int x = s.xt * TILE_M + wq * 32 + lane;
             const bool valid = x < a.W;
             const __nv_bfloat16* res_img = nullptr;
