@@ -26,7 +26,7 @@ static_assert(16 * A_RING + 16 + 16 + 8 + 8 <= 256, "barrier block overflows int
 
 struct DecArgs {
     int B, H, W, x_tiles;
-    long long tiles;                           // B * H * x_tiles
+    uint32_t tiles;                            // B * H * x_tiles (31 bits, checked by the launcher)
     const uint8_t* w_img;                      // pre-swizzled B image (device)
     const float* bd;                           // deconv bias (64)
     const float* wf;                           // final 1x1 weights (64)
@@ -77,10 +77,10 @@ decoder_umma_kernel(const __grid_constant__ CUtensorMap in_map, const DecArgs a)
             for (int off = 0; off < W_BYTES; off += 8192) ptx::bulk_copy_g2s(w_s + off, a.w_img + off, 8192, bar_w);
             ptx::pdl_wait();
             uint32_t it = 0;
-            for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
-                const int xt = static_cast<int>(t % a.x_tiles);
-                const int y = static_cast<int>((t / a.x_tiles) % a.H);
-                const int b = static_cast<int>(t / (static_cast<long long>(a.x_tiles) * a.H));
+            for (uint32_t t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
+                const uint32_t per_img = static_cast<uint32_t>(a.x_tiles) * a.H;
+                const uint32_t bi = t / per_img, rem = t - bi * per_img, yy = a.x_tiles == 1 ? rem : rem / a.x_tiles;
+                const int xt = static_cast<int>(rem - yy * a.x_tiles), y = static_cast<int>(yy), b = static_cast<int>(bi);
                 const uint32_t slot = it % A_RING;
                 ptx::mbar_wait(bar_empty + 8 * slot, ((it / A_RING) & 1) ^ 1, 1);
                 ptx::mbar_expect_tx(bar_full + 8 * slot, A_BYTES);
@@ -93,7 +93,7 @@ decoder_umma_kernel(const __grid_constant__ CUtensorMap in_map, const DecArgs a)
             const uint32_t a_lo0 = desc_lo(ring_s), b_lo0 = desc_lo(w_s);
             ptx::mbar_wait(bar_w, 0, 2);
             uint32_t it = 0, grp = 0;
-            for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
+            for (uint32_t t = blockIdx.x; t < a.tiles; t += gridDim.x, ++it) {
                 const uint32_t slot = it % A_RING;
                 ptx::mbar_wait(bar_full + 8 * slot, (it / A_RING) & 1, 3);
                 ptx::tc_fence_after();
@@ -121,10 +121,10 @@ decoder_umma_kernel(const __grid_constant__ CUtensorMap in_map, const DecArgs a)
         const float slope_m1 = a.prelu - 1.0f;
         ptx::pdl_wait();
         uint32_t grp = 0;
-        for (long long t = blockIdx.x; t < a.tiles; t += gridDim.x) {
-            const int xt = static_cast<int>(t % a.x_tiles);
-            const int y = static_cast<int>((t / a.x_tiles) % a.H);
-            const int b = static_cast<int>(t / (static_cast<long long>(a.x_tiles) * a.H));
+        for (uint32_t t = blockIdx.x; t < a.tiles; t += gridDim.x) {
+            const uint32_t per_img = static_cast<uint32_t>(a.x_tiles) * a.H;
+            const uint32_t bi = t / per_img, rem = t - bi * per_img, yy = a.x_tiles == 1 ? rem : rem / a.x_tiles;
+            const int xt = static_cast<int>(rem - yy * a.x_tiles), y = static_cast<int>(yy), b = static_cast<int>(bi);
             const int x = xt * TILE_M + wq * 32 + lane;
 #pragma unroll 1
             for (int g = 0; g < 3; ++g, ++grp) {
@@ -192,7 +192,12 @@ int decoder_umma_launch(const __nv_bfloat16* in, int B, int image_stride, int H,
     a.H = H;
     a.W = W;
     a.x_tiles = (W + TILE_M - 1) / TILE_M;
-    a.tiles = static_cast<long long>(B) * H * a.x_tiles;
+    const long long tiles64 = static_cast<long long>(B) * H * a.x_tiles;
+    if (tiles64 >= (1LL << 31) - sm_count) {
+        set_error("decoder: %lld row tiles exceed the 31-bit tile index; split the batch", tiles64);
+        return -1;
+    }
+    a.tiles = static_cast<uint32_t>(tiles64);
     a.w_img = w_img;
     a.bd = bd;
     a.wf = wf;
