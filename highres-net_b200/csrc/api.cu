@@ -60,6 +60,7 @@ struct hrn_handle {
     size_t io_cap[3] = {0, 0, 0};
     float* io[3] = {nullptr, nullptr, nullptr};   // device staging for hrn_forward_host: lrs, alphas, sr
     int max_ctas = 0;                  // 0 = one CTA per SM (test knob)
+    int strip_split = 0;               // ranges of the row space per CTA (0/1 = one contiguous range)
     int host_chunks = 0;               // hrn_forward_host pipeline depth (0 = automatic)
     long long workspace_mb = 65536;    // cap on the activation workspace; larger batches are run in slices
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of hrn_forward_host
@@ -174,6 +175,7 @@ int run_conv(hrn_handle* h, const hrn::ConvLayer& l, hrn::ConvArgs a, cudaStream
     a.prelu = l.prelu;
     a.has_prelu = l.has_prelu ? 1 : 0;
     a.max_ctas = h->max_ctas;
+    a.strip_split = h->strip_split;
     a.debug_flags = h->debug_flags;
     return hrn::conv3x3_launch(a, h->sm_count, s);
 }
@@ -697,6 +699,7 @@ int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value) {
     else if (strcmp(knob, "host_chunks") == 0) h->host_chunks = value;
     else if (strcmp(knob, "workspace_mb") == 0) h->workspace_mb = value > 0 ? value : 65536;
     else if (strcmp(knob, "skip_dead_views") == 0) h->skip_dead = value != 0;
+    else if (strcmp(knob, "strip_split") == 0) h->strip_split = value;
     else {
         set_error("hrn_debug_set: unknown knob '%s'", knob);
         return -1;

@@ -64,6 +64,7 @@ struct Geometry {
     int groups;       // CTAs per part
     int x_tiles;      // ceil(W / 128)
     long long total_rows;   // n_img * x_tiles * H
+    int split;        // ranges per CTA group (round-robin), >= 1
 };
 
 struct Strip {
@@ -74,18 +75,26 @@ struct Strip {
 // space covers only the *live_count listed images (the count is known on the device only, so every CTA derives its
 // own share from it) and Strip::m is looked up in the list; the MMA role never needs m and passes want_m = false.
 struct StripWalker {
-    long long g, g_end;
-    int H, x_tiles;
+    long long total, g, g_end;
+    int H, x_tiles, vg, vg_total, vg_stride;
     const int* list;
+    // The flattened space is cut into groups * split equal ranges dealt round-robin to the CTA groups (split = 1: one
+    // contiguous range per CTA).
     __device__ StripWalker(const Geometry& geo, const ConvArgs& a, int gi, bool want_m = true)
-        : H(a.H), x_tiles(geo.x_tiles), list(want_m ? a.live_list : nullptr) {
-        long long total = geo.total_rows;
+        : H(a.H), x_tiles(geo.x_tiles), vg(gi), vg_total(geo.groups * geo.split), vg_stride(geo.groups),
+          list(want_m ? a.live_list : nullptr) {
+        total = geo.total_rows;
         if (a.live_count != nullptr) total = static_cast<long long>(*a.live_count) * geo.x_tiles * a.H;
-        g = total * gi / geo.groups;
-        g_end = total * (gi + 1) / geo.groups;
+        g = total * vg / vg_total;
+        g_end = total * (vg + 1) / vg_total;
     }
     __device__ bool next(Strip& s) {
-        if (g >= g_end) return false;
+        while (g >= g_end) {
+            vg += vg_stride;
+            if (vg >= vg_total) return false;
+            g = total * vg / vg_total;
+            g_end = total * (vg + 1) / vg_total;
+        }
         const long long col = g / H;
         s.y0 = static_cast<int>(g % H);
         s.rows = static_cast<int>(min(static_cast<long long>(H - s.y0), g_end - g));
@@ -503,6 +512,7 @@ int conv3x3_launch(const ConvArgs& a, int sm_count, cudaStream_t stream) {
     ctas = std::max(g.n_parts, (ctas / g.n_parts) * g.n_parts);
     g.groups = static_cast<int>(std::min<long long>(ctas / g.n_parts, g.total_rows));
     ctas = g.groups * g.n_parts;
+    g.split = a.strip_split > 0 ? a.strip_split : 1;
 
     CUtensorMap map;
     if (encode_nhwc_map(&map, a.in, a.in_c, a.W, a.H, a.in_images, SLOT_PIX)) return -1;

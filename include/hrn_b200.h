@@ -120,7 +120,8 @@ int32_t hrn_forward_dump(hrn_handle* h, const float* lrs, const float* alphas, i
                          int32_t W, float* sr, int32_t stage, float* dump, void* stream);
 
 /* Test knobs.  "max_ctas" = N > 0 limits the tcgen05 conv kernels to N CTAs (0 = one per SM), which moves
- * the strip boundaries of the row partition; results must not change.  "host_chunks" = pipeline depth of
+ * the strip boundaries of the row partition; "strip_split" = k > 1 gives every CTA k shorter row ranges dealt round-robin
+ * instead of one contiguous range (measured slower: tools/strip_split.py); results must not change.  "host_chunks" = pipeline depth of
  * hrn_forward_host (0 = automatic, 1 = no overlap).  "workspace_mb" caps the activation workspace (default 65536 MB);
  * batches that need more are run as consecutive slices with identical results.  "skip_dead_views" = 0 makes the forward
  * compute every view and pair even when alpha = 0 padding keeps it from reaching the output (default 1: skipped; the

@@ -286,6 +286,10 @@ def test_row_partition_does_not_change_results(hb, dev):
         model = model.to(dev)
         model.debug_set(dev, "max_ctas", ctas)
         outs.append(model(tl, ta))
+    for split in (3, 16, 1000):             # several short ranges per CTA, dealt round-robin (1000: mostly empty ranges)
+        model.debug_set(dev, "max_ctas", 5)
+        model.debug_set(dev, "strip_split", split)
+        outs.append(model(tl, ta))
     for o in outs[1:]:
         assert torch.equal(o, outs[0])
 
