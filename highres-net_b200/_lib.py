@@ -32,6 +32,9 @@ SYMBOLS = {
     "hrn_forward": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "hrn_forward_host": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                    c_void_p]),
+    "hrn_forward_host_u16": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                       c_void_p]),
+    "hrn_u16_to_unit_float": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),
     "hrn_lanczos_shift": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                     c_int32, c_void_p, c_void_p]),
     "hrn_lanczos_taps": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),

@@ -59,6 +59,8 @@ struct hrn_handle {
     int skip_dead = 1;                 // 0: process every view and pair even when it cannot reach the output (test knob)
     size_t io_cap[3] = {0, 0, 0};
     float* io[3] = {nullptr, nullptr, nullptr};   // device staging for hrn_forward_host: lrs, alphas, sr
+    uint16_t* io_u16 = nullptr;                   // raw uint16 views of hrn_forward_host_u16
+    size_t io_u16_cap = 0;
     int max_ctas = 0;                  // 0 = one CTA per SM (test knob)
     int strip_split = 0;               // ranges of the row space per CTA (0/1 = one contiguous range)
     int host_chunks = 0;               // hrn_forward_host pipeline depth (0 = automatic)
@@ -425,6 +427,7 @@ void hrn_destroy(hrn_handle* h) {
     rel(h->lists);
     rel(h->live_scratch);
     for (auto* p : h->io) rel(p);
+    rel(h->io_u16);
     if (h->copy_in != nullptr) {
         cudaStreamDestroy(h->copy_in);
         cudaStreamDestroy(h->copy_out);
@@ -552,8 +555,10 @@ int32_t hrn_forward_dump(hrn_handle* h, const float* lrs, const float* alphas, i
     return forward_impl(h, lrs, alphas, B, L, H, W, sr, static_cast<cudaStream_t>(stream), &d);
 }
 
-int32_t hrn_forward_host(hrn_handle* h, const float* lrs_host, const float* alphas_host, int32_t B, int32_t L,
-                         int32_t H, int32_t W, float* sr_host, void* stream) {
+// Shared body of hrn_forward_host / hrn_forward_host_u16.  lrs_u16 != nullptr: the views arrive as raw uint16 (half the
+// H2D bytes) and become float32 on the device.
+static int forward_host_impl(hrn_handle* h, const float* lrs_host, const uint16_t* lrs_u16, const float* alphas_host,
+                             int32_t B, int32_t L, int32_t H, int32_t W, float* sr_host, void* stream) {
     if (h == nullptr) {
         set_error("null handle");
         return -1;
@@ -568,6 +573,7 @@ int32_t hrn_forward_host(hrn_handle* h, const float* lrs_host, const float* alph
     if (grow(reinterpret_cast<void**>(&h->io[0]), &h->io_cap[0], B * set_in * 4)) return -1;
     if (grow(reinterpret_cast<void**>(&h->io[1]), &h->io_cap[1], static_cast<size_t>(B) * L * 4)) return -1;
     if (grow(reinterpret_cast<void**>(&h->io[2]), &h->io_cap[2], B * set_out * 4)) return -1;
+    if (lrs_u16 != nullptr && grow(reinterpret_cast<void**>(&h->io_u16), &h->io_u16_cap, B * set_in * 2)) return -1;
     if (h->copy_in == nullptr) {
         HRN_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
         HRN_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
@@ -589,8 +595,12 @@ int32_t hrn_forward_host(hrn_handle* h, const float* lrs_host, const float* alph
     for (int k = 0; k < chunks; ++k) {
         const int b0 = k * per, nb = (b0 + per <= B ? per : B - b0);
         if (nb <= 0) break;
-        HRN_CUDA_OK(cudaMemcpyAsync(h->io[0] + b0 * set_in, lrs_host + b0 * set_in, nb * set_in * 4, cudaMemcpyHostToDevice,
-                                    h->copy_in));
+        if (lrs_u16 != nullptr)
+            HRN_CUDA_OK(cudaMemcpyAsync(h->io_u16 + b0 * set_in, lrs_u16 + b0 * set_in, nb * set_in * 2,
+                                        cudaMemcpyHostToDevice, h->copy_in));
+        else
+            HRN_CUDA_OK(cudaMemcpyAsync(h->io[0] + b0 * set_in, lrs_host + b0 * set_in, nb * set_in * 4,
+                                        cudaMemcpyHostToDevice, h->copy_in));
         HRN_CUDA_OK(cudaMemcpyAsync(h->io[1] + static_cast<size_t>(b0) * L, alphas_host + static_cast<size_t>(b0) * L,
                                     static_cast<size_t>(nb) * L * 4, cudaMemcpyHostToDevice, h->copy_in));
         HRN_CUDA_OK(cudaEventRecord(h->ev_in[k], h->copy_in));
@@ -599,6 +609,8 @@ int32_t hrn_forward_host(hrn_handle* h, const float* lrs_host, const float* alph
         const int b0 = k * per, nb = (b0 + per <= B ? per : B - b0);
         if (nb <= 0) break;
         HRN_CUDA_OK(cudaStreamWaitEvent(s, h->ev_in[k], 0));
+        if (lrs_u16 != nullptr && hrn::u16_to_unit_float_launch(h->io_u16 + b0 * set_in, nb * set_in, h->io[0] + b0 * set_in, s))
+            return -1;
         if (forward_sliced(h, h->io[0] + b0 * set_in, h->io[1] + static_cast<size_t>(b0) * L, nb, L, H, W,
                            h->io[2] + b0 * set_out, s))
             return -1;
@@ -610,6 +622,32 @@ int32_t hrn_forward_host(hrn_handle* h, const float* lrs_host, const float* alph
     HRN_CUDA_OK(cudaStreamSynchronize(h->copy_out));
     HRN_CUDA_OK(cudaStreamSynchronize(s));
     return 0;
+}
+
+int32_t hrn_forward_host(hrn_handle* h, const float* lrs_host, const float* alphas_host, int32_t B, int32_t L,
+                         int32_t H, int32_t W, float* sr_host, void* stream) {
+    if (lrs_host == nullptr || alphas_host == nullptr || sr_host == nullptr) {
+        set_error("hrn_forward_host: null pointer");
+        return -1;
+    }
+    return forward_host_impl(h, lrs_host, nullptr, alphas_host, B, L, H, W, sr_host, stream);
+}
+
+int32_t hrn_forward_host_u16(hrn_handle* h, const uint16_t* lrs_host, const float* alphas_host, int32_t B, int32_t L,
+                             int32_t H, int32_t W, float* sr_host, void* stream) {
+    if (lrs_host == nullptr || alphas_host == nullptr || sr_host == nullptr) {
+        set_error("hrn_forward_host_u16: null pointer");
+        return -1;
+    }
+    return forward_host_impl(h, nullptr, lrs_host, alphas_host, B, L, H, W, sr_host, stream);
+}
+
+int32_t hrn_u16_to_unit_float(const uint16_t* src, int64_t n, float* dst, void* stream) {
+    if (src == nullptr || dst == nullptr || n < 0) {
+        set_error("hrn_u16_to_unit_float: bad argument");
+        return -1;
+    }
+    return n == 0 ? 0 : hrn::u16_to_unit_float_launch(src, static_cast<size_t>(n), dst, static_cast<cudaStream_t>(stream));
 }
 
 int32_t hrn_lanczos_shift(const float* img, const float* shift, int32_t Nb, int32_t C, int32_t H, int32_t W, int32_t p,

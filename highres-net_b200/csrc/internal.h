@@ -84,6 +84,7 @@ int decoder_umma_launch(const __nv_bfloat16* in, int B, int image_stride, int H,
                         float prelu, const float* wf, float bf, float* out, int sm_count, cudaStream_t s);
 int nhwc_bf16_to_nchw_f32_launch(const __nv_bfloat16* in, int n, int H, int W, int C, int group, int stride, float* out,
                                  cudaStream_t s);
+int u16_to_unit_float_launch(const uint16_t* in, size_t n, float* out, cudaStream_t s);
 // live-work lists (see pointwise.cu)
 int live_levels(int L);
 size_t live_scratch_bytes(int B, int L);

@@ -47,6 +47,14 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, size_t
     out[idx] = __bfloat162float(in[(src * hw + p) * C + c]);
 }
 
+// ------------------------------------------------------------------ uint16 pixels -> float32 in [0, 1]
+// DataLoader.py:195-198: skimage.img_as_float(uint16).astype(float32) = RN32(x / 65535).  A true fp32 division gives the
+// same bits for all 65536 inputs; multiplying by an fp32 reciprocal does not (512 values differ).
+__global__ void u16_to_unit_float_kernel(const uint16_t* __restrict__ in, size_t n, float* __restrict__ out) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        out[i] = __fdiv_rn(static_cast<float>(in[i]), 65535.0f);
+}
+
 // ------------------------------------------------------------------ live-work lists
 // Which views and view pairs can reach the output?  HRNet.py:123-128 merges a pair as alice + alpha_bob * fuse(alice, bob),
 // so a pair whose bob has alpha = 0 contributes nothing but alice, and everything that only feeds such pairs (the
@@ -143,6 +151,14 @@ int nhwc_bf16_to_nchw_f32_launch(const __nv_bfloat16* in, int n, int H, int W, i
                                  cudaStream_t s) {
     const size_t hw = static_cast<size_t>(H) * W, total = hw * C * n;
     nhwc_to_nchw_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, hw, C, total, group, stride, out);
+    note_launches(1);
+    HRN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int u16_to_unit_float_launch(const uint16_t* in, size_t n, float* out, cudaStream_t s) {
+    const size_t want = (n + 255) / 256;
+    u16_to_unit_float_kernel<<<static_cast<unsigned>(want < 148 * 16 ? want : 148 * 16), 256, 0, s>>>(in, n, out);
     note_launches(1);
     HRN_CUDA_OK(cudaGetLastError());
     return 0;

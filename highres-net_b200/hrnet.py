@@ -144,10 +144,13 @@ class HRNet(nn.Module):
     def forward_host(self, lrs_host: torch.Tensor, alphas_host: torch.Tensor, out_host: torch.Tensor = None,
                      device="cuda:0") -> torch.Tensor:
         """Host-buffer variant of the train.py:200-208 pattern (H2D, forward, D2H) through hrn_forward_host.
-        Inputs are CPU float32 tensors (pinned memory recommended); returns a CPU tensor."""
+        Inputs are CPU float32 tensors (pinned memory recommended); returns a CPU tensor.  ``lrs_host`` may also be a
+        uint16 tensor holding the raw 16-bit views (DataLoader.py:134): it is then copied as is and scaled to [0, 1] on
+        the device exactly like DataLoader.py:195-198 (hrn_forward_host_u16)."""
         if lrs_host.is_cuda or alphas_host.is_cuda:
             raise ValueError("forward_host takes host tensors")
-        lrs_host = lrs_host.to(torch.float32).contiguous()
+        raw16 = lrs_host.dtype == torch.uint16
+        lrs_host = lrs_host.contiguous() if raw16 else lrs_host.to(torch.float32).contiguous()
         alphas_host = alphas_host.to(torch.float32).contiguous()
         b, l, h, w = lrs_host.shape
         device = torch.device(device)
@@ -155,9 +158,9 @@ class HRNet(nn.Module):
         if out_host is None:
             out_host = torch.empty((b, 1, 3 * h, 3 * w), dtype=torch.float32, pin_memory=True)
         with torch.cuda.device(device):
-            _lib.check(_lib.load().hrn_forward_host(handle, lrs_host.data_ptr(), alphas_host.data_ptr(), b, l, h, w,
-                                                    out_host.data_ptr(), _lib.current_stream_ptr(device)),
-                       "hrn_forward_host")
+            entry = _lib.load().hrn_forward_host_u16 if raw16 else _lib.load().hrn_forward_host
+            _lib.check(entry(handle, lrs_host.data_ptr(), alphas_host.data_ptr(), b, l, h, w, out_host.data_ptr(),
+                             _lib.current_stream_ptr(device)), "hrn_forward_host_u16" if raw16 else "hrn_forward_host")
         return out_host
 
     def forward_stage(self, lrs, alphas, stage: int, shape):

@@ -14,7 +14,22 @@ from collections.abc import Mapping
 import numpy as np
 import torch
 
+from . import _lib
 from .evaluator import shift_cPSNR
+
+
+def img_as_float_u16(raw):
+    """DataLoader.py:195-198 on the device: ``skimage.img_as_float(lr).astype(np.float32)`` for 16-bit views, i.e.
+    x / 65535 with the same rounding.  raw: CUDA uint16 tensor (any shape) -> float32 tensor of that shape."""
+    _lib.require_cuda_tensor(raw, "raw")
+    if raw.dtype != torch.uint16:
+        raise TypeError("img_as_float_u16 expects a uint16 tensor (the on-disk format of the Proba-V views)")
+    src = raw.contiguous()
+    out = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        _lib.check(_lib.load().hrn_u16_to_unit_float(src.data_ptr(), src.numel(), out.data_ptr(),
+                                                     _lib.current_stream_ptr(src.device)), "hrn_u16_to_unit_float")
+    return out
 
 
 class collateFunction:

@@ -77,6 +77,14 @@ int32_t hrn_forward(hrn_handle* h, const float* lrs, const float* alphas, int32_
 int32_t hrn_forward_host(hrn_handle* h, const float* lrs_host, const float* alphas_host, int32_t B, int32_t L,
                          int32_t H, int32_t W, float* sr_host, void* stream);
 
+/* hrn_forward_host for views still in the on-disk 16-bit format (DataLoader.py:134, 195-198: io.imread -> uint16,
+ * skimage.img_as_float(...).astype(float32) = x / 65535): lrs_host is (B, L, H, W) uint16, copied as is (half the H2D
+ * bytes) and converted on the device with the same rounding.  hrn_u16_to_unit_float is that conversion alone on
+ * DEVICE pointers (n elements). */
+int32_t hrn_forward_host_u16(hrn_handle* h, const uint16_t* lrs_host, const float* alphas_host, int32_t B, int32_t L,
+                             int32_t H, int32_t W, float* sr_host, void* stream);
+int32_t hrn_u16_to_unit_float(const uint16_t* src, int64_t n, float* dst, void* stream);
+
 /* Replaces lanczos.lanczos_shift (src/lanczos.py:47-107) incl. lanczos_kernel (5-43).
  * DEVICE pointers: img (Nb, C, H, W) fp32, shift (C, 2) = (dy, dx) per channel, out like img.
  * p = reflect padding width, a = lobes, ntaps = N (odd). */

@@ -577,3 +577,28 @@ def test_apply_shifts_integer_theta_is_a_roll(hb, dev):
     assert torch.allclose(out[0, 1], img[0, 1], atol=2e-6)
     ref = scoring_oracle.apply_shifts(img.cpu().numpy(), theta.cpu().numpy())
     assert np.abs(out.cpu().numpy() - ref).max() <= LANCZOS_GATE
+
+
+# ---------------------------------------------------------------------------- 16-bit view ingestion
+def test_u16_views_scale_like_the_dataloader(hb, dev):
+    """DataLoader.py:195-198 = skimage.img_as_float(uint16).astype(float32): x / 65535 (or x * (1 / 65535)) in float64,
+    rounded once to float32.  All 65536 inputs must come out bit-identical."""
+    from highres_net_b200 import predict
+    x = np.arange(65536, dtype=np.uint16)
+    got = predict.img_as_float_u16(torch.from_numpy(x).to(dev)).cpu().numpy()
+    assert np.array_equal(got, (x.astype(np.float64) / 65535.0).astype(np.float32))
+    assert np.array_equal(got, (x.astype(np.float64) * (1.0 / 65535.0)).astype(np.float32))
+    with pytest.raises(Exception):
+        predict.img_as_float_u16(torch.from_numpy(x))                          # host tensor: no CPU fallback
+
+
+def test_forward_host_accepts_raw_u16_views(net, dev):
+    rng = np.random.RandomState(8)
+    raw = rng.randint(0, 1 << 14, size=(3, 5, 32, 32)).astype(np.uint16)       # Proba-V views are 14-bit in 16-bit PNGs
+    alphas = np.ones((3, 5), dtype=np.float32)
+    alphas[1, 3:] = 0
+    raw[1, 3:] = 0
+    as_float = torch.from_numpy((raw.astype(np.float64) / 65535.0).astype(np.float32))
+    a = net.forward_host(torch.from_numpy(raw), torch.from_numpy(alphas), device=dev)
+    b = net.forward_host(as_float, torch.from_numpy(alphas), device=dev)
+    assert torch.equal(a, b)
