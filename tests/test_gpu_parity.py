@@ -346,6 +346,31 @@ def test_forward_on_side_stream(net, dev):
     assert torch.equal(out, ref) and big.shape == (4096, 4096)
 
 
+def test_two_handles_on_two_streams(hb, dev):
+    """Handles own their workspace and live-work lists: two models with different weights, interleaved on two streams,
+    must each reproduce their own sequential result bit for bit."""
+    lrs, alphas = cases.hrnet_inputs("b2_l9_s16")
+    tl, ta = torch.from_numpy(lrs).to(dev), torch.from_numpy(alphas).to(dev)
+    models = []
+    for seed in (0, 1):
+        m = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval()
+        m.load_state_dict(hrnet_oracle.make_params(seed))
+        models.append(m.to(dev))
+    refs = [m(tl, ta).clone() for m in models]
+    assert not torch.equal(refs[0], refs[1])
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(device=dev) for _ in models]
+    outs = [[], []]
+    for _ in range(8):
+        for k, (m, st) in enumerate(zip(models, streams)):
+            with torch.cuda.stream(st):
+                outs[k].append(m(tl, ta))
+    torch.cuda.synchronize()
+    for k in range(2):
+        for o in outs[k]:
+            assert torch.equal(o, refs[k])
+
+
 def test_forward_rejects_bad_inputs(hb, net, dev):
     with pytest.raises(RuntimeError):
         net(torch.rand(1, 2, 16, 16), torch.ones(1, 2))                  # CPU tensors: no fallback
