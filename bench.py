@@ -59,6 +59,21 @@ def ncu_traffic_per_launch(kernel_class):
     return sum((float(r["rd"]) + float(r["wr"])) * 1e9 for r in rows) / len(rows)
 
 
+def ncu_tensor_pipe_active(kernel_class):
+    """sm__pipe_tensor_cycles_active (% of elapsed) of a kernel class from the same committed capture: mean over its
+    launches in one forward step and the best single launch; None if the capture is not there."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")
+    if not os.path.exists(path):
+        return None
+    tag = kernel_class.replace("conv3x3_umma", "conv3x3_umma_kernel")
+    with open(path) as f:
+        vals = [float(r["tensor"]) for r in json.load(f) if tag in r["name"]]
+    if not vals:
+        return None
+    return {"mean": sum(vals) / len(vals), "best_launch": max(vals), "launches": len(vals),
+            "source": "profiles/r01_ncu_full_summary.json (ncu --set full, one forward step, kernels serialised)"}
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -304,6 +319,7 @@ def main():
         roofline = {
             "bound": "tensor", "kernel": dom, "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
             "frac": ach / peaks["bf16_tflops"], "peak_source": peaks["source"], "traffic": ncu_traffic_per_launch(dom),
+            "tensor_pipe_active_pct": ncu_tensor_pipe_active(dom),
             "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the launches of this class in one "
                             "forward step (profiles/r01_ncu_full_summary.json); equals the activation bytes read + written once",
             "avg_launch_ms": prof[dom]["ms"] / max(prof[dom]["launches"], 1),

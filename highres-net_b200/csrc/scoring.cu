@@ -325,21 +325,36 @@ __global__ void cpsnr_finalize_kernel(const double* __restrict__ partial, CpGeom
         }
     }
     if (MODE == 2) {
-        __syncthreads();
-        if (site == 0) {
-            // np.max / np.argmax semantics: NaN wins and the first NaN (else first maximum) is the argmax
-            int arg = 0;
-            float best = score[0];
-            for (int k = 1; k < sites; ++k) {
-                const float v = score[k];
-                if (best != best) break;
-                if (v != v || v > best) {
-                    best = v;
-                    arg = k;
-                }
+        // np.max / np.argmax over the shift window as a warp-shuffle reduction: NaN beats everything and the first NaN
+        // (else the first maximum) is the argmax, so the comparator orders by (is NaN, value, lower site index).
+        float v = site < sites ? score[site] : -INFINITY;
+        int arg = site < sites ? site : 0x7fffffff;
+        auto better = [](float av, int ai, float bv, int bi) {
+            const bool an = av != av, bn = bv != bv;
+            if (an || bn) return (an && bn) ? ai < bi : an;
+            if (av != bv) return av > bv;
+            return ai < bi;
+        };
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (better(ov, oi, v, arg)) {
+                v = ov;
+                arg = oi;
             }
-            best_db[set] = best;
-            best_site[set] = arg;
+        }
+        __shared__ float wv[2];
+        __shared__ int wi[2];
+        if ((threadIdx.x & 31) == 0) {
+            wv[threadIdx.x >> 5] = v;
+            wi[threadIdx.x >> 5] = arg;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const bool second = better(wv[1], wi[1], wv[0], wi[0]);
+            best_db[set] = second ? wv[1] : wv[0];
+            best_site[set] = second ? wi[1] : wi[0];
         }
     }
 }
