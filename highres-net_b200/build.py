@@ -16,8 +16,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libhrn_b200.so")
-SOURCES = ["api.cu", "conv3x3_umma.cu", "conv_init_umma.cu", "decoder_umma.cu", "pointwise.cu", "scoring.cu"]
-HEADERS = ["internal.h", "ptx.cuh", "umma_common.cuh", os.path.join("..", "..", "include", "hrn_b200.h")]
+SOURCES = ["api.cu", "conv3x3_umma.cu", "resblock64_umma.cu", "conv_init_umma.cu", "decoder_umma.cu", "pointwise.cu", "scoring.cu"]
+HEADERS = ["internal.h", "ptx.cuh", "umma_common.cuh", "strips.cuh", os.path.join("..", "..", "include", "hrn_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

@@ -63,6 +63,7 @@ struct hrn_handle {
     size_t io_u16_cap = 0;
     int max_ctas = 0;                  // 0 = one CTA per SM (test knob)
     int strip_split = 0;               // ranges of the row space per CTA (0/1 = one contiguous range)
+    int fuse_resblock = 1;             // encoder ResidualBlocks as one launch each (resblock64_umma.cu) when W <= 128
     int host_chunks = 0;               // hrn_forward_host pipeline depth (0 = automatic)
     long long workspace_mb = 65536;    // cap on the activation workspace; larger batches are run in slices
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of hrn_forward_host
@@ -258,6 +259,32 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
         const int t1 = (cur + 1) % 3, t2 = (cur + 2) % 3;
         hrn::ConvArgs a = base;
         a.in = h->act[cur];
+        // One launch for the whole ResidualBlock when the image is a single column tile wide (the intermediate never
+        // leaves the SM); the stage-dump hook and wider images take the two-launch path below.
+        if (h->fuse_resblock && dump == nullptr && h->enc[2 * r].has_prelu && h->enc[2 * r + 1].has_prelu) {
+            const hrn::ConvLayer &l1 = h->enc[2 * r], &l2 = h->enc[2 * r + 1];
+            a.out = h->act[t2];
+            a.cin = a.cout = 64;
+            a.w_img = l1.w_img;
+            a.bias = l1.bias;
+            a.prelu = l1.prelu;
+            a.has_prelu = 1;
+            a.max_ctas = h->max_ctas;
+            a.strip_split = h->strip_split;
+            int rc;
+            {
+                SpanGuard guard(h, s, HRN_PROF_CONV64, 2.0 * 2.0 * 9.0 * 64 * 64 * static_cast<double>(a.n_img) * H * W);
+                rc = hrn::resblock64_launch(a, l2.w_img, l2.bias, l2.prelu, h->sm_count, s);
+            }
+            if (rc < 0) return -1;
+            if (rc == 0) {
+                stage += 2;
+                cur = t2;
+                continue;
+            }
+            a = base;
+            a.in = h->act[cur];
+        }
         a.out = h->act[t1];
         a.res_mode = hrn::RES_NONE;
         if (run_conv(h, h->enc[2 * r], a, s)) return -1;
@@ -738,6 +765,7 @@ int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value) {
     else if (strcmp(knob, "workspace_mb") == 0) h->workspace_mb = value > 0 ? value : 65536;
     else if (strcmp(knob, "skip_dead_views") == 0) h->skip_dead = value != 0;
     else if (strcmp(knob, "strip_split") == 0) h->strip_split = value;
+    else if (strcmp(knob, "fuse_resblock") == 0) h->fuse_resblock = value != 0;
     else {
         set_error("hrn_debug_set: unknown knob '%s'", knob);
         return -1;
