@@ -361,19 +361,29 @@ resblock64_umma_kernel(const __grid_constant__ CUtensorMap in_map, const RbArgs 
                 if (valid) {
                     uint8_t* dst = smem_gen + H_OFFSET + hs * CHUNK_BYTES + row_off;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {                      // 16-byte chunk j = channels [8j, 8j + 8)
-                        uint32_t o[4];
+                    for (int half = 0; half < 2; ++half) {
+                        // the 32 bias values of this half arrive as eight 128-bit shared loads issued together (scalar
+                        // loads next to their use left this warp stalled on the shared-memory scoreboard all the time)
+                        float4 b4[8];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int c = 8 * j + 2 * e;
-                            float x0 = __uint_as_float(v[c >> 5][c & 31]) + bias1_s[c];
-                            float x1 = __uint_as_float(v[c >> 5][(c & 31) + 1]) + bias1_s[c + 1];
-                            x0 = fmaf(slope_m1, fminf(x0, 0.0f), x0);
-                            x1 = fmaf(slope_m1, fminf(x1, 0.0f), x1);
-                            const __nv_bfloat162 y = __floats2bfloat162_rn(x0, x1);
-                            o[e] = inside ? *reinterpret_cast<const uint32_t*>(&y) : 0u;
+                        for (int k = 0; k < 8; ++k) b4[k] = reinterpret_cast<const float4*>(bias1_s + 32 * half)[k];
+                        const float* bb = reinterpret_cast<const float*>(b4);
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {               // 16-byte chunk j = channels [8j, 8j + 8)
+                            const int j = 4 * half + jj;
+                            uint32_t o[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int c = 8 * jj + 2 * e;
+                                float x0 = __uint_as_float(v[half][c]) + bb[c];
+                                float x1 = __uint_as_float(v[half][c + 1]) + bb[c + 1];
+                                x0 = fmaf(slope_m1, fminf(x0, 0.0f), x0);
+                                x1 = fmaf(slope_m1, fminf(x1, 0.0f), x1);
+                                const __nv_bfloat162 y = __floats2bfloat162_rn(x0, x1);
+                                o[e] = inside ? *reinterpret_cast<const uint32_t*>(&y) : 0u;
+                            }
+                            *reinterpret_cast<uint4*>(dst + ((static_cast<uint32_t>(j) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
                         }
-                        *reinterpret_cast<uint4*>(dst + ((static_cast<uint32_t>(j) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
