@@ -32,8 +32,8 @@ constexpr int ACCS = 4;                      // accumulator slots per pipeline
 constexpr int RING = 2;                      // x rows / h rows resident per pipeline
 constexpr int BTILE_BYTES = 3 * NT * 128;    // one kx tile: [W(ky=2) | W(ky=1) | W(ky=0)] x 64 ci
 constexpr int W_BYTES = 3 * BTILE_BYTES;     // 73,728 per conv
-constexpr int EPI2_WARPS = 8, EPI1_WARPS = 4;
-constexpr int NUM_THREADS = 128 + EPI2_WARPS * 32 + EPI1_WARPS * 32;     // 512
+constexpr int EPI2_WARPS = 8, EPI1_WARPS = 8;
+constexpr int NUM_THREADS = 128 + EPI2_WARPS * 32 + EPI1_WARPS * 32;     // 640: at most 102 registers per thread
 
 constexpr int X_OFFSET = 2 * W_BYTES;
 constexpr int H_OFFSET = X_OFFSET + RING * CHUNK_BYTES;
@@ -282,10 +282,8 @@ resblock64_umma_kernel(const __grid_constant__ CUtensorMap in_map, const RbArgs 
         const int wq = warp & 3;
         const int hf = (warp - 4) >> 2;
         const int co0 = hf * 32;
-        float bias_r[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) bias_r[e] = bias2_s[hf * 32 + e];
         const float slope_m1 = r.prelu2 - 1.0f;
+        const float4* bias4 = reinterpret_cast<const float4*>(bias2_s + hf * 32);
         StripWalker walk(geo, a, group);
         Strip s;
         bool have = walk.next(s);
@@ -314,30 +312,36 @@ resblock64_umma_kernel(const __grid_constant__ CUtensorMap in_map, const RbArgs 
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(p2.bar_tempty + 8 * acc);
-                uint32_t o[2][8];
                 const __nv_bfloat162 one2 = __floats2bfloat162_rn(1.0f, 1.0f);
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    float x0 = __uint_as_float(v[2 * e]) + bias_r[2 * e];
-                    float x1 = __uint_as_float(v[2 * e + 1]) + bias_r[2 * e + 1];
-                    x0 = fmaf(slope_m1, fminf(x0, 0.0f), x0);
-                    x1 = fmaf(slope_m1, fminf(x1, 0.0f), x1);
-                    __nv_bfloat162 y = __floats2bfloat162_rn(x0, x1);
-                    if (valid) y = __hfma2(one2, y, *reinterpret_cast<const __nv_bfloat162*>(&rv[e >> 3][e & 7]));
-                    o[e >> 3][e & 7] = *reinterpret_cast<const uint32_t*>(&y);
-                }
-                if (valid) {
-                    ptx::stg_v8(op, o[0]);
-                    ptx::stg_v8(op + 16, o[1]);
+                for (int g = 0; g < 2; ++g) {                          // 16 channels at a time: the bias comes from shared
+                    float4 b4[4];                                      // memory (640 threads leave 102 registers each)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) b4[k] = bias4[4 * g + k];
+                    const float* bb = reinterpret_cast<const float*>(b4);
+                    uint32_t o[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        float x0 = __uint_as_float(v[16 * g + 2 * e]) + bb[2 * e];
+                        float x1 = __uint_as_float(v[16 * g + 2 * e + 1]) + bb[2 * e + 1];
+                        x0 = fmaf(slope_m1, fminf(x0, 0.0f), x0);
+                        x1 = fmaf(slope_m1, fminf(x1, 0.0f), x1);
+                        __nv_bfloat162 y = __floats2bfloat162_rn(x0, x1);
+                        if (valid) y = __hfma2(one2, y, *reinterpret_cast<const __nv_bfloat162*>(&rv[g][e]));
+                        o[e] = *reinterpret_cast<const uint32_t*>(&y);
+                    }
+                    if (valid) ptx::stg_v8(op + 16 * g, o);
                 }
             }
         }
     } else if (warp >= 4 + EPI2_WARPS) {
         // ===================================================== epilogue 1: h = PReLU1(acc + b1) -> bf16 -> smem A row of conv 2
         const int wq = warp & 3;                       // TMEM lanes [32 wq, 32 wq + 32)
+        const int hf = (warp - 4 - EPI2_WARPS) >> 2;   // channels [32 hf, 32 hf + 32) = 16-byte chunks 4 hf .. 4 hf + 3
         const int px = wq * 32 + lane;                 // pixel of the row; its smem row is px + 1 (slot 0 = left halo)
         const bool valid = px < a.W;
         const float slope_m1 = a.prelu - 1.0f;
+        const float4* bias4 = reinterpret_cast<const float4*>(bias1_s + hf * 32);
         const uint32_t row_off = static_cast<uint32_t>(px + 1) * 128u, sw = static_cast<uint32_t>((px + 1) & 7);
         StripWalker walk(geo, a, group, false);
         Strip s;
@@ -350,9 +354,8 @@ resblock64_umma_kernel(const __grid_constant__ CUtensorMap in_map, const RbArgs 
                 const uint32_t hs = tile % RING, hph = (tile / RING) & 1;
                 ptx::mbar_wait(p1.bar_tfull + 8 * acc, aph, 8);
                 ptx::tc_fence_after();
-                uint32_t v[2][32];
-                ptx::tmem_ld_x32(p1.acc_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * NT, v[0]);
-                ptx::tmem_ld_x32(p1.acc_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * NT + 32, v[1]);
+                uint32_t v[32];
+                ptx::tmem_ld_x32(p1.acc_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * NT + hf * 32, v);
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
@@ -361,28 +364,26 @@ resblock64_umma_kernel(const __grid_constant__ CUtensorMap in_map, const RbArgs 
                 if (valid) {
                     uint8_t* dst = smem_gen + H_OFFSET + hs * CHUNK_BYTES + row_off;
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        // the 32 bias values of this half arrive as eight 128-bit shared loads issued together (scalar
-                        // loads next to their use left this warp stalled on the shared-memory scoreboard all the time)
-                        float4 b4[8];
+                    for (int g = 0; g < 2; ++g) {
+                        float4 b4[4];
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) b4[k] = reinterpret_cast<const float4*>(bias1_s + 32 * half)[k];
+                        for (int k = 0; k < 4; ++k) b4[k] = bias4[4 * g + k];
                         const float* bb = reinterpret_cast<const float*>(b4);
 #pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {               // 16-byte chunk j = channels [8j, 8j + 8)
-                            const int j = 4 * half + jj;
+                        for (int jj = 0; jj < 2; ++jj) {               // 16-byte chunk j = channels [8j, 8j + 8)
+                            const uint32_t j = static_cast<uint32_t>(4 * hf + 2 * g + jj);
                             uint32_t o[4];
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const int c = 8 * jj + 2 * e;
-                                float x0 = __uint_as_float(v[half][c]) + bb[c];
-                                float x1 = __uint_as_float(v[half][c + 1]) + bb[c + 1];
+                                float x0 = __uint_as_float(v[16 * g + c]) + bb[c];
+                                float x1 = __uint_as_float(v[16 * g + c + 1]) + bb[c + 1];
                                 x0 = fmaf(slope_m1, fminf(x0, 0.0f), x0);
                                 x1 = fmaf(slope_m1, fminf(x1, 0.0f), x1);
                                 const __nv_bfloat162 y = __floats2bfloat162_rn(x0, x1);
                                 o[e] = inside ? *reinterpret_cast<const uint32_t*>(&y) : 0u;
                             }
-                            *reinterpret_cast<uint4*>(dst + ((static_cast<uint32_t>(j) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<uint4*>(dst + ((j ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
                         }
                     }
                 }
