@@ -28,6 +28,7 @@ struct ConvLayer {
     int cin = 0, cout = 0;
     uint8_t* w_img = nullptr;   // device, pre-swizzled bf16
     float* bias = nullptr;      // device
+    float bias_host[128] = {};  // host copy (the fused ResidualBlock kernel takes its biases as kernel parameters)
     float prelu = 0.0f;
     bool has_prelu = false;
 };
@@ -121,6 +122,7 @@ int set_conv_bias(hrn::ConvLayer& l, const float* data, const int64_t* shape, in
         set_error("conv bias: expected shape (%d,)", l.cout);
         return -1;
     }
+    std::memcpy(l.bias_host, data, static_cast<size_t>(l.cout) * sizeof(float));
     return upload(&l.bias, data, l.cout);
 }
 
@@ -274,7 +276,7 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
             int rc;
             {
                 SpanGuard guard(h, s, HRN_PROF_CONV64, 2.0 * 2.0 * 9.0 * 64 * 64 * static_cast<double>(a.n_img) * H * W);
-                rc = hrn::resblock64_launch(a, l2.w_img, l2.bias, l2.prelu, h->sm_count, s);
+                rc = hrn::resblock64_launch(a, l1.bias_host, l2.w_img, l2.bias_host, l2.prelu, h->sm_count, s);
             }
             if (rc < 0) return -1;
             if (rc == 0) {

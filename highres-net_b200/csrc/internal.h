@@ -67,8 +67,9 @@ void conv3x3_pack_weights(const float* oihw, int cin, int cout, uint8_t* dst);
 int conv3x3_launch(const ConvArgs& a, int sm_count, cudaStream_t stream);
 // resblock64_umma.cu: x + PReLU2(conv2(PReLU1(conv1(x)))) for 64 channels in one launch (the intermediate stays in shared
 // memory).  a1 = conv 1 (x = a1.in, out = a1.out).  Returns 1 when the shape is not supported (W > 128): use two launches.
-int resblock64_launch(const ConvArgs& a1, const uint8_t* w2_img, const float* bias2, float prelu2, int sm_count,
-                      cudaStream_t stream);
+// bias1_host / bias2_host: HOST pointers to the 64 biases of each conv (they travel as kernel parameters).
+int resblock64_launch(const ConvArgs& a1, const float* bias1_host, const uint8_t* w2_img, const float* bias2_host,
+                      float prelu2, int sm_count, cudaStream_t stream);
 
 // ------------------------------------------------------------------ pointwise / CUDA-core kernels
 int median_anchor_launch(const float* lrs, int B, int L, int H, int W, float* anchor, cudaStream_t s);

@@ -38,16 +38,18 @@ constexpr int NUM_THREADS = 128 + EPI2_WARPS * 32 + EPI1_WARPS * 32;     // 640:
 constexpr int X_OFFSET = 2 * W_BYTES;
 constexpr int H_OFFSET = X_OFFSET + RING * CHUNK_BYTES;
 constexpr int BAR_OFFSET = H_OFFSET + RING * CHUNK_BYTES;
-constexpr int BIAS_OFFSET = BAR_OFFSET + 512;
-constexpr int SMEM_BYTES = BIAS_OFFSET + 2 * NT * 4 + 1024;
+constexpr int SMEM_BYTES = BAR_OFFSET + 512 + 1024;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-static_assert((4 * RING + 4 * ACCS) * 8 + 16 <= 512, "barrier block overflows into the bias arrays");
+static_assert((4 * RING + 4 * ACCS) * 8 + 16 <= 512, "barrier block");
 
 struct RbArgs {
-    ConvArgs c;                 // geometry, x (in), out, live list, conv 1 weights / bias / PReLU
-    const uint8_t* w2_img;      // conv 2: pre-swizzled weights, bias, PReLU slope
-    const float* bias2;
+    ConvArgs c;                 // geometry, x (in), out, live list, conv 1 weights / PReLU
+    const uint8_t* w2_img;      // conv 2: pre-swizzled weights, PReLU slope
     float prelu2;
+    // Biases live in the kernel parameters (constant bank): the epilogues read them with LDC.  From shared memory the
+    // loads queued behind the tensor cores' operand traffic (a fifth of the epilogue time), and 640 threads leave no
+    // room to keep them in registers.
+    float bias1[NT], bias2[NT];
 };
 
 // Barriers of one pipeline and where its operands / accumulators live.
@@ -213,8 +215,6 @@ resblock64_umma_kernel(const __grid_constant__ CUtensorMap in_map, const RbArgs 
     p1.extra_rows = 2;
     p2.extra_rows = 0;
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
-    float* bias1_s = reinterpret_cast<float*>(smem_gen + BIAS_OFFSET);
-    float* bias2_s = bias1_s + NT;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int group = blockIdx.x;
@@ -238,10 +238,6 @@ resblock64_umma_kernel(const __grid_constant__ CUtensorMap in_map, const RbArgs 
     }
     ptx::pdl_launch_dependents();
     if (warp == 2) ptx::tmem_alloc<512>(tmem_slot);
-    if (threadIdx.x >= 128 && threadIdx.x < 128 + NT) {
-        bias1_s[threadIdx.x - 128] = a.bias[threadIdx.x - 128];
-        bias2_s[threadIdx.x - 128] = r.bias2[threadIdx.x - 128];
-    }
     // the h ring starts as zeros: halo pixels, pixels past W and nothing else are left untouched by epilogue 1
     for (int i = threadIdx.x; i < RING * CHUNK_BYTES / 16; i += NUM_THREADS)
         reinterpret_cast<uint4*>(smem_gen + H_OFFSET)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -265,8 +261,13 @@ resblock64_umma_kernel(const __grid_constant__ CUtensorMap in_map, const RbArgs 
             ptx::pdl_wait();
             uint32_t it = 0;
             for (; have; have = walk.next(s)) {
+                // With two slots the ring cannot hide an HBM round trip, so rows are pulled into L2 X_AHEAD rows ahead
+                // of the load that brings them into shared memory.
+                constexpr int X_AHEAD = 6;
+                for (int q = 0; q < X_AHEAD && q < s.rows + 4; ++q) ptx::tma_prefetch_4d(&in_map, 0, -1, s.y0 - 2 + q, s.m);
                 for (int q = 0; q < s.rows + 4; ++q, ++it) {
                     const uint32_t slot = it % RING, ph = (it / RING) & 1;
+                    if (q + X_AHEAD < s.rows + 4) ptx::tma_prefetch_4d(&in_map, 0, -1, s.y0 - 2 + q + X_AHEAD, s.m);
                     ptx::mbar_wait(p1.bar_empty + 8 * slot, ph ^ 1, 1);
                     ptx::mbar_expect_tx(p1.bar_full + 8 * slot, CHUNK_TX);
                     ptx::tma_load_4d(p1.ring_s + slot * CHUNK_BYTES, &in_map, 0, -1, s.y0 - 2 + q, s.m, p1.bar_full + 8 * slot);
@@ -283,7 +284,7 @@ resblock64_umma_kernel(const __grid_constant__ CUtensorMap in_map, const RbArgs 
         const int hf = (warp - 4) >> 2;
         const int co0 = hf * 32;
         const float slope_m1 = r.prelu2 - 1.0f;
-        const float4* bias4 = reinterpret_cast<const float4*>(bias2_s + hf * 32);
+        const float* bias = r.bias2 + hf * 32;
         StripWalker walk(geo, a, group);
         Strip s;
         bool have = walk.next(s);
@@ -314,11 +315,8 @@ resblock64_umma_kernel(const __grid_constant__ CUtensorMap in_map, const RbArgs 
                 if (lane == 0) ptx::mbar_arrive(p2.bar_tempty + 8 * acc);
                 const __nv_bfloat162 one2 = __floats2bfloat162_rn(1.0f, 1.0f);
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {                          // 16 channels at a time: the bias comes from shared
-                    float4 b4[4];                                      // memory (640 threads leave 102 registers each)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) b4[k] = bias4[4 * g + k];
-                    const float* bb = reinterpret_cast<const float*>(b4);
+                for (int g = 0; g < 2; ++g) {                          // 16 channels at a time
+                    const float* bb = bias + 16 * g;
                     uint32_t o[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
@@ -341,7 +339,7 @@ resblock64_umma_kernel(const __grid_constant__ CUtensorMap in_map, const RbArgs 
         const int px = wq * 32 + lane;                 // pixel of the row; its smem row is px + 1 (slot 0 = left halo)
         const bool valid = px < a.W;
         const float slope_m1 = a.prelu - 1.0f;
-        const float4* bias4 = reinterpret_cast<const float4*>(bias1_s + hf * 32);
+        const float* bias = r.bias1 + hf * 32;
         const uint32_t row_off = static_cast<uint32_t>(px + 1) * 128u, sw = static_cast<uint32_t>((px + 1) & 7);
         StripWalker walk(geo, a, group, false);
         Strip s;
@@ -365,10 +363,7 @@ resblock64_umma_kernel(const __grid_constant__ CUtensorMap in_map, const RbArgs 
                     uint8_t* dst = smem_gen + H_OFFSET + hs * CHUNK_BYTES + row_off;
 #pragma unroll
                     for (int g = 0; g < 2; ++g) {
-                        float4 b4[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) b4[k] = bias4[4 * g + k];
-                        const float* bb = reinterpret_cast<const float*>(b4);
+                        const float* bb = bias + 16 * g;
 #pragma unroll
                         for (int jj = 0; jj < 2; ++jj) {               // 16-byte chunk j = channels [8j, 8j + 8)
                             const uint32_t j = static_cast<uint32_t>(4 * hf + 2 * g + jj);
@@ -402,10 +397,10 @@ resblock64_umma_kernel(const __grid_constant__ CUtensorMap in_map, const RbArgs 
 
 }  // namespace
 
-// One fused ResidualBlock(64): a1 describes conv 1 (x = a1.in, weights, bias, PReLU) and the output tensor a1.out;
-// w2 / b2 / prelu2 are conv 2.  Returns 1 if the shape is not supported (caller falls back to two launches).
-int resblock64_launch(const ConvArgs& a1, const uint8_t* w2_img, const float* bias2, float prelu2, int sm_count,
-                      cudaStream_t stream) {
+// One fused ResidualBlock(64): a1 describes conv 1 (x = a1.in, weights, PReLU) and the output tensor a1.out; w2 / prelu2
+// are conv 2; the biases are HOST arrays of 64 floats.  Returns 1 if the shape is not supported (caller falls back to two launches).
+int resblock64_launch(const ConvArgs& a1, const float* bias1_host, const uint8_t* w2_img, const float* bias2_host,
+                      float prelu2, int sm_count, cudaStream_t stream) {
     if (a1.W > TILE_M || a1.cin != 64 || a1.cout != 64 || !a1.has_prelu) return 1;
     if (a1.n_img <= 0 || a1.H <= 0 || a1.W <= 0) {
         set_error("resblock64: empty problem");
@@ -414,8 +409,11 @@ int resblock64_launch(const ConvArgs& a1, const uint8_t* w2_img, const float* bi
     RbArgs r;
     r.c = a1;
     r.w2_img = w2_img;
-    r.bias2 = bias2;
     r.prelu2 = prelu2;
+    for (int i = 0; i < NT; ++i) {
+        r.bias1[i] = bias1_host[i];
+        r.bias2[i] = bias2_host[i];
+    }
     Geometry g;
     g.n_parts = 1;
     g.x_tiles = 1;
