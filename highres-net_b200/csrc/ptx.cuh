@@ -56,6 +56,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return done != 0;
 }
+// Non-blocking probe (try_wait may suspend the thread for a while; test_wait never does).
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 // Bounded wait: a pipeline bug must surface as a CUDA error, never as a hung GPU.  The retry loop lives out of
 // line so that the common case (barrier already complete) costs one TRYWAIT and one branch at the call site.
 #ifndef HRN_WAIT_LIMIT_CYCLES

@@ -92,14 +92,15 @@ __device__ __forceinline__ void mma_role(const Pipe& p, const Geometry& geo, con
                 uint64_t ad = make_desc(a_lo0 + slot * (CHUNK_BYTES / 16));
                 uint64_t bd = make_desc(b_lo0);
                 const uint32_t dA = p.acc_base + sl * NT;
+                // Probe (never block on) the barriers of the next row while the MMA queue is full: a blocking wait here
+                // would hold back the last MMAs and the commits of THIS row until the other pipeline has produced the
+                // next one, which chains the two pipelines' latencies together.
                 auto early = [&]() {
                     const uint32_t itn = it + 1;
-                    ptx::mbar_wait(p.bar_full + 8 * (itn % RING), (itn / RING) & 1, 6);
-                    full_seen = true;
+                    full_seen = ptx::mbar_test_wait(p.bar_full + 8 * (itn % RING), (itn / RING) & 1);
                     if (nxt_opens) {
                         const uint32_t tn = t_new + 1;
-                        ptx::mbar_wait(p.bar_tempty + 8 * (tn % ACCS), ((tn / ACCS) & 1) ^ 1, 7);
-                        tempty_seen = true;
+                        tempty_seen = ptx::mbar_test_wait(p.bar_tempty + 8 * (tn % ACCS), ((tn / ACCS) & 1) ^ 1);
                     }
                 };
                 if (sl <= ACCS - 3) {
@@ -173,12 +174,8 @@ __device__ __forceinline__ void mma_role(const Pipe& p, const Geometry& geo, con
                 if (w1 > 0) ptx::umma_bf16(d1, ad, bd1, id1, 1u);
                 if (step == 7 && more_rows) {
                     const uint32_t itn = it + 1;
-                    ptx::mbar_wait(p.bar_full + 8 * (itn % RING), (itn / RING) & 1, 6);
-                    full_seen = true;
-                    if (next_opens) {
-                        ptx::mbar_wait(p.bar_tempty + 8 * (t_next % ACCS), ((t_next / ACCS) & 1) ^ 1, 7);
-                        tempty_seen = true;
-                    }
+                    full_seen = ptx::mbar_test_wait(p.bar_full + 8 * (itn % RING), (itn / RING) & 1);
+                    if (next_opens) tempty_seen = ptx::mbar_test_wait(p.bar_tempty + 8 * (t_next % ACCS), ((t_next / ACCS) & 1) ^ 1);
                 }
             }
             ptx::umma_commit(p.bar_empty + 8 * slot);
