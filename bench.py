@@ -45,13 +45,17 @@ def synthetic_batch(b, l, s, seed, device=None, pin=False):
     return lrs, alphas
 
 
+def _ncu_tag(kernel_class):
+    return kernel_class.replace("conv3x3_umma", "conv3x3_umma_kernel").replace("resblock64_umma", "resblock64_umma_kernel")
+
+
 def ncu_traffic_per_launch(kernel_class):
     """DRAM bytes (read + write) per launch of a kernel class, averaged over the launches of one forward step, from the
     committed `ncu --set full` capture (profiles/r01_ncu_full_summary.json); None if the capture is not there."""
     path = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")
     if not os.path.exists(path):
         return None
-    tag = kernel_class.replace("conv3x3_umma", "conv3x3_umma_kernel")
+    tag = _ncu_tag(kernel_class)
     with open(path) as f:
         rows = [r for r in json.load(f) if tag in r["name"]]
     if not rows:
@@ -65,7 +69,7 @@ def ncu_tensor_pipe_active(kernel_class):
     path = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")
     if not os.path.exists(path):
         return None
-    tag = kernel_class.replace("conv3x3_umma", "conv3x3_umma_kernel")
+    tag = _ncu_tag(kernel_class)
     with open(path) as f:
         vals = [float(r["tensor"]) for r in json.load(f) if tag in r["name"]]
     if not vals:
@@ -282,16 +286,36 @@ def main():
     clocks = sampler.stop(t_wall0, t_wall1) if sampler is not None else None
 
     # ---------------- end to end through the host-buffer API ----------------
-    for i in range(2):
-        net.forward_host(*host_inputs[i % len(host_inputs)], out_host=host_out, device=dev)
+    # The validation-loop pattern (train.py:199-208) through forward_host_submit / forward_host_wait: every step copies
+    # its own inputs from pinned host memory and its SR back into pinned host memory; two steps are in flight, so the
+    # copies of step n +- 1 overlap the kernels of step n.  The region ends when the last step's SR is on the host.
+    host_outs = [host_out, torch.empty_like(host_out).pin_memory()]
+
+    def e2e_loop(n):
+        pending = None
+        for i in range(n):
+            nxt = net.forward_host_submit(*host_inputs[i % len(host_inputs)], out_host=host_outs[i % 2], device=dev)
+            if pending is not None:
+                net.forward_host_wait(pending)
+            pending = nxt
+        net.forward_host_wait(pending)
+
+    e2e_loop(3)
     sync_all()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    for i in range(args.steps):
-        net.forward_host(*host_inputs[i % len(host_inputs)], out_host=host_out, device=dev)
+    e2e_loop(args.steps)
     e3.record()
     sync_all()
     ms_e2e = e2.elapsed_time(e3)
+    # the same loop one call at a time (forward_host: copy in, kernels, copy out, nothing overlapped)
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e4.record()
+    for i in range(args.steps):
+        net.forward_host(*host_inputs[i % len(host_inputs)], out_host=host_out, device=dev)
+    e5.record()
+    sync_all()
+    ms_e2e_sync = e4.elapsed_time(e5)
 
     # ---------------- per-kernel-class timing for the roofline ----------------
     net.profile_begin(dev)
@@ -301,9 +325,9 @@ def main():
     prof = net.profile_end(dev)
 
     if world > 1:
-        t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms_total, ms_e2e, ms_e2e_sync], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_e2e = float(t[0]), float(t[1])
+        ms_total, ms_e2e, ms_e2e_sync = float(t[0]), float(t[1]), float(t[2])
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
         dist.all_reduce(lt)
         launches = int(lt[0])
@@ -313,7 +337,7 @@ def main():
         total_sets = b * world * args.steps
         value = total_sets / ms_total * 1e3
         e2e_value = total_sets / ms_e2e * 1e3
-        dom = max(("conv3x3_umma<64>", "conv3x3_umma<128>"), key=lambda k: prof[k]["ms"])
+        dom = max(("conv3x3_umma<64>", "conv3x3_umma<128>", "resblock64_umma"), key=lambda k: prof[k]["ms"])
         ach = prof[dom]["flops"] / max(prof[dom]["ms"], 1e-9) / 1e9       # TFLOP/s
         step_ms = sum(v["ms"] for v in prof.values()) / prof_steps
         roofline = {
@@ -345,7 +369,11 @@ def main():
             "model_tflops": flops_step * world * args.steps / ms_total / 1e9,
             "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (b * l * s * s + b * l) * 4,
-                    "d2h_bytes_per_step": b * 9 * s * s * 4, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": b * 9 * s * s * 4, "ms_per_step": ms_e2e / args.steps,
+                    "api": "HRNet.forward_host_submit / forward_host_wait (hrn_forward_host_submit): pinned host lrs/alphas "
+                           "in, pinned host sr out, every step; two steps in flight",
+                    "one_call_at_a_time": {"value": total_sets / ms_e2e_sync * 1e3, "ms_per_step": ms_e2e_sync / args.steps,
+                                           "api": "HRNet.forward_host (hrn_forward_host), synchronous"}},
             "gpu_launches": launches,
             "clocks": clocks,
         }

@@ -69,6 +69,14 @@ struct hrn_handle {
     long long workspace_mb = 65536;    // cap on the activation workspace; larger batches are run in slices
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of hrn_forward_host
     cudaEvent_t ev_in[8] = {}, ev_done[8] = {};
+    // hrn_forward_host_submit / _wait: two calls in flight, each with its own device staging and events
+    struct HostSlot {
+        float *lrs = nullptr, *alphas = nullptr, *sr = nullptr;
+        size_t cap[3] = {0, 0, 0};
+        cudaEvent_t ev_in = nullptr, ev_kernels = nullptr, ev_out = nullptr;   // H2D done, kernels done, D2H done
+        int64_t ticket = 0;                                                      // 0 = free
+    } slots[2];
+    int64_t next_ticket = 1;
     int debug_flags = 0;
     // optional per-launch timing (hrn_profile_begin / hrn_profile_end)
     bool profiling = false;
@@ -275,7 +283,7 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
             a.strip_split = h->strip_split;
             int rc;
             {
-                SpanGuard guard(h, s, HRN_PROF_CONV64, 2.0 * 2.0 * 9.0 * 64 * 64 * static_cast<double>(a.n_img) * H * W);
+                SpanGuard guard(h, s, HRN_PROF_RESBLOCK64, 2.0 * 2.0 * 9.0 * 64 * 64 * static_cast<double>(a.n_img) * H * W);
                 rc = hrn::resblock64_launch(a, l1.bias_host, l2.w_img, l2.bias_host, l2.prelu, h->sm_count, s);
             }
             if (rc < 0) return -1;
@@ -457,6 +465,16 @@ void hrn_destroy(hrn_handle* h) {
     rel(h->live_scratch);
     for (auto* p : h->io) rel(p);
     rel(h->io_u16);
+    for (auto& sl : h->slots) {
+        rel(sl.lrs);
+        rel(sl.alphas);
+        rel(sl.sr);
+        if (sl.ev_in != nullptr) {
+            cudaEventDestroy(sl.ev_in);
+            cudaEventDestroy(sl.ev_kernels);
+            cudaEventDestroy(sl.ev_out);
+        }
+    }
     if (h->copy_in != nullptr) {
         cudaStreamDestroy(h->copy_in);
         cudaStreamDestroy(h->copy_out);
@@ -584,6 +602,17 @@ int32_t hrn_forward_dump(hrn_handle* h, const float* lrs, const float* alphas, i
     return forward_impl(h, lrs, alphas, B, L, H, W, sr, static_cast<cudaStream_t>(stream), &d);
 }
 
+static int ensure_copy_streams(hrn_handle* h) {
+    if (h->copy_in != nullptr) return 0;
+    HRN_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+    HRN_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) {
+        HRN_CUDA_OK(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+        HRN_CUDA_OK(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
 // Shared body of hrn_forward_host / hrn_forward_host_u16.  lrs_u16 != nullptr: the views arrive as raw uint16 (half the
 // H2D bytes) and become float32 on the device.
 static int forward_host_impl(hrn_handle* h, const float* lrs_host, const uint16_t* lrs_u16, const float* alphas_host,
@@ -603,14 +632,7 @@ static int forward_host_impl(hrn_handle* h, const float* lrs_host, const uint16_
     if (grow(reinterpret_cast<void**>(&h->io[1]), &h->io_cap[1], static_cast<size_t>(B) * L * 4)) return -1;
     if (grow(reinterpret_cast<void**>(&h->io[2]), &h->io_cap[2], B * set_out * 4)) return -1;
     if (lrs_u16 != nullptr && grow(reinterpret_cast<void**>(&h->io_u16), &h->io_u16_cap, B * set_in * 2)) return -1;
-    if (h->copy_in == nullptr) {
-        HRN_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
-        HRN_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
-        for (int i = 0; i < 8; ++i) {
-            HRN_CUDA_OK(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
-            HRN_CUDA_OK(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
-        }
-    }
+    if (ensure_copy_streams(h)) return -1;
     // Imagesets are independent, so the batch is cut into chunks and pipelined: the H2D copy of chunk k+1 and the
     // D2H copy of chunk k-1 overlap the kernels of chunk k (three streams, events in between).
     // Measured on B200 at B = 32, L = 16, 128x128 (tools/host_chunks.py): 1 / 2 / 4 chunks = 8.99 / 9.00 / 9.14 ms, i.e. the
@@ -669,6 +691,72 @@ int32_t hrn_forward_host_u16(hrn_handle* h, const uint16_t* lrs_host, const floa
         return -1;
     }
     return forward_host_impl(h, nullptr, lrs_host, alphas_host, B, L, H, W, sr_host, stream);
+}
+
+// Pipelined host-buffer forward: submit returns as soon as the copies and kernels are enqueued, so the H2D copy of call
+// n + 1 and the D2H copy of call n - 1 overlap the kernels of call n.  Two calls may be in flight (two staging slots);
+// a third submit first retires the oldest one.
+int32_t hrn_forward_host_submit(hrn_handle* h, const float* lrs_host, const float* alphas_host, int32_t B, int32_t L,
+                                int32_t H, int32_t W, float* sr_host, void* stream, int64_t* ticket) {
+    if (h == nullptr || lrs_host == nullptr || alphas_host == nullptr || sr_host == nullptr || ticket == nullptr) {
+        set_error("hrn_forward_host_submit: null argument");
+        return -1;
+    }
+    *ticket = 0;
+    if (B <= 0 || L <= 0 || H <= 0 || W <= 0) {
+        set_error("hrn_forward_host_submit: empty input");
+        return -1;
+    }
+    HRN_CUDA_OK(cudaSetDevice(h->device));
+    if (ensure_copy_streams(h)) return -1;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    hrn_handle::HostSlot& sl = h->slots[h->next_ticket & 1];
+    hrn_handle::HostSlot& other = h->slots[(h->next_ticket & 1) ^ 1];
+    if (sl.ev_in == nullptr) {
+        HRN_CUDA_OK(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
+        HRN_CUDA_OK(cudaEventCreateWithFlags(&sl.ev_kernels, cudaEventDisableTiming));
+        HRN_CUDA_OK(cudaEventCreateWithFlags(&sl.ev_out, cudaEventDisableTiming));
+    }
+    if (sl.ticket != 0) {      // the call that used this slot two submits ago: its results are complete after this
+        HRN_CUDA_OK(cudaEventSynchronize(sl.ev_out));
+        sl.ticket = 0;
+    }
+    const size_t n_in = static_cast<size_t>(B) * L * H * W, n_out = static_cast<size_t>(B) * 9 * H * W;
+    if (grow(reinterpret_cast<void**>(&sl.lrs), &sl.cap[0], n_in * 4)) return -1;
+    if (grow(reinterpret_cast<void**>(&sl.alphas), &sl.cap[1], static_cast<size_t>(B) * L * 4)) return -1;
+    if (grow(reinterpret_cast<void**>(&sl.sr), &sl.cap[2], n_out * 4)) return -1;
+    HRN_CUDA_OK(cudaMemcpyAsync(sl.lrs, lrs_host, n_in * 4, cudaMemcpyHostToDevice, h->copy_in));
+    HRN_CUDA_OK(cudaMemcpyAsync(sl.alphas, alphas_host, static_cast<size_t>(B) * L * 4, cudaMemcpyHostToDevice, h->copy_in));
+    HRN_CUDA_OK(cudaEventRecord(sl.ev_in, h->copy_in));
+    // the activation workspace is shared: kernels of this call run after the kernels of the previous one even if the
+    // caller switched streams in between
+    if (other.ticket != 0) HRN_CUDA_OK(cudaStreamWaitEvent(s, other.ev_kernels, 0));
+    HRN_CUDA_OK(cudaStreamWaitEvent(s, sl.ev_in, 0));
+    if (forward_sliced(h, sl.lrs, sl.alphas, B, L, H, W, sl.sr, s)) return -1;
+    HRN_CUDA_OK(cudaEventRecord(sl.ev_kernels, s));
+    HRN_CUDA_OK(cudaStreamWaitEvent(h->copy_out, sl.ev_kernels, 0));
+    HRN_CUDA_OK(cudaMemcpyAsync(sr_host, sl.sr, n_out * 4, cudaMemcpyDeviceToHost, h->copy_out));
+    HRN_CUDA_OK(cudaEventRecord(sl.ev_out, h->copy_out));
+    sl.ticket = h->next_ticket++;
+    *ticket = sl.ticket;
+    return 0;
+}
+
+int32_t hrn_forward_host_wait(hrn_handle* h, int64_t ticket) {
+    if (h == nullptr) {
+        set_error("null handle");
+        return -1;
+    }
+    if (ticket <= 0 || ticket >= h->next_ticket) {
+        set_error("hrn_forward_host_wait: unknown ticket %lld", static_cast<long long>(ticket));
+        return -1;
+    }
+    hrn_handle::HostSlot& sl = h->slots[ticket & 1];
+    if (sl.ticket != ticket) return 0;      // already retired by a later submit (or waited before): sr_host is complete
+    HRN_CUDA_OK(cudaSetDevice(h->device));
+    HRN_CUDA_OK(cudaEventSynchronize(sl.ev_out));
+    sl.ticket = 0;
+    return 0;
 }
 
 int32_t hrn_u16_to_unit_float(const uint16_t* src, int64_t n, float* dst, void* stream) {

@@ -98,7 +98,8 @@ class HRNet(nn.Module):
         handle = self._handle_for(torch.device(device))
         _lib.check(_lib.load().hrn_debug_set(handle, knob.encode(), int(value)), "hrn_debug_set")
 
-    PROFILE_CLASSES = ("conv3x3_umma<64>", "conv3x3_umma<128>", "conv_init", "decoder", "median_anchor")
+    PROFILE_CLASSES = ("conv3x3_umma<64>", "conv3x3_umma<128>", "conv_init", "decoder", "median_anchor",
+                       "resblock64_umma")
 
     def profile_begin(self, device) -> None:
         """Arm per-launch CUDA-event timing of the following forward calls (hrn_profile_begin)."""
@@ -162,6 +163,45 @@ class HRNet(nn.Module):
             _lib.check(entry(handle, lrs_host.data_ptr(), alphas_host.data_ptr(), b, l, h, w, out_host.data_ptr(),
                              _lib.current_stream_ptr(device)), "hrn_forward_host_u16" if raw16 else "hrn_forward_host")
         return out_host
+
+    def forward_host_submit(self, lrs_host: torch.Tensor, alphas_host: torch.Tensor, out_host: torch.Tensor = None,
+                            device="cuda:0"):
+        """Asynchronous forward_host (hrn_forward_host_submit): enqueues H2D, forward and D2H and returns a pending
+        handle for forward_host_wait.  Two calls may be in flight, so the copies of one batch overlap the kernels of
+        its neighbours; use pinned float32 tensors and do not touch them (or ``out_host``) before the wait."""
+        if lrs_host.is_cuda or alphas_host.is_cuda:
+            raise ValueError("forward_host_submit takes host tensors")
+        lrs_host = lrs_host.to(torch.float32).contiguous()
+        alphas_host = alphas_host.to(torch.float32).contiguous()
+        b, l, h, w = lrs_host.shape
+        device = torch.device(device)
+        handle = self._handle_for(device)
+        if out_host is None:
+            out_host = torch.empty((b, 1, 3 * h, 3 * w), dtype=torch.float32, pin_memory=True)
+        ticket = ctypes.c_int64(0)
+        with torch.cuda.device(device):
+            _lib.check(_lib.load().hrn_forward_host_submit(handle, lrs_host.data_ptr(), alphas_host.data_ptr(), b, l, h, w,
+                                                           out_host.data_ptr(), _lib.current_stream_ptr(device),
+                                                           ctypes.byref(ticket)), "hrn_forward_host_submit")
+        return (handle, ticket.value, out_host, lrs_host, alphas_host)     # the host tensors stay alive until the wait
+
+    def forward_host_wait(self, pending) -> torch.Tensor:
+        """Blocks until the call behind ``pending`` (from forward_host_submit) is complete; returns its SR host tensor."""
+        handle, ticket, out_host = pending[0], pending[1], pending[2]
+        _lib.check(_lib.load().hrn_forward_host_wait(handle, ticket), "hrn_forward_host_wait")
+        return out_host
+
+    def forward_host_iter(self, batches, device="cuda:0"):
+        """Pipelined validation loop (train.py:199-208): yields the SR host tensor of every (lrs_host, alphas_host)
+        batch in order while the next batch is already copying / computing."""
+        pending = None
+        for lrs_host, alphas_host in batches:
+            nxt = self.forward_host_submit(lrs_host, alphas_host, device=device)
+            if pending is not None:
+                yield self.forward_host_wait(pending)
+            pending = nxt
+        if pending is not None:
+            yield self.forward_host_wait(pending)
 
     def forward_stage(self, lrs, alphas, stage: int, shape):
         """Test hook: run forward and return (srs, fp32 NCHW copy of the named intermediate)."""

@@ -77,6 +77,16 @@ int32_t hrn_forward(hrn_handle* h, const float* lrs, const float* alphas, int32_
 int32_t hrn_forward_host(hrn_handle* h, const float* lrs_host, const float* alphas_host, int32_t B, int32_t L,
                          int32_t H, int32_t W, float* sr_host, void* stream);
 
+/* The same H2D -> forward -> D2H pattern for a LOOP over batches (the validation loop train.py:199-208, where the
+ * DataLoader hands over pinned batches, train.py:276-287 pin_memory=True): submit returns once copies and kernels are
+ * enqueued and hands back a ticket; wait blocks until that call's sr_host is complete.  Two calls may be in flight, so
+ * the H2D copy of batch n + 1 and the D2H copy of batch n - 1 overlap the kernels of batch n; a third submit first
+ * retires the oldest call.  lrs_host / alphas_host / sr_host must stay valid (and unmodified / unread) until the wait;
+ * pinned memory is needed for the overlap.  All submits of a handle should use the same `stream`. */
+int32_t hrn_forward_host_submit(hrn_handle* h, const float* lrs_host, const float* alphas_host, int32_t B, int32_t L,
+                                int32_t H, int32_t W, float* sr_host, void* stream, int64_t* ticket);
+int32_t hrn_forward_host_wait(hrn_handle* h, int64_t ticket);
+
 /* hrn_forward_host for views still in the on-disk 16-bit format (DataLoader.py:134, 195-198: io.imread -> uint16,
  * skimage.img_as_float(...).astype(float32) = x / 65535): lrs_host is (B, L, H, W) uint16, copied as is (half the H2D
  * bytes) and converted on the device with the same rounding.  hrn_u16_to_unit_float is that conversion alone on
@@ -146,7 +156,8 @@ int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value);
 #define HRN_PROF_CONV_INIT 2  /* conv 2 -> 64 (+ PReLU)           */
 #define HRN_PROF_DECODER 3    /* deconv + PReLU + 1x1             */
 #define HRN_PROF_MEDIAN 4     /* median anchor                    */
-#define HRN_PROF_CLASSES 5
+#define HRN_PROF_RESBLOCK64 5 /* fused encoder ResidualBlock (two 64 -> 64 convs in one launch) */
+#define HRN_PROF_CLASSES 6
 int32_t hrn_profile_begin(hrn_handle* h);
 int32_t hrn_profile_end(hrn_handle* h, double* ms, double* flops, int64_t* launches);
 

@@ -316,6 +316,40 @@ def test_forward_host_pipeline_depths(hb, dev):
     assert torch.equal(model.forward_host(lrs.clone(), alphas.clone(), device=dev), ref)    # pageable host memory too
 
 
+def test_forward_host_submit_wait_pipeline(hb, dev):
+    """hrn_forward_host_submit / _wait: batches of different shapes in flight two at a time, waited in and out of
+    order, give exactly what the device path gives; a retired ticket can still be waited; unknown tickets raise."""
+    model = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval()
+    model.load_state_dict(hrnet_oracle.make_params(cases.WEIGHT_SEED))
+    model = model.to(dev)
+    g = torch.Generator().manual_seed(31)
+    shapes = [(3, 4, 32), (2, 5, 40), (1, 16, 24), (4, 2, 32), (2, 3, 33), (3, 4, 32), (1, 1, 16)]
+    batches = []
+    for (b, l, s) in shapes:
+        al = (torch.rand(b, l, generator=g) > 0.2).float()
+        al[:, 0] = 1.0
+        batches.append((torch.rand(b, l, s, s, generator=g).pin_memory(), al.pin_memory()))
+    refs = [model(x.to(dev), a.to(dev)).cpu() for x, a in batches]
+    outs = list(model.forward_host_iter(batches, device=dev))
+    assert len(outs) == len(refs)
+    for o, r in zip(outs, refs):
+        assert torch.equal(o, r)
+    # four submits without a wait: the third and fourth retire the first and second
+    pend = [model.forward_host_submit(*batches[i], device=dev) for i in range(4)]
+    for i in (3, 0, 2, 1):
+        assert torch.equal(model.forward_host_wait(pend[i]), refs[i]), i
+    assert torch.equal(model.forward_host_wait(pend[0]), refs[0])          # waiting twice is harmless
+    # mixes with the synchronous call on the same stream
+    p = model.forward_host_submit(*batches[4], device=dev)
+    assert torch.equal(model.forward_host(*batches[5], device=dev), refs[5])
+    assert torch.equal(model.forward_host_wait(p), refs[4])
+    with pytest.raises(RuntimeError):
+        model.forward_host_wait((p[0], 10 ** 6, p[2]))
+    # pageable host memory works too (no overlap then)
+    q = model.forward_host_submit(batches[6][0].clone(), batches[6][1].clone(), out_host=torch.empty(1, 1, 48, 48), device=dev)
+    assert torch.equal(model.forward_host_wait(q), refs[6])
+
+
 def test_workspace_cap_slices_the_batch(hb, dev):
     """A batch whose activation workspace exceeds the cap is run in slices; the output must not change."""
     model = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval()
