@@ -49,6 +49,7 @@ SYMBOLS = {
     "hrn_profile_begin": (c_int32, [c_void_p]),
     "hrn_profile_end": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "hrn_debug_set": (c_int32, [c_void_p, c_char_p, c_int32]),
+    "hrn_scoring_debug_set": (c_int32, [c_char_p, c_int32]),
     "hrn_kernel_launch_count": (c_int64, []),
 }
 

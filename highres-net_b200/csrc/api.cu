@@ -795,6 +795,15 @@ int32_t hrn_shift_cpsnr(const float* sr, const float* hr, const float* hr_map, i
                                    static_cast<cudaStream_t>(stream));
 }
 
+int32_t hrn_scoring_debug_set(const char* knob, int32_t value) {
+    if (knob != nullptr && strcmp(knob, "cpsnr_generic") == 0) {
+        hrn::g_cpsnr_generic = value != 0;
+        return 0;
+    }
+    set_error("hrn_scoring_debug_set: unknown knob");
+    return -1;
+}
+
 int32_t hrn_clear_loss(const float* sr, const float* hr, const float* hr_map, int32_t B, int32_t H, int32_t W,
                        int32_t metric, float* loss, void* stream) {
     if (sr == nullptr || hr == nullptr || hr_map == nullptr || loss == nullptr) {

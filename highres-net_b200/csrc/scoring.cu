@@ -11,6 +11,8 @@
 // fixed order, so results are deterministic and within ~1e-6 dB of the fp32 numpy loop.
 #include "internal.h"
 
+#include <mutex>
+
 namespace hrn {
 namespace {
 
@@ -300,6 +302,205 @@ cpsnr_pass_kernel(const float* __restrict__ sr, const float* __restrict__ hr, co
     }
 }
 
+// border_w = 3 search, second generation: ONE warp per block owns 128 crop columns x a band of rows and ALL 49 sites.
+// A lane sweeps the hr / map rows of its band once (three aligned float4 each = 10 useful values for its 4 columns x 7
+// column shifts) and keeps the last 7 sr rows of its 4 columns in registers: hr row h meets sr rows h - x, x = 0..6, so
+// one row of loads (8 float4, issued one row ahead) feeds 196 (pixel, site) terms instead of 28.
+// The 49 (or 2 x 49) per-lane accumulators are fp32 and live for at most CW_FLUSH rows (<= 64 terms); they are then
+// staged through shared memory and folded into fp64 totals in a fixed order (lane l owns quantities l, l + 32, ...).
+// Element-wise arithmetic is the reference's fp32 arithmetic, exactly as in cpsnr_pass_kernel.
+constexpr int CW_COLS = 128, CW_FLUSH = 16, CW_S = 7, CW_SITES = CW_S * CW_S;
+constexpr int CW_TARGET_WARPS = 148 * 11;      // one-warp blocks resident per wave (168 registers, 19 KB of shared memory)
+
+struct CwRow {                                 // one hr / map row segment (12 columns) and the sr row that enters the window
+    float4 h[3], m[3], s[2];
+};
+
+// All terms of one hr row: sites (x, y) with x in [xlo, xhi], columns c < ncol (CPRED) or all four.
+template <int PASS, bool CPRED>
+__device__ __forceinline__ void cw_terms(float (&acc)[CW_S][CW_S], const float (&aux)[CW_S][CW_S], float (&rs)[CW_S],
+                                         const float (&hw)[12], const float (&mw)[12], const float (&svw)[CW_S][4],
+                                         int xlo, int xhi, int ncol) {
+    if (PASS == 1) {                           // rs = sum of the map over this lane's columns, per column shift
+#pragma unroll
+        for (int y = 0; y < CW_S; ++y) {
+            float r = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) r += (!CPRED || c < ncol) ? mw[c + y] : 0.0f;      // n_clear (Evaluator.py:34)
+            rs[y] = r;
+        }
+    }
+#pragma unroll
+    for (int x = 0; x < CW_S; ++x) {
+        if (x < xlo || x > xhi) continue;      // warp-uniform: sr crop row h - x lies outside this band
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (CPRED && c >= ncol) continue;
+#pragma unroll
+            for (int y = 0; y < CW_S; ++y) {
+                const float m = mw[c + y];
+                const float d = hw[c + y] - svw[x][c];               // diff = hr - sr            (Evaluator.py:35)
+                if (PASS == 1) {
+                    acc[x][y] += d * m;                              // sum(diff * hr_map)        (Evaluator.py:36)
+                } else {
+                    const float t = (d - aux[x][y]) * m;             // (diff - bias) * hr_map    (Evaluator.py:37)
+                    acc[x][y] += t * t;
+                }
+            }
+        }
+    }
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(32, 9)
+cpsnr_window_kernel(const float* __restrict__ sr, const float* __restrict__ hr, const float* __restrict__ hm, CpGeom g,
+                    int clip_sr, const float* __restrict__ bias, double* __restrict__ partial) {
+    constexpr int NQ = PASS == 1 ? 2 * CW_SITES : CW_SITES;      // quantities per block: [site][n, sum d*m] or [site]
+    constexpr int NK = (NQ + 31) / 32;
+    __shared__ float stage[NQ][33];
+    // PASS 1, n_clear: a row whose 7 sr partners all lie in the band adds rs[y] to every site (x, y), so those rows go
+    // into 7 registers; the few rows at the top and bottom of a band go to the per-site array in shared memory.
+    __shared__ float edge_n[PASS == 1 ? CW_SITES : 1][32];
+    const int lane = threadIdx.x;
+    const int set = blockIdx.y;
+    const int band = blockIdx.x / g.col_blocks, cb = blockIdx.x % g.col_blocks;
+    const int j0 = cb * CW_COLS + lane * 4;                      // first crop column of this lane
+    const int ncol = min(4, g.size - j0);                        // <= 0: idle lane
+    const bool all_full = __all_sync(0xffffffffu, ncol == 4);
+    const size_t plane = static_cast<size_t>(g.H) * g.W;
+    const float* srp = sr + set * plane + static_cast<size_t>(g.border) * g.W + j0;
+    const float* hrp = hr + set * plane + j0;
+    const float* hmp = hm + set * plane + j0;
+    const int i0 = band * g.band_rows, i1 = min(g.size, i0 + g.band_rows);
+    const int h_end = i1 + CW_S - 1;                             // hr rows [i0, h_end) meet sr crop rows [i0, i1)
+    const bool q_ok[3] = {j0 + 4 <= g.W, j0 + 8 <= g.W, j0 + 12 <= g.W};
+
+    float acc[CW_S][CW_S], aux[CW_S][CW_S];     // PASS 1: acc = sum d*m (aux unused).  PASS 2: acc = sum t*t, aux = bias
+    float n_all[CW_S];                          // PASS 1: sum of rs over the rows that count for every x
+#pragma unroll
+    for (int x = 0; x < CW_S; ++x) {
+        n_all[x] = 0.0f;
+#pragma unroll
+        for (int y = 0; y < CW_S; ++y) {
+            acc[x][y] = 0.0f;
+            aux[x][y] = PASS == 2 ? bias[(set * CW_S + x) * CW_S + y] : 0.0f;
+            if (PASS == 1) edge_n[x * CW_S + y][lane] = 0.0f;
+        }
+    }
+    double tot[NK];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) tot[k] = 0.0;
+
+    auto flush = [&]() {
+#pragma unroll
+        for (int x = 0; x < CW_S; ++x)
+#pragma unroll
+            for (int y = 0; y < CW_S; ++y) {
+                if (PASS == 1) {
+                    stage[(x * CW_S + y) * 2][lane] = n_all[y] + edge_n[x * CW_S + y][lane];
+                    stage[(x * CW_S + y) * 2 + 1][lane] = acc[x][y];
+                    edge_n[x * CW_S + y][lane] = 0.0f;
+                } else {
+                    stage[x * CW_S + y][lane] = acc[x][y];
+                }
+                acc[x][y] = 0.0f;
+            }
+        if (PASS == 1) {
+#pragma unroll
+            for (int y = 0; y < CW_S; ++y) n_all[y] = 0.0f;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+            const int q = lane + 32 * k;
+            if (q < NQ) {
+                double a = 0.0;
+#pragma unroll 8
+                for (int l = 0; l < 32; ++l) a += static_cast<double>(stage[q][l]);
+                tot[k] += a;
+            }
+        }
+        __syncwarp();
+    };
+
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto load_row = [&](int h, CwRow& r) {
+        const size_t off = static_cast<size_t>(h) * g.W;
+        const bool in = h < h_end;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            r.h[q] = (in && q_ok[q]) ? __ldg(reinterpret_cast<const float4*>(hrp + off) + q) : zero4;
+            r.m[q] = (in && q_ok[q]) ? __ldg(reinterpret_cast<const float4*>(hmp + off) + q) : zero4;
+        }
+        const bool sin = h < i1;                                     // sr crop row h exists in this band
+#pragma unroll
+        for (int q = 0; q < 2; ++q) r.s[q] = (sin && q_ok[q]) ? __ldg(reinterpret_cast<const float4*>(srp + off) + q) : zero4;
+    };
+
+    float svw[CW_S][4];                                              // svw[x] = sr crop row h - x (columns j0 .. j0 + 3)
+#pragma unroll
+    for (int x = 0; x < CW_S; ++x)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) svw[x][c] = 0.0f;
+    CwRow nxt;
+    load_row(i0, nxt);
+    int since_flush = 0;
+    for (int h = i0; h < h_end; ++h) {
+        const CwRow cur = nxt;
+        load_row(h + 1, nxt);                                        // in flight while this row is being consumed
+        float hw[12], mw[12];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            hw[4 * q] = cur.h[q].x, hw[4 * q + 1] = cur.h[q].y, hw[4 * q + 2] = cur.h[q].z, hw[4 * q + 3] = cur.h[q].w;
+            mw[4 * q] = cur.m[q].x, mw[4 * q + 1] = cur.m[q].y, mw[4 * q + 2] = cur.m[q].z, mw[4 * q + 3] = cur.m[q].w;
+        }
+#pragma unroll
+        for (int x = CW_S - 1; x > 0; --x)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) svw[x][c] = svw[x - 1][c];
+        svw[0][0] = cur.s[0].w, svw[0][1] = cur.s[1].x, svw[0][2] = cur.s[1].y, svw[0][3] = cur.s[1].z;   // crop column j0 + c = image column j0 + c + 3
+        if (clip_sr) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) svw[0][c] = fminf(fmaxf(svw[0][c], 0.0f), 1.0f);
+        }
+        // sr crop rows i = h - x that lie in this band: x in [xlo, xhi]
+        const int xlo = max(0, h - i1 + 1), xhi = min(CW_S - 1, h - i0);
+        float rs[CW_S];
+        if (all_full)
+            cw_terms<PASS, false>(acc, aux, rs, hw, mw, svw, xlo, xhi, 4);
+        else
+            cw_terms<PASS, true>(acc, aux, rs, hw, mw, svw, xlo, xhi, ncol);
+        if (PASS == 1) {
+            if (xlo == 0 && xhi == CW_S - 1) {
+#pragma unroll
+                for (int y = 0; y < CW_S; ++y) n_all[y] += rs[y];
+            } else {
+                for (int x = xlo; x <= xhi; ++x)
+#pragma unroll
+                    for (int y = 0; y < CW_S; ++y) edge_n[x * CW_S + y][lane] += rs[y];
+            }
+        }
+        if (++since_flush == CW_FLUSH) {
+            flush();
+            since_flush = 0;
+        }
+    }
+    if (since_flush > 0) flush();
+    double* dst = partial + (static_cast<size_t>(set) * g.blocks_per_set + blockIdx.x) * CW_SITES * 2;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+        const int q = lane + 32 * k;
+        if (q < NQ) {
+            if (PASS == 1) {
+                dst[q] = tot[k];
+            } else {
+                dst[2 * q] = tot[k];
+                dst[2 * q + 1] = 0.0;
+            }
+        }
+    }
+}
+
 // One block per imageset, one thread per site.  MODE 1: bias = sum(d*m) / n.  MODE 2: scores + argmax.
 template <int MODE>
 __global__ void cpsnr_finalize_kernel(const double* __restrict__ partial, CpGeom g, float* __restrict__ bias,
@@ -477,6 +678,39 @@ int lanczos_taps_launch(const float* d, int n, int a, int ntaps, float* out, cud
     return 0;
 }
 
+int g_cpsnr_generic = 0;
+
+// Scratch of the scoring entry points (they take no handle): a private stream-ordered pool per device that KEEPS its
+// memory across synchronisations.  With the default pool (release threshold 0) every call that follows a
+// cudaStreamSynchronize -- the normal pattern of a validation loop -- paid a fresh driver allocation: 3.8 ms for a 0.15 ms
+// search on 32 imagesets (tools/cpsnr_trace.py).
+static int scratch_alloc(void** p, size_t bytes, cudaStream_t s) {
+    constexpr int MAX_DEV = 64;
+    static cudaMemPool_t pools[MAX_DEV] = {};
+    int dev = 0;
+    HRN_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEV) {
+        set_error("scratch_alloc: device %d out of range", dev);
+        return -1;
+    }
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (pools[dev] == nullptr) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool = nullptr;
+        HRN_CUDA_OK(cudaMemPoolCreate(&pool, &props));
+        unsigned long long keep = ~0ull;
+        HRN_CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        pools[dev] = pool;
+    }
+    HRN_CUDA_OK(cudaMallocFromPoolAsync(p, bytes, pools[dev], s));
+    return 0;
+}
+
 int shift_cpsnr_launch(const float* sr, const float* hr, const float* hm, int B, int H, int W, int border,
                        int clip_sr, float* best_db, int32_t* best_site, float* site_db, cudaStream_t s) {
     if (H != W) {
@@ -497,30 +731,44 @@ int shift_cpsnr_launch(const float* sr, const float* hr, const float* hm, int B,
     g.border = border;
     g.S = 2 * border + 1;
     g.size = W - 2 * border;
-    g.col_blocks = (g.size + CP_COLS - 1) / CP_COLS;
-    // enough row bands to fill the GPU (224-thread blocks, ~8 per SM), at least 8 rows each, a multiple of 4 rows
-    int want = (CP_TARGET_BLOCKS + B * g.col_blocks - 1) / (B * g.col_blocks);
-    want = want < 1 ? 1 : (want > (g.size + 7) / 8 ? (g.size + 7) / 8 : want);
-    g.band_rows = (((g.size + want - 1) / want) + 3) & ~3;
+    g.vec_ok = (W % 4 == 0) && (((reinterpret_cast<uintptr_t>(sr) | reinterpret_cast<uintptr_t>(hr) | reinterpret_cast<uintptr_t>(hm)) & 15) == 0);
+    // border_w = 3 on 16-byte aligned rows (every case the reference produces) takes the 49-site window kernel
+    const bool window = g.S == CW_S && g.vec_ok && g_cpsnr_generic == 0;
+    if (window) {
+        g.col_blocks = (g.size + CW_COLS - 1) / CW_COLS;
+        // one-warp blocks, at most one full wave of them when the batch is small; a band is at least 8 rows
+        int want = CW_TARGET_WARPS / (B * g.col_blocks);
+        want = want < 1 ? 1 : (want > (g.size + 7) / 8 ? (g.size + 7) / 8 : want);
+        g.band_rows = (g.size + want - 1) / want;
+    } else {
+        g.col_blocks = (g.size + CP_COLS - 1) / CP_COLS;
+        // enough row bands to fill the GPU (224-thread blocks, ~8 per SM), at least 8 rows each, a multiple of 4 rows
+        int want = (CP_TARGET_BLOCKS + B * g.col_blocks - 1) / (B * g.col_blocks);
+        want = want < 1 ? 1 : (want > (g.size + 7) / 8 ? (g.size + 7) / 8 : want);
+        g.band_rows = (((g.size + want - 1) / want) + 3) & ~3;
+    }
     const int bands = (g.size + g.band_rows - 1) / g.band_rows;
-    g.vec_ok = (W % 4 == 0) && (((reinterpret_cast<uintptr_t>(hr) | reinterpret_cast<uintptr_t>(hm)) & 15) == 0);
     g.blocks_per_set = bands * g.col_blocks;
     const int sites = g.S * g.S;
     const size_t partial_bytes = static_cast<size_t>(B) * g.blocks_per_set * sites * 2 * sizeof(double);
     const size_t nclear_bytes = static_cast<size_t>(B) * sites * sizeof(double);
     const size_t bias_bytes = static_cast<size_t>(B) * sites * sizeof(float);
     uint8_t* ws = nullptr;
-    HRN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&ws), partial_bytes + nclear_bytes + bias_bytes, s));
+    if (scratch_alloc(reinterpret_cast<void**>(&ws), partial_bytes + nclear_bytes + bias_bytes, s)) return -1;
     double* partial = reinterpret_cast<double*>(ws);
     double* nclear = reinterpret_cast<double*>(ws + partial_bytes);
     float* bias = reinterpret_cast<float*>(ws + partial_bytes + nclear_bytes);
     dim3 grid(g.blocks_per_set, B), block(CP_LANES, g.S);
-    if (g.S == 7)
+    if (window)
+        cpsnr_window_kernel<1><<<grid, 32, 0, s>>>(sr, hr, hm, g, clip_sr, nullptr, partial);
+    else if (g.S == 7)
         cpsnr_pass_kernel<1, 7><<<grid, block, 0, s>>>(sr, hr, hm, g, clip_sr, nullptr, partial);
     else
         cpsnr_pass_kernel<1, 0><<<grid, block, 0, s>>>(sr, hr, hm, g, clip_sr, nullptr, partial);
     cpsnr_finalize_kernel<1><<<B, 64, 0, s>>>(partial, g, bias, nclear, nullptr, nullptr, nullptr);
-    if (g.S == 7)
+    if (window)
+        cpsnr_window_kernel<2><<<grid, 32, 0, s>>>(sr, hr, hm, g, clip_sr, bias, partial);
+    else if (g.S == 7)
         cpsnr_pass_kernel<2, 7><<<grid, block, 0, s>>>(sr, hr, hm, g, clip_sr, bias, partial);
     else
         cpsnr_pass_kernel<2, 0><<<grid, block, 0, s>>>(sr, hr, hm, g, clip_sr, bias, partial);
@@ -544,7 +792,7 @@ int clear_loss_launch(const float* sr, const float* hr, const float* hm, int B, 
     const size_t hw = static_cast<size_t>(H) * W;
     const size_t partial_bytes = static_cast<size_t>(B) * CL_BLOCKS * 2 * sizeof(double);
     uint8_t* ws = nullptr;
-    HRN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&ws), partial_bytes + B * sizeof(double) + B * sizeof(float), s));
+    if (scratch_alloc(reinterpret_cast<void**>(&ws), partial_bytes + B * sizeof(double) + B * sizeof(float), s)) return -1;
     double* partial = reinterpret_cast<double*>(ws);
     double* nclear = reinterpret_cast<double*>(ws + partial_bytes);
     float* bias = reinterpret_cast<float*>(ws + partial_bytes + B * sizeof(double));

@@ -48,6 +48,11 @@ def _search(sr, hr, hr_map, border_w, clip_sr=False, device=None):
     return best, arg, table, single, is_numpy
 
 
+def scoring_debug_set(knob: str, value: int) -> None:
+    """Process-wide test knobs of the scoring kernels (hrn_scoring_debug_set), e.g. ("cpsnr_generic", 1)."""
+    _lib.check(_lib.load().hrn_scoring_debug_set(knob.encode(), int(value)), "hrn_scoring_debug_set")
+
+
 def _finish(t, single, is_numpy):
     if is_numpy:
         a = t.cpu().numpy()

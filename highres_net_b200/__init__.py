@@ -12,9 +12,9 @@ __path__.append(_os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath
 
 from .hrnet import HRNet  # noqa: E402
 from .lanczos import lanczos_kernel, lanczos_shift, apply_shifts  # noqa: E402
-from .evaluator import cPSNR, shift_cPSNR, shift_cPSNR_argmax  # noqa: E402
+from .evaluator import cPSNR, shift_cPSNR, shift_cPSNR_argmax, scoring_debug_set  # noqa: E402
 from .losses import get_loss, get_crop_mask  # noqa: E402
 from ._lib import library_path, kernel_launch_count  # noqa: E402
 
 __all__ = ["HRNet", "lanczos_kernel", "lanczos_shift", "apply_shifts", "cPSNR", "shift_cPSNR", "shift_cPSNR_argmax", "get_loss", "get_crop_mask",
-           "library_path", "kernel_launch_count"]
+           "library_path", "kernel_launch_count", "scoring_debug_set"]

@@ -146,6 +146,9 @@ int32_t hrn_forward_dump(hrn_handle* h, const float* lrs, const float* alphas, i
  * super-resolved image is bit-identical either way).  "debug_flags" disables parts of the conv kernel for
  * performance triage (results are then garbage). */
 int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value);
+/* Process-wide test knobs of the scoring entry points (they take no handle).  "cpsnr_generic" = 1 makes hrn_shift_cpsnr use
+ * the general shift-window kernel also for border_w = 3 (default 0: the 49-site window kernel); both must agree. */
+int32_t hrn_scoring_debug_set(const char* knob, int32_t value);
 
 /* Per-launch device timing of HRNet.forward, by kernel class, with CUDA events recorded on the stream the
  * kernels run on.  hrn_profile_begin arms it; every later hrn_forward* call records one event pair per launch;

@@ -519,6 +519,48 @@ def test_shift_cpsnr_known_shift_full_size(hb, dev):
     assert torch.equal(xy.cpu().long(), shifts + 3)
 
 
+@pytest.mark.parametrize("b,s,kind", [(2, 8, "rand"), (3, 12, "rand"), (2, 20, "soft"), (5, 136, "rand"), (2, 260, "shift"),
+                                      (3, 384, "rand"), (40, 64, "rand"), (3, 40, "degenerate")])
+def test_shift_cpsnr_window_kernel_vs_generic_and_oracle(hb, dev, b, s, kind):
+    """border_w = 3 runs the 49-site window kernel (one warp sweeps a band of rows for all sites); the general
+    shift-window kernel behind the "cpsnr_generic" knob and the oracle must give the same table and the same best shift.
+    Sizes cover one lane of columns, partly filled column blocks, several bands and the degenerate masks."""
+    rng = np.random.RandomState(100 + s + b)
+    sr = rng.rand(b, s, s).astype(np.float32)
+    hr = rng.rand(b, s, s).astype(np.float32)
+    hm = (rng.rand(b, s, s) > 0.1).astype(np.float32)
+    if kind == "soft":
+        hm = rng.rand(b, s, s).astype(np.float32)
+    if kind == "shift":
+        hr = np.clip(np.roll(sr, (2, -1), (1, 2)) + 0.02 + 0.01 * rng.randn(b, s, s), 0, 1).astype(np.float32)
+    if kind == "degenerate":
+        hm[0] = 0.0
+        hr[1] = sr[1]
+        hm[2] = 0.0
+        hm[2, s // 2, s // 2] = 1.0
+    args = [torch.from_numpy(a).to(dev) for a in (sr, hr, hm)]
+    best_w, xy_w, tab_w = hb.shift_cPSNR_argmax(*args)
+    hb.scoring_debug_set("cpsnr_generic", 1)
+    try:
+        best_g, xy_g, tab_g = hb.shift_cPSNR_argmax(*args)
+    finally:
+        hb.scoring_debug_set("cpsnr_generic", 0)
+    ref_max, ref_arg, ref_sites = scoring_oracle.shift_cpsnr(sr, hr, hm)
+    tab_w, tab_g, ref_sites = tab_w.cpu().numpy(), tab_g.cpu().numpy(), ref_sites.T
+    for tab in (tab_w, tab_g):
+        assert np.array_equal(np.isnan(tab), np.isnan(ref_sites))
+        assert np.array_equal(np.isposinf(tab), np.isposinf(ref_sites))
+        fin = np.isfinite(ref_sites)
+        assert np.abs(tab[fin] - ref_sites[fin]).max(initial=0.0) <= CPSNR_KERNEL_GATE_DB
+    arg_w = (xy_w[:, 0] * 7 + xy_w[:, 1]).cpu().numpy()
+    arg_g = (xy_g[:, 0] * 7 + xy_g[:, 1]).cpu().numpy()
+    assert np.array_equal(arg_w, ref_arg) and np.array_equal(arg_g, ref_arg)
+    assert torch.equal(torch.isnan(best_w), torch.isnan(best_g))
+    # run to run: fixed-order reductions -> bit-identical
+    best_w2, xy_w2, tab_w2 = hb.shift_cPSNR_argmax(*args)
+    assert np.array_equal(tab_w2.cpu().numpy(), tab_w, equal_nan=True) and torch.equal(xy_w2, xy_w)
+
+
 def test_shift_cpsnr_rejects_bad_arguments(hb, dev):
     sr = torch.rand(1, 20, 24, device=dev)
     with pytest.raises(RuntimeError):
