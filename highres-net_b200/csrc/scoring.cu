@@ -102,22 +102,21 @@ constexpr int L7_TW = 128, L7_TH = 32, L7_THREADS = 288, L7_HALF = 3;   // 288 >
 constexpr int L7_INW = L7_TW + 2 * L7_HALF, L7_PITCH = L7_INW + 2;   // 134, 136
 constexpr int L7_SEG = 16;                                            // output rows per y-pass work item
 
-__global__ void __launch_bounds__(L7_THREADS)
-lanczos_shift7_kernel(const float* __restrict__ img, const float* __restrict__ shift, int C, int H, int W, int p, int a,
+__global__ void __launch_bounds__(L7_THREADS, 4)
+lanczos_shift7_kernel(const float* __restrict__ img, const float* __restrict__ taps, int C, int H, int W, int p,
                       float* __restrict__ out) {
     __shared__ __align__(16) float tmp[L7_TH][L7_PITCH];
-    __shared__ float taps[2][MAX_TAPS];
     const int plane = blockIdx.z, c = plane % C;
     const int x0 = blockIdx.x * L7_TW, y0 = blockIdx.y * L7_TH;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* src = img + static_cast<size_t>(plane) * H * W;
-    if (threadIdx.x < 2) lanczos_taps_device(shift[c * 2 + threadIdx.x], a, 7, taps[threadIdx.x]);
-    __syncthreads();
+    // taps[(c * 2 + axis) * 7 + t] come from lanczos_taps_kernel (one launch for all channels): computing them here cost
+    // every block two serial sinf chains with every other thread waiting at a barrier (ncu: barrier stalls first)
     float ky[7], kx[7];
 #pragma unroll
     for (int t = 0; t < 7; ++t) {
-        ky[t] = taps[0][t];
-        kx[t] = taps[1][t];
+        ky[t] = __ldg(taps + (c * 2) * 7 + t);
+        kx[t] = __ldg(taps + (c * 2 + 1) * 7 + t);
     }
     const bool y_interior = (y0 - L7_HALF >= 0) && (y0 + L7_TH + L7_HALF <= H);
     // y pass (dim 0 taps first, lanczos.py:90): work item = (column q of the strip, 16-row segment)
@@ -633,53 +632,6 @@ __global__ void clear_loss_finalize_kernel(const double* __restrict__ partial, i
 
 }  // namespace
 
-int lanczos_shift_launch(const float* img, const float* shift, int nb, int c, int H, int W, int p, int a, int ntaps,
-                         float* out, cudaStream_t s) {
-    if (ntaps < 1 || ntaps > MAX_TAPS || (ntaps & 1) == 0) {
-        set_error("lanczos_shift: kernel width N=%d unsupported (odd, <= %d)", ntaps, MAX_TAPS);
-        return -1;
-    }
-    if (p < 0 || p >= H || p >= W) {
-        set_error("lanczos_shift: reflect padding p=%d must be smaller than the image (%d x %d)", p, H, W);
-        return -1;
-    }
-    if (a <= 0) {
-        set_error("lanczos_shift: a must be positive");
-        return -1;
-    }
-    const long long planes = static_cast<long long>(nb) * c;
-    if (planes <= 0 || planes > 65535) {
-        set_error("lanczos_shift: %lld planes outside [1, 65535]", planes);
-        return -1;
-    }
-    if (ntaps == 7) {
-        // the width the reference uses everywhere (ShiftNet.py:87-89): compile-time tile geometry
-        dim3 grid((W + L7_TW - 1) / L7_TW, (H + L7_TH - 1) / L7_TH, static_cast<unsigned>(planes));
-        lanczos_shift7_kernel<<<grid, L7_THREADS, 0, s>>>(img, shift, c, H, W, p, a, out);
-    } else {
-        const int half = ntaps / 2;
-        const size_t smem = (static_cast<size_t>(LZ_TH + 2 * half) + LZ_TH) * (LZ_TW + 2 * half) * sizeof(float);
-        dim3 grid((W + LZ_TW - 1) / LZ_TW, (H + LZ_TH - 1) / LZ_TH, static_cast<unsigned>(planes));
-        lanczos_shift_kernel<<<grid, LZ_THREADS, smem, s>>>(img, shift, c, H, W, p, a, ntaps, out);
-    }
-    note_launches(1);
-    HRN_CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
-int lanczos_taps_launch(const float* d, int n, int a, int ntaps, float* out, cudaStream_t s) {
-    if (ntaps < 1 || ntaps > MAX_TAPS || (ntaps & 1) == 0 || a <= 0 || n <= 0) {
-        set_error("lanczos_taps: need n > 0, a > 0 and odd N <= %d (got n=%d a=%d N=%d)", MAX_TAPS, n, a, ntaps);
-        return -1;
-    }
-    lanczos_taps_kernel<<<(n + 127) / 128, 128, 0, s>>>(d, n, a, ntaps, out);
-    note_launches(1);
-    HRN_CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
-int g_cpsnr_generic = 0;
-
 // Scratch of the scoring entry points (they take no handle): a private stream-ordered pool per device that KEEPS its
 // memory across synchronisations.  With the default pool (release threshold 0) every call that follows a
 // cudaStreamSynchronize -- the normal pattern of a validation loop -- paid a fresh driver allocation: 3.8 ms for a 0.15 ms
@@ -710,6 +662,58 @@ static int scratch_alloc(void** p, size_t bytes, cudaStream_t s) {
     HRN_CUDA_OK(cudaMallocFromPoolAsync(p, bytes, pools[dev], s));
     return 0;
 }
+
+int lanczos_shift_launch(const float* img, const float* shift, int nb, int c, int H, int W, int p, int a, int ntaps,
+                         float* out, cudaStream_t s) {
+    if (ntaps < 1 || ntaps > MAX_TAPS || (ntaps & 1) == 0) {
+        set_error("lanczos_shift: kernel width N=%d unsupported (odd, <= %d)", ntaps, MAX_TAPS);
+        return -1;
+    }
+    if (p < 0 || p >= H || p >= W) {
+        set_error("lanczos_shift: reflect padding p=%d must be smaller than the image (%d x %d)", p, H, W);
+        return -1;
+    }
+    if (a <= 0) {
+        set_error("lanczos_shift: a must be positive");
+        return -1;
+    }
+    const long long planes = static_cast<long long>(nb) * c;
+    if (planes <= 0 || planes > 65535) {
+        set_error("lanczos_shift: %lld planes outside [1, 65535]", planes);
+        return -1;
+    }
+    if (ntaps == 7) {
+        // the width the reference uses everywhere (ShiftNet.py:87-89): compile-time tile geometry
+        float* taps = nullptr;
+        if (scratch_alloc(reinterpret_cast<void**>(&taps), static_cast<size_t>(c) * 2 * 7 * sizeof(float), s)) return -1;
+        lanczos_taps_kernel<<<(2 * c + 127) / 128, 128, 0, s>>>(shift, 2 * c, a, 7, taps);
+        dim3 grid((W + L7_TW - 1) / L7_TW, (H + L7_TH - 1) / L7_TH, static_cast<unsigned>(planes));
+        lanczos_shift7_kernel<<<grid, L7_THREADS, 0, s>>>(img, taps, c, H, W, p, out);
+        note_launches(1);
+        HRN_CUDA_OK(cudaFreeAsync(taps, s));
+    } else {
+        const int half = ntaps / 2;
+        const size_t smem = (static_cast<size_t>(LZ_TH + 2 * half) + LZ_TH) * (LZ_TW + 2 * half) * sizeof(float);
+        dim3 grid((W + LZ_TW - 1) / LZ_TW, (H + LZ_TH - 1) / LZ_TH, static_cast<unsigned>(planes));
+        lanczos_shift_kernel<<<grid, LZ_THREADS, smem, s>>>(img, shift, c, H, W, p, a, ntaps, out);
+    }
+    note_launches(1);
+    HRN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int lanczos_taps_launch(const float* d, int n, int a, int ntaps, float* out, cudaStream_t s) {
+    if (ntaps < 1 || ntaps > MAX_TAPS || (ntaps & 1) == 0 || a <= 0 || n <= 0) {
+        set_error("lanczos_taps: need n > 0, a > 0 and odd N <= %d (got n=%d a=%d N=%d)", MAX_TAPS, n, a, ntaps);
+        return -1;
+    }
+    lanczos_taps_kernel<<<(n + 127) / 128, 128, 0, s>>>(d, n, a, ntaps, out);
+    note_launches(1);
+    HRN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int g_cpsnr_generic = 0;
 
 int shift_cpsnr_launch(const float* sr, const float* hr, const float* hm, int B, int H, int W, int border,
                        int clip_sr, float* best_db, int32_t* best_site, float* site_db, cudaStream_t s) {
