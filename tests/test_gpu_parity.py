@@ -294,6 +294,33 @@ def test_row_partition_does_not_change_results(hb, dev):
         assert torch.equal(o, outs[0])
 
 
+@pytest.mark.parametrize("b,l,s", [(1, 1, 8), (1, 2, 16), (2, 3, 33), (2, 4, 128), (1, 5, 100), (3, 2, 1), (2, 2, 2), (1, 16, 64)])
+def test_fused_resblock_is_bit_identical_to_two_launches(hb, dev, b, l, s):
+    """resblock64_umma (both convs of an encoder ResidualBlock in one launch, the intermediate rows never leave the SM)
+    rounds the intermediate to bf16 exactly like the stand-alone layer: the SR image must equal the two-launch path bit
+    for bit, for any CTA count (strip boundaries move, two extra intermediate rows per strip are recomputed), with
+    alpha = 0 views skipped or not."""
+    model = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval()
+    model.load_state_dict(hrnet_oracle.make_params(cases.WEIGHT_SEED))
+    model = model.to(dev)
+    g = torch.Generator().manual_seed(1000 + 10 * s + l)
+    lrs = torch.rand(b, l, s, s, generator=g).to(dev)
+    al = torch.ones(b, l)
+    if l > 2:
+        al[0, -1] = 0.0
+    al = al.to(dev)
+    outs = []
+    for fuse in (1, 0):
+        for ctas in (0, 3, 37):
+            model.debug_set(dev, "fuse_resblock", fuse)
+            model.debug_set(dev, "max_ctas", ctas)
+            outs.append(model(lrs, al).clone())
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    ref = hrnet_oracle.hrnet_forward(hrnet_oracle.make_params(cases.WEIGHT_SEED), lrs.cpu().numpy(), al.cpu().numpy()).numpy()
+    assert np.abs(outs[0].cpu().numpy() - ref).max() <= SR_GATE
+
+
 def test_forward_host_equals_device_path(net, dev):
     lrs, alphas = cases.hrnet_inputs("b2_l4_s32")
     a = net(torch.from_numpy(lrs).to(dev), torch.from_numpy(alphas).to(dev)).cpu()
