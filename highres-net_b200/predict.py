@@ -2,7 +2,9 @@
 
   * ``collateFunction(min_L)``       -- src/utils.py:49-113: pad / truncate every imageset to ``min_L`` views
                                         (zero views, alpha = 0) and stack the batch;
-  * ``get_sr_and_score(imset, model, min_L=16)`` -- src/predict.py:17-49: collate, HRNet forward, clip, shifted cPSNR.
+  * ``get_sr_and_score(imset, model, min_L=16)`` -- src/predict.py:17-49: collate, HRNet forward, clip, shifted cPSNR;
+  * ``load_model``, ``evaluate``, ``benchmark``, ``Model`` -- src/predict.py:83-158, 200-217: the harness around it
+                                        (evaluate batches imagesets of equal shape; file readers / writers stay out).
 
 Same names, arguments and return values as the reference; the forward and the scoring run through the C ABI on
 the GPU and the SR never takes the D2H -> NumPy -> cPSNR detour of predict.py:40-45 (it is copied back once, only
@@ -112,3 +114,92 @@ def get_sr_and_score_batch(imsets, model, min_L=16):
         scores = shift_cPSNR(sr_dev, hrs.float().to(device), hr_maps.float().to(device), border_w=3, clip_sr=True)
         scores = scores.cpu().numpy().astype(np.float32)
     return sr_dev.cpu().numpy(), scores
+
+
+# ------------------------------------------------------------------ the harness around get_sr_and_score
+def load_model(config, checkpoint_file, device=None):
+    """predict.py:83-100: build ``HRNet(config["network"])`` on the GPU and load a checkpoint written by the reference
+    (``torch.save(fusion_model.state_dict(), ...)``, train.py:220-222 -- the 31 state_dict keys are the same)."""
+    from .hrnet import HRNet
+    if device is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("load_model: no CUDA device; the B200 path has no CPU fallback")
+        device = torch.device("cuda", torch.cuda.current_device())
+    model = HRNet(config["network"]).to(device)
+    model.load_state_dict(torch.load(checkpoint_file, map_location="cpu"))
+    # The reference hands the module back in training mode and calls it that way (predict.py:39; HRNet has no dropout or
+    # batch norm, so the mode changes nothing there).  This path is inference-only and refuses training mode with grad
+    # enabled, so the loaded model is switched to eval here.
+    return model.eval()
+
+
+def _shape_key(imset):
+    return (tuple(imset["lr"].shape[1:]), imset["hr"] is not None)
+
+
+def evaluate(model, train_dataset, val_dataset, test_dataset, min_L=16, batch_size=32):
+    """predict.py:103-135: scores every imageset of the three datasets.  Returns the same three dicts
+    (scores, clerances, part), keyed by imageset name.  Unlike the reference loop (one imageset per forward, D2H of the
+    SR image, NumPy scoring) imagesets of equal shape are grouped ``batch_size`` at a time into one forward and one
+    scoring launch; the SR image never leaves the device.  Per-imageset results are identical to get_sr_and_score
+    (imagesets are independent in every kernel)."""
+    model.eval()
+    device = _device_of(model)
+    if device.type != "cuda":
+        raise RuntimeError("the model must live on a CUDA device: the B200 path has no CPU fallback")
+    scores, clerances, part = {}, {}, {}
+    for split, dataset in (("train", train_dataset), ("val", val_dataset), ("test", test_dataset)):
+        pending = {}                                   # shape key -> imagesets waiting for a full batch
+
+        def flush(group):
+            lrs, alphas, hrs, hr_maps, names = collateFunction(min_L=min_L)(group)
+            sr_dev = model(lrs.float().to(device), alphas.float().to(device))[:, 0]
+            if len(hrs) > 0:
+                sc = shift_cPSNR(sr_dev, hrs.float().to(device), hr_maps.float().to(device), border_w=3, clip_sr=True)
+                sc = sc.cpu().numpy().astype(np.float32)
+            for i, imset in enumerate(group):
+                scores[imset["name"]] = sc[i] if len(hrs) > 0 else None
+                clerances[imset["name"]] = imset["clearances"] if "clearances" in imset else None
+                part[imset["name"]] = split
+
+        for imset in dataset if dataset is not None else ():
+            key = _shape_key(imset)
+            group = pending.setdefault(key, [])
+            group.append(imset)
+            if len(group) == batch_size:
+                flush(group)
+                pending[key] = []
+        for group in pending.values():
+            if group:
+                flush(group)
+    return scores, clerances, part
+
+
+def benchmark(baseline_cpsnrs, scores, part, clerances):
+    """predict.py:138-158: table of the ESA baseline against the model (score = ESA / model, clearance statistics)."""
+    import pandas as pd
+    table = pd.DataFrame({"ESA": baseline_cpsnrs, "model": scores, "clr": clerances, "part": part})
+    table["score"] = table["ESA"] / table["model"]
+    table["mean_clr"] = table["clr"].map(np.mean)
+    table["std_clr"] = table["clr"].map(np.std)
+    return table
+
+
+class Model(object):
+    """predict.py:200-220 without the file writers: ``Model(config).load_checkpoint(f)``, ``model(imset)`` ->
+    (sr, scPSNR), ``model.evaluate(train, val, test, baseline_cpsnrs)`` -> results table."""
+
+    def __init__(self, config):
+        self.config = config
+        self.model = None
+
+    def load_checkpoint(self, checkpoint_file):
+        self.model = load_model(self.config, checkpoint_file)
+
+    def __call__(self, imset):
+        return get_sr_and_score(imset, self.model, min_L=self.config["training"]["min_L"])
+
+    def evaluate(self, train_dataset, val_dataset, test_dataset, baseline_cpsnrs):
+        scores, clearance, part = evaluate(self.model, train_dataset, val_dataset, test_dataset,
+                                           min_L=self.config["training"]["min_L"])
+        return benchmark(baseline_cpsnrs, scores, part, clearance)

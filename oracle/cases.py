@@ -149,3 +149,27 @@ def apply_shifts_inputs(name: str):
     images = rng.rand(b, v, s, s).astype(np.float32)
     thetas = rng.uniform(-1.5, 1.5, size=(b, v, 2)).astype(np.float32)
     return images, thetas
+
+
+# predict.evaluate / benchmark: three tiny datasets built from the PREDICT cases.
+# name -> (predict case that supplies lr / hr / hr_map, split)
+EVALUATE_SETS = {
+    "imgset_a": ("v5_s32", "train"),
+    "imgset_b": ("v20_s32", "train"),
+    "imgset_c": ("v20_s32", "val"),
+    "imgset_d": ("v5_s32", "val"),
+    "imgset_e": ("v16_s24_nohr", "test"),
+}
+EVALUATE_BASELINE = {"imgset_a": 40.0, "imgset_b": 45.5, "imgset_c": 50.25, "imgset_d": 38.125, "imgset_e": 47.0}
+
+
+def evaluate_clearances(name: str):
+    n = PREDICT_CASES[EVALUATE_SETS[name][0]][0]
+    rng = np.random.RandomState(6000 + sorted(EVALUATE_SETS).index(name))
+    return rng.rand(n).astype(np.float64)
+
+
+def evaluate_lrs(name: str):
+    """Distinct inputs per imageset: the predict case's views, scaled a little so that two sets sharing a case differ."""
+    scale = 1.0 - 0.05 * sorted(EVALUATE_SETS).index(name)
+    return (predict_lrs(EVALUATE_SETS[name][0]) * scale).astype(np.float32)

@@ -648,6 +648,59 @@ def test_get_sr_and_score_matches_reference_golden(net, golden, name):
         assert score is None
 
 
+def _evaluate_datasets(golden):
+    g = golden["evaluate"]
+    sets = {"train": [], "val": [], "test": []}
+    for name, (case, split) in cases.EVALUATE_SETS.items():
+        n, s, has_hr = cases.PREDICT_CASES[case]
+        sets[split].append({"name": name, "lr": torch.from_numpy(cases.evaluate_lrs(name)),
+                            "hr": torch.from_numpy(g[name + "__hr"]) if has_hr else None,
+                            "hr_map": torch.from_numpy(g[name + "__hr_map"]) if has_hr else torch.ones(3 * s, 3 * s),
+                            "clearances": cases.evaluate_clearances(name)})
+    return sets
+
+
+@pytest.mark.parametrize("batch_size", [1, 2, 32])
+def test_evaluate_matches_reference_golden(net, golden, batch_size):
+    """predict.evaluate (predict.py:103-135): same three dicts as the reference, scores within the gate; batching
+    imagesets of equal shape does not change a single score (bit-identical to one imageset per forward)."""
+    from highres_net_b200.predict import evaluate, get_sr_and_score
+    g = golden["evaluate"]
+    sets = _evaluate_datasets(golden)
+    scores, clerances, part = evaluate(net, sets["train"], sets["val"], sets["test"], min_L=cases.PREDICT_MIN_L,
+                                       batch_size=batch_size)
+    assert set(scores) == set(cases.EVALUATE_SETS) == set(clerances) == set(part)
+    for name, (case, split) in cases.EVALUATE_SETS.items():
+        assert part[name] == split
+        assert np.array_equal(clerances[name], cases.evaluate_clearances(name))
+        if cases.PREDICT_CASES[case][2]:
+            assert abs(float(scores[name]) - float(g[name + "__score"])) <= CPSNR_GATE_DB
+            one = next(im for im in sets[split] if im["name"] == name)
+            assert np.float32(scores[name]) == get_sr_and_score(one, net, min_L=cases.PREDICT_MIN_L)[1]
+        else:
+            assert scores[name] is None
+
+
+def test_model_wrapper_and_load_model(hb, golden, dev, tmp_path):
+    """predict.Model / load_model (predict.py:83-100, 200-217): a checkpoint written the reference's way
+    (torch.save(state_dict), train.py:220-222) loads into the B200 module and scores like the reference."""
+    from highres_net_b200.predict import Model
+    g = golden["evaluate"]
+    ckpt = tmp_path / "HRNet.pth"
+    torch.save(hrnet_oracle.make_params(cases.WEIGHT_SEED), ckpt)
+    config = {"network": hrnet_oracle.DEFAULT_NETWORK_CONFIG, "training": {"min_L": cases.PREDICT_MIN_L}}
+    m = Model(config)
+    m.load_checkpoint(str(ckpt))
+    sets = _evaluate_datasets(golden)
+    sr, score = m(sets["train"][0])
+    assert sr.shape == (96, 96) and abs(float(score) - float(g["imgset_a__score"])) <= CPSNR_GATE_DB
+    scored = [n for n, (c, _) in cases.EVALUATE_SETS.items() if cases.PREDICT_CASES[c][2]]
+    table = m.evaluate(sets["train"], sets["val"], [], {n: cases.EVALUATE_BASELINE[n] for n in scored})
+    assert list(table.index) == [str(n) for n in g["benchmark__index"]]
+    assert np.abs(table["model"].to_numpy(dtype=np.float64) - g["benchmark__model"]).max() <= CPSNR_GATE_DB
+    assert np.allclose(table["score"].to_numpy(dtype=np.float64), g["benchmark__score"], rtol=1e-3)
+
+
 # ---------------------------------------------------------------------------- train.get_loss twin (SURVEY.md section 8f N3)
 LOSS_REL_GATE = 1e-5      # fp32 element ops as in the reference, fp64 sums
 

@@ -166,3 +166,36 @@ def test_apply_shifts_oracle_matches_reference_golden(golden, name):
     images, thetas = cases.apply_shifts_inputs(name)
     out = scoring_oracle.apply_shifts(images, thetas)
     assert np.abs(out - golden["apply_shifts"][name]).max() <= 2e-6
+
+
+def test_evaluate_oracle_matches_reference_golden(golden):
+    """predict.evaluate of the reference (predict.py:103-135) on the tiny datasets of cases.EVALUATE_SETS: the oracle's
+    get_sr_and_score reproduces every score."""
+    from oracle import predict_oracle
+    g = golden["evaluate"]
+    params = hrnet_oracle.make_params(cases.WEIGHT_SEED)
+    for name, (case, split) in cases.EVALUATE_SETS.items():
+        has_hr = cases.PREDICT_CASES[case][2]
+        im = {"lr": cases.evaluate_lrs(name), "hr": g[name + "__hr"] if has_hr else None,
+              "hr_map": g[name + "__hr_map"] if has_hr else None}
+        _, score = predict_oracle.get_sr_and_score(im, params, cases.PREDICT_MIN_L)
+        if has_hr:
+            assert abs(float(score) - float(g[name + "__score"])) <= 1e-4
+        else:
+            assert score is None and np.isnan(g[name + "__score"])
+
+
+def test_benchmark_mirror_matches_reference_golden(golden):
+    """predict.benchmark (predict.py:138-158) is host-side pandas: same columns, index and values as the reference table."""
+    import importlib
+    predict = importlib.import_module("highres_net_b200.predict")
+    g = golden["evaluate"]
+    names = [str(n) for n in g["benchmark__index"]]
+    scores = {n: np.float32(g[n + "__score"]) for n in names}
+    part = {n: cases.EVALUATE_SETS[n][1] for n in names}
+    clr = {n: cases.evaluate_clearances(n) for n in names}
+    table = predict.benchmark({n: cases.EVALUATE_BASELINE[n] for n in names}, scores, part, clr)
+    assert list(table.columns) == [str(c) for c in g["benchmark__columns"]]
+    assert list(table.index) == names and list(table["part"]) == [str(p) for p in g["benchmark__part"]]
+    for col in ("ESA", "model", "score", "mean_clr", "std_clr"):
+        assert np.allclose(table[col].to_numpy(dtype=np.float64), g["benchmark__" + col], rtol=1e-6, atol=0), col
