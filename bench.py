@@ -352,6 +352,18 @@ def main():
                               "tflops": (v["flops"] / max(v["ms"], 1e-9) / 1e9) if v["flops"] else None}
                           for k, v in prof.items()},
         }
+        # Tensor-pipe utilisation at the clock the timed loop actually ran at: one SM issues 8192 dense bf16 flop per
+        # cycle (tcgen05.mma M128 N192 K16 = 96.1 cycles, tools/umma_probe.cu), 148 SMs.  The ncu figure above is taken
+        # with the kernels serialised at ~1.9 GHz (no power cap), where memory latency weighs more.
+        if clocks and clocks.get("sm_mhz"):
+            per_ghz = 148 * 8192 * 1e-3                         # TFLOP/s per GHz of SM clock at 100 % pipe activity
+            tf_clock = per_ghz * clocks["sm_mhz"] * 1e-3
+            roofline["tensor_pipe_util_at_sampled_clock"] = {
+                "sm_mhz": clocks["sm_mhz"], "pipe_peak_tflops_at_clock": tf_clock,
+                "dominant_kernel": ach / tf_clock,
+                "whole_step": hrnet_oracle.flops_per_imageset(l, s, s) * b * world * args.steps / ms_total / 1e9 / world / tf_clock,
+                "note": "achieved TFLOP/s / (148 SMs x 8192 flop/cycle x median SM clock of rank 0 during the timed loop); "
+                        "dominant_kernel uses the per-class time of the profile loop that follows the timed loop"}
         flops_step = hrnet_oracle.flops_per_imageset(l, s, s) * b
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
