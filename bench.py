@@ -365,12 +365,15 @@ def main():
                 "note": "achieved TFLOP/s / (148 SMs x 8192 flop/cycle x median SM clock of rank 0 during the timed loop); "
                         "dominant_kernel uses the per-class time of the profile loop that follows the timed loop"}
         flops_step = hrnet_oracle.flops_per_imageset(l, s, s) * b
+        which = {(32, 16, 128): "BASELINE.json configs[1]", (32, 32, 128): "BASELINE.json configs[2], per-GPU shard",
+                 (2, 4, 128): "BASELINE.json configs[0] shape", (8, 8, 512): "BASELINE.json configs[4] shape"}.get(
+                     (b, l, s), "non-default shape")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"HRNet inference n_views={l} batch={b}/GPU {s}x{s}->{3 * s}x{3 * s} "
-                                   f"(BASELINE.json configs[1]), random-init weights, fp32 in/out, bf16 activations "
+                                   f"({which}), random-init weights, fp32 in/out, bf16 activations "
                                    f"with fp32 accumulation",
                        "l2": f"inputs rotate over {n_rot} distinct batches ({n_rot * b * l * s * s * 4 / 1e6:.0f} MB "
                              f"> 126 MB L2); activations stream through HBM every step",
