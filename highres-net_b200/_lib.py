@@ -38,6 +38,7 @@ SYMBOLS = {
                                           c_void_p, POINTER(c_int64)]),
     "hrn_forward_host_wait": (c_int32, [c_void_p, c_int64]),
     "hrn_u16_to_unit_float": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "hrn_unit_float_to_u16": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "hrn_lanczos_shift": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                     c_int32, c_void_p, c_void_p]),
     "hrn_lanczos_taps": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),

@@ -767,6 +767,14 @@ int32_t hrn_u16_to_unit_float(const uint16_t* src, int64_t n, float* dst, void* 
     return n == 0 ? 0 : hrn::u16_to_unit_float_launch(src, static_cast<size_t>(n), dst, static_cast<cudaStream_t>(stream));
 }
 
+int32_t hrn_unit_float_to_u16(const float* src, int64_t n, uint16_t* dst, int32_t* out_of_range, void* stream) {
+    if (src == nullptr || dst == nullptr || n < 0) {
+        set_error("hrn_unit_float_to_u16: bad argument");
+        return -1;
+    }
+    return n == 0 ? 0 : hrn::unit_float_to_u16_launch(src, static_cast<size_t>(n), dst, out_of_range, static_cast<cudaStream_t>(stream));
+}
+
 int32_t hrn_lanczos_shift(const float* img, const float* shift, int32_t Nb, int32_t C, int32_t H, int32_t W, int32_t p,
                           int32_t a, int32_t ntaps, float* out, void* stream) {
     if (img == nullptr || shift == nullptr || out == nullptr) {

@@ -90,6 +90,7 @@ int decoder_umma_launch(const __nv_bfloat16* in, int B, int image_stride, int H,
 int nhwc_bf16_to_nchw_f32_launch(const __nv_bfloat16* in, int n, int H, int W, int C, int group, int stride, float* out,
                                  cudaStream_t s);
 int u16_to_unit_float_launch(const uint16_t* in, size_t n, float* out, cudaStream_t s);
+int unit_float_to_u16_launch(const float* in, size_t n, uint16_t* out, int* bad, cudaStream_t s);
 // live-work lists (see pointwise.cu)
 int live_levels(int L);
 size_t live_scratch_bytes(int B, int L);

@@ -55,6 +55,20 @@ __global__ void u16_to_unit_float_kernel(const uint16_t* __restrict__ in, size_t
         out[i] = __fdiv_rn(static_cast<float>(in[i]), 65535.0f);
 }
 
+// predict.py:176 on the way out: skimage.img_as_uint(sr) for a float32 image (scikit-image 0.24, util/dtype.py _convert:
+// float32 arithmetic because the output has 2 bytes) = clip(rint(x * 65535), 0, 65535) with round-half-to-even; values
+// outside [-1, 1] make skimage raise, here they set *bad (the host wrapper raises).  NaN -> 0 without a flag.
+__global__ void unit_float_to_u16_kernel(const float* __restrict__ in, size_t n, uint16_t* __restrict__ out, int* __restrict__ bad) {
+    bool any_bad = false;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float x = in[i];
+        any_bad |= (x < -1.0f) || (x > 1.0f);
+        const float r = rintf(__fmul_rn(x, 65535.0f));
+        out[i] = static_cast<uint16_t>(fminf(fmaxf(r, 0.0f), 65535.0f));      // fmaxf(NaN, 0) = 0
+    }
+    if (__any_sync(0xffffffffu, any_bad) && (threadIdx.x & 31) == 0 && bad != nullptr) atomicOr(bad, 1);
+}
+
 // ------------------------------------------------------------------ live-work lists
 // Which views and view pairs can reach the output?  HRNet.py:123-128 merges a pair as alice + alpha_bob * fuse(alice, bob),
 // so a pair whose bob has alpha = 0 contributes nothing but alice, and everything that only feeds such pairs (the
@@ -159,6 +173,15 @@ int nhwc_bf16_to_nchw_f32_launch(const __nv_bfloat16* in, int n, int H, int W, i
 int u16_to_unit_float_launch(const uint16_t* in, size_t n, float* out, cudaStream_t s) {
     const size_t want = (n + 255) / 256;
     u16_to_unit_float_kernel<<<static_cast<unsigned>(want < 148 * 16 ? want : 148 * 16), 256, 0, s>>>(in, n, out);
+    note_launches(1);
+    HRN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int unit_float_to_u16_launch(const float* in, size_t n, uint16_t* out, int* bad, cudaStream_t s) {
+    const size_t want = (n + 255) / 256;
+    if (bad != nullptr) HRN_CUDA_OK(cudaMemsetAsync(bad, 0, sizeof(int), s));
+    unit_float_to_u16_kernel<<<static_cast<unsigned>(want < 148 * 16 ? want : 148 * 16), 256, 0, s>>>(in, n, out, bad);
     note_launches(1);
     HRN_CUDA_OK(cudaGetLastError());
     return 0;

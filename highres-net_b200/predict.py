@@ -34,6 +34,25 @@ def img_as_float_u16(raw):
     return out
 
 
+def img_as_uint_u16(sr):
+    """predict.py:176 on the device: ``skimage.img_as_uint(sr)`` for a float32 image, i.e. clip(rint(x * 65535), 0, 65535)
+    in fp32 with round-half-to-even (scikit-image 0.24 ``util/dtype.py: _convert``).  sr: CUDA float32 tensor (any shape)
+    -> uint16 tensor of that shape (half the D2H bytes of the float image).  Raises ValueError like skimage when a value
+    lies outside [-1, 1] (an unclipped SR image can: clip first, as predict.py:43 does for scoring)."""
+    _lib.require_cuda_tensor(sr, "sr")
+    if sr.dtype != torch.float32:
+        raise TypeError("img_as_uint_u16 expects a float32 tensor")
+    src = sr.contiguous()
+    out = torch.empty(src.shape, dtype=torch.uint16, device=src.device)
+    bad = torch.zeros(1, dtype=torch.int32, device=src.device)
+    with torch.cuda.device(src.device):
+        _lib.check(_lib.load().hrn_unit_float_to_u16(src.data_ptr(), src.numel(), out.data_ptr(), bad.data_ptr(),
+                                                     _lib.current_stream_ptr(src.device)), "hrn_unit_float_to_u16")
+    if int(bad.item()) != 0:
+        raise ValueError("Images of type float must be between -1 and 1.")
+    return out
+
+
 class collateFunction:
     """Util class to create padded batches of data (utils.py:49-113)."""
 

@@ -94,6 +94,10 @@ int32_t hrn_forward_host_wait(hrn_handle* h, int64_t ticket);
 int32_t hrn_forward_host_u16(hrn_handle* h, const uint16_t* lrs_host, const float* alphas_host, int32_t B, int32_t L,
                              int32_t H, int32_t W, float* sr_host, void* stream);
 int32_t hrn_u16_to_unit_float(const uint16_t* src, int64_t n, float* dst, void* stream);
+/* The way out (predict.py:176, generate_submission_file: sr = skimage.img_as_uint(sr) before io.imsave): float32 in
+ * [-1, 1] -> uint16 = clip(rint(x * 65535 in fp32), 0, 65535), round half to even, on DEVICE pointers (n elements).
+ * *out_of_range (device int32, may be NULL) is set to 1 if any value lies outside [-1, 1] (skimage raises there). */
+int32_t hrn_unit_float_to_u16(const float* src, int64_t n, uint16_t* dst, int32_t* out_of_range, void* stream);
 
 /* Replaces lanczos.lanczos_shift (src/lanczos.py:47-107) incl. lanczos_kernel (5-43).
  * DEVICE pointers: img (Nb, C, H, W) fp32, shift (C, 2) = (dy, dx) per channel, out like img.

@@ -34,3 +34,17 @@ def get_sr_and_score(imset, params, min_l=16):
     score = scoring_oracle.shift_cpsnr(np.clip(sr, 0, 1), np.asarray(imset["hr"], np.float32),
                                        np.asarray(imset["hr_map"], np.float32))[0]
     return sr, np.float32(score)
+
+
+def img_as_uint(image):
+    """skimage.img_as_uint for a float32 image (predict.py:176), restated from scikit-image 0.24.0 (the version
+    environment.yml:375 pins; the package is not installed in the build container, so this one function is NOT pinned
+    against the library itself): util/dtype.py `_convert`, float -> unsigned branch: values outside [-1, 1] raise;
+    image * 65535 in float32 (the computation type for a 2-byte output), np.rint (half to even), clip to [0, 65535]."""
+    image = np.asarray(image, dtype=np.float32)
+    if np.min(image) < -1.0 or np.max(image) > 1.0:
+        raise ValueError("Images of type float must be between -1 and 1.")
+    out = np.multiply(image, 65535, dtype=np.float32)
+    np.rint(out, out=out)
+    np.clip(out, 0, 65535, out=out)
+    return out.astype(np.uint16)

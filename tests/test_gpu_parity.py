@@ -701,6 +701,24 @@ def test_model_wrapper_and_load_model(hb, golden, dev, tmp_path):
     assert np.allclose(table["score"].to_numpy(dtype=np.float64), g["benchmark__score"], rtol=1e-3)
 
 
+def test_img_as_uint_matches_the_skimage_rule(dev):
+    """predict.py:176 (img_as_uint before the PNG writer) on the device: every uint16 value survives the round trip
+    through img_as_float_u16, half-way cases round to even, negatives clip to 0, values outside [-1, 1] raise."""
+    from highres_net_b200 import predict
+    from oracle import predict_oracle
+    codes = torch.arange(65536, dtype=torch.int32).to(torch.uint16).to(dev)
+    back = predict.img_as_uint_u16(predict.img_as_float_u16(codes))
+    assert torch.equal(back.cpu().view(torch.int16), codes.cpu().view(torch.int16))
+    rng = np.random.RandomState(9)
+    x = np.concatenate([rng.uniform(-1, 1, 100000), (np.arange(0, 2000) + 0.5) / 65535.0, [-1.0, 1.0, -0.0, 0.0, 1e-9]]).astype(np.float32)
+    got = predict.img_as_uint_u16(torch.from_numpy(x).to(dev)).cpu().view(torch.int16).numpy().view(np.uint16)
+    assert np.array_equal(got, predict_oracle.img_as_uint(x))
+    with pytest.raises(ValueError):
+        predict.img_as_uint_u16(torch.tensor([0.5, 1.001], device=dev))
+    with pytest.raises(RuntimeError):
+        predict.img_as_uint_u16(torch.tensor([0.5]))                               # host tensor: no CPU fallback
+
+
 # ---------------------------------------------------------------------------- train.get_loss twin (SURVEY.md section 8f N3)
 LOSS_REL_GATE = 1e-5      # fp32 element ops as in the reference, fp64 sums
 
