@@ -52,6 +52,11 @@ SYMBOLS = {
     "hrn_debug_set": (c_int32, [c_void_p, c_char_p, c_int32]),
     "hrn_scoring_debug_set": (c_int32, [c_char_p, c_int32]),
     "hrn_kernel_launch_count": (c_int64, []),
+    "hrn_shiftnet_create": (c_int32, [c_int32, POINTER(c_void_p)]),
+    "hrn_shiftnet_destroy": (None, [c_void_p]),
+    "hrn_shiftnet_set_weight": (c_int32, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int32]),
+    "hrn_shiftnet_missing_weights": (c_int32, [c_void_p]),
+    "hrn_shiftnet_forward": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,487 @@
+// ShiftNet, the registration network of the training graph (ShiftNet.py:6-75), as an inference (eval-mode) forward:
+//   x - mean(x, (H, W))  ->  8 x [conv3x3 + BatchNorm (running statistics) + ReLU], MaxPool2d(2) after layers 2, 4, 6
+//   ->  flatten  ->  (Dropout: identity in eval)  ->  Linear(32768, 1024) + ReLU  ->  Linear(1024, 2, no bias)
+// BatchNorm is folded into the conv weights and biases on the host; the convs reuse the tcgen05 kernels of the HRNet
+// path (conv_init_umma for 2 -> 64 with the fp32 planes split hi/lo, conv3x3_umma for 64/128 channels, ReLU = PReLU with
+// slope 0); new here are the plane centring, the 2x2 max pool on bf16 NHWC, the Linear(32768, 1024) as a split-K
+// tcgen05 GEMM fed by TMA and the small fixed-order finish (bias, ReLU, Linear(1024, 2)).
+#include "umma_common.cuh"
+
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/hrn_b200.h"
+
+namespace hrn {
+namespace {
+
+constexpr int SN_SIZE = 128;                 // input crop (ShiftNet.py:45: fc1 expects 128 * 16 * 16 features)
+constexpr int SN_LAYERS = 8;
+constexpr int SN_CIN[SN_LAYERS] = {2, 64, 64, 64, 64, 128, 128, 128};
+constexpr int SN_COUT[SN_LAYERS] = {64, 64, 64, 64, 128, 128, 128, 128};
+constexpr bool SN_POOL[SN_LAYERS] = {false, true, false, true, false, true, false, false};
+constexpr int FC_K = 128 * 16 * 16, FC_N = 1024;
+
+// ------------------------------------------------------------------ x - mean(x, dim=(2, 3))      (ShiftNet.py:58)
+// One block per (pair, channel) plane; the sum is taken in fp64 in a fixed order, the mean rounded to fp32 like
+// torch.mean's result, then subtracted.  Channel 0 planes go to c0 (N, H, W), channel 1 planes to c1.
+constexpr int CP_THREADS = 256;
+__global__ void __launch_bounds__(CP_THREADS)
+center_planes_kernel(const float* __restrict__ x, int hw, float* __restrict__ c0, float* __restrict__ c1) {
+    __shared__ double part[CP_THREADS / 32];
+    __shared__ float mean_s;
+    const int plane = blockIdx.x;
+    const float* src = x + static_cast<size_t>(plane) * hw;
+    float* dst = ((plane & 1) ? c1 : c0) + static_cast<size_t>(plane >> 1) * hw;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < hw; i += CP_THREADS) acc += static_cast<double>(src[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < CP_THREADS / 32; ++w) t += part[w];
+        mean_s = static_cast<float>(t / hw);
+    }
+    __syncthreads();
+    const float mean = mean_s;
+    for (int i = threadIdx.x; i < hw; i += CP_THREADS) dst[i] = src[i] - mean;
+}
+
+// ------------------------------------------------------------------ MaxPool2d(2) on bf16 NHWC
+// Thread = (output pixel, 8-channel group): four 16-byte loads, three packed maxima, one 16-byte store.
+__global__ void maxpool2_nhwc_kernel(const __nv_bfloat16* __restrict__ in, int n_img, int H, int W, int C,
+                                     __nv_bfloat16* __restrict__ out) {
+    const int groups = C / 8, Ho = H / 2, Wo = W / 2;
+    const size_t total = static_cast<size_t>(n_img) * Ho * Wo * groups;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % groups);
+        size_t p = i / groups;
+        const int xo = static_cast<int>(p % Wo);
+        p /= Wo;
+        const int yo = static_cast<int>(p % Ho);
+        const int n = static_cast<int>(p / Ho);
+        const __nv_bfloat16* s = in + ((static_cast<size_t>(n) * H + 2 * yo) * W + 2 * xo) * C + g * 8;
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(s));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(s + C));
+        const uint4 c = __ldg(reinterpret_cast<const uint4*>(s + static_cast<size_t>(W) * C));
+        const uint4 d = __ldg(reinterpret_cast<const uint4*>(s + static_cast<size_t>(W) * C + C));
+        uint4 r;
+        const uint32_t* pa = &a.x;
+        const uint32_t* pb = &b.x;
+        const uint32_t* pc = &c.x;
+        const uint32_t* pd = &d.x;
+        uint32_t* pr = &r.x;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 m0 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(pa + e), *reinterpret_cast<const __nv_bfloat162*>(pb + e));
+            const __nv_bfloat162 m1 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(pc + e), *reinterpret_cast<const __nv_bfloat162*>(pd + e));
+            const __nv_bfloat162 m = __hmax2(m0, m1);
+            pr[e] = *reinterpret_cast<const uint32_t*>(&m);
+        }
+        *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * Ho + yo) * Wo + xo) * C + g * 8) = r;
+    }
+}
+
+// ------------------------------------------------------------------ Linear(32768, 1024) on the tensor cores
+// out[m][n] = sum_k A[m][k] * W[n][k]: A = the layer-8 activations, bf16 [M][32768] (NHWC flatten, the weight columns
+// are permuted to that order when they are set), W bf16 [1024][32768], both K-major, so both operands are plain 2-D TMA
+// tiles (128 rows x 64 k, SWIZZLE_128B) and one tcgen05.mma M128 N128 K16 chain per CTA accumulates in 128 TMEM columns.
+// Grid = 8 column tiles x FC_SPLITS k-ranges x ceil(M / 128) row tiles; every CTA writes its fp32 partial tile, the
+// finish kernel adds the partials in a fixed order (deterministic, no atomics).
+constexpr int FC_TILE = 128, FC_KB = 64, FC_STAGES = 4, FC_SPLITS = 16;
+constexpr int FC_OP_BYTES = FC_TILE * 128;                 // one operand tile: 128 rows x 128 B
+constexpr int FC_STAGE_BYTES = 2 * FC_OP_BYTES;
+constexpr int FC_BAR_OFFSET = FC_STAGES * FC_STAGE_BYTES;
+constexpr int FC_SMEM_BYTES = FC_BAR_OFFSET + 256 + 1024;
+constexpr int FC_THREADS = 192;                            // warp 0: TMA, warp 1: MMA, warps 2-5: TMEM alloc + epilogue
+constexpr int FC_ITERS = FC_K / FC_SPLITS / FC_KB;
+
+__global__ void __launch_bounds__(FC_THREADS, 1)
+fc1_umma_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap b_map,
+                float* __restrict__ partial, int m_pad) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (base - ptx::smem_u32(smem_raw));
+    const uint32_t bars = base + FC_BAR_OFFSET;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * FC_STAGES, bar_done = bars + 16 * FC_STAGES;
+    const uint32_t tmem_slot = bar_done + 8;
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tile = blockIdx.x, split = blockIdx.y, m_tile = blockIdx.z;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < FC_STAGES; ++i) {
+            ptx::mbar_init(bar_full + 8 * i, 1);
+            ptx::mbar_init(bar_empty + 8 * i, 1);
+        }
+        ptx::mbar_init(bar_done, 1);
+        ptx::fence_barrier_init();
+        ptx::prefetch_tensormap(&a_map);
+        ptx::prefetch_tensormap(&b_map);
+    }
+    if (warp == 2) ptx::tmem_alloc<FC_TILE>(tmem_slot);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    if (warp == 0) {
+        if (ptx::elect_one()) {
+            const int k0 = split * (FC_K / FC_SPLITS);
+            for (int it = 0; it < FC_ITERS; ++it) {
+                const uint32_t slot = it % FC_STAGES, ph = (it / FC_STAGES) & 1;
+                ptx::mbar_wait(bar_empty + 8 * slot, ph ^ 1, 1);
+                ptx::mbar_expect_tx(bar_full + 8 * slot, FC_STAGE_BYTES);
+                const uint32_t dst = base + slot * FC_STAGE_BYTES;
+                ptx::tma_load_4d(dst, &a_map, k0 + it * FC_KB, m_tile * FC_TILE, 0, 0, bar_full + 8 * slot);
+                ptx::tma_load_4d(dst + FC_OP_BYTES, &b_map, k0 + it * FC_KB, n_tile * FC_TILE, 0, 0, bar_full + 8 * slot);
+            }
+        }
+    } else if (warp == 1) {
+        if (ptx::elect_one()) {
+            constexpr uint32_t idesc = ptx::umma_idesc_bf16(FC_TILE, FC_TILE);
+            for (int it = 0; it < FC_ITERS; ++it) {
+                const uint32_t slot = it % FC_STAGES;
+                ptx::mbar_wait(bar_full + 8 * slot, (it / FC_STAGES) & 1, 2);
+                ptx::tc_fence_after();
+                uint64_t ad = make_desc(desc_lo(base + slot * FC_STAGE_BYTES));
+                uint64_t bd = make_desc(desc_lo(base + slot * FC_STAGE_BYTES + FC_OP_BYTES));
+#pragma unroll
+                for (int j = 0; j < FC_KB / 16; ++j) {
+                    ptx::umma_bf16(tmem_base, ad, bd, idesc, (it > 0 || j > 0) ? 1u : 0u);
+                    ad += 2;
+                    bd += 2;
+                }
+                ptx::umma_commit(bar_empty + 8 * slot);
+            }
+            ptx::umma_commit(bar_done);
+        }
+    } else {
+        // epilogue: warp w reads TMEM lanes [32 (w % 4), +32) = output rows, all 128 columns, 32 at a time
+        const int q = warp & 3;
+        ptx::mbar_wait(bar_done, 0, 3);
+        ptx::tc_fence_after();
+        const int row = m_tile * FC_TILE + q * 32 + lane;
+        float* dst = partial + (static_cast<size_t>(split) * m_pad + row) * FC_N + n_tile * FC_TILE;
+#pragma unroll 1
+        for (int cg = 0; cg < FC_TILE / 32; ++cg) {
+            uint32_t v[32];
+            ptx::tmem_ld_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + cg * 32, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                *reinterpret_cast<uint4*>(dst + cg * 32 + 4 * e) = make_uint4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+        }
+        ptx::tc_fence_before();
+    }
+    __syncthreads();
+    ptx::tc_fence_after();
+    if (warp == 2) ptx::tmem_dealloc<FC_TILE>(tmem_base);
+}
+
+// h = ReLU(sum over splits + b1) (ShiftNet.py:70-71), theta = h . W2^T (ShiftNet.py:72): one block per pair, fixed order.
+constexpr int FF_THREADS = 256;
+__global__ void __launch_bounds__(FF_THREADS)
+fc_finish_kernel(const float* __restrict__ partial, int m_pad, const float* __restrict__ b1, const float* __restrict__ w2,
+                 float* __restrict__ theta) {
+    __shared__ float red[2][FF_THREADS / 32];
+    const int m = blockIdx.x;
+    float t0 = 0.0f, t1 = 0.0f;
+    for (int k = threadIdx.x; k < FC_N; k += FF_THREADS) {
+        float h = b1[k];
+#pragma unroll
+        for (int s = 0; s < FC_SPLITS; ++s) h += partial[(static_cast<size_t>(s) * m_pad + m) * FC_N + k];
+        h = fmaxf(h, 0.0f);
+        t0 = fmaf(h, w2[k], t0);
+        t1 = fmaf(h, w2[FC_N + k], t1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        t0 += __shfl_down_sync(0xffffffffu, t0, o);
+        t1 += __shfl_down_sync(0xffffffffu, t1, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = t0;
+        red[1][threadIdx.x >> 5] = t1;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        float t = 0.0f;
+        for (int w = 0; w < FF_THREADS / 32; ++w) t += red[threadIdx.x][w];
+        theta[2 * m + threadIdx.x] = t;
+    }
+}
+
+// 2-D bf16 matrix [rows][cols] row-major as a TMA map with 128-row x 64-column boxes (the NHWC encoder with W = rows).
+int encode_matrix_map(CUtensorMap* map, const void* base, int rows, int cols) {
+    return encode_nhwc_map(map, base, cols, rows, 1, 1, FC_TILE);
+}
+
+struct Layer {
+    std::vector<float> w, b, gamma, beta, mean, var;     // host copies until the fold
+    uint8_t* w_img = nullptr;                            // device: packed bf16 weights with BatchNorm folded in
+    float* bias = nullptr;                               // device: folded bias
+};
+
+}  // namespace
+}  // namespace hrn
+
+struct hrn_shiftnet {
+    int device = 0, sm_count = 0;
+    hrn::Layer layer[hrn::SN_LAYERS];
+    std::vector<float> fc1_w, fc1_b, fc2_w;
+    std::map<std::string, bool> have;
+    bool dirty = true;                                   // host weights changed since the last fold / upload
+    __nv_bfloat16* fc1_w_dev = nullptr;                  // [1024][32768] bf16, columns in NHWC flatten order
+    float *fc1_b_dev = nullptr, *fc2_w_dev = nullptr;
+    // workspace
+    size_t cap_pairs = 0;
+    float *c0 = nullptr, *c1 = nullptr, *partial = nullptr;
+    __nv_bfloat16* act[2] = {nullptr, nullptr};
+};
+
+namespace {
+
+using hrn::set_error;
+using namespace hrn;
+
+constexpr int EXPECTED_TENSORS = SN_LAYERS * 6 + 3;
+
+int fold_and_upload(hrn_shiftnet* h) {
+    // BatchNorm2d in eval mode (ShiftNet.py:17-42): y = gamma * (conv(x) + b - mean) / sqrt(var + eps) + beta, eps = 1e-5
+    for (int l = 0; l < SN_LAYERS; ++l) {
+        Layer& L = h->layer[l];
+        const int cin = SN_CIN[l], cout = SN_COUT[l];
+        std::vector<float> w(L.w.size()), b(cout);
+        for (int co = 0; co < cout; ++co) {
+            const float s = L.gamma[co] / std::sqrt(L.var[co] + 1e-5f);
+            for (int i = 0; i < cin * 9; ++i) w[static_cast<size_t>(co) * cin * 9 + i] = L.w[static_cast<size_t>(co) * cin * 9 + i] * s;
+            b[co] = (L.b[co] - L.mean[co]) * s + L.beta[co];
+        }
+        const size_t bytes = l == 0 ? conv_init_weight_image_bytes() : conv3x3_bytes_per_weight_image(cin, cout);
+        std::vector<uint8_t> img(bytes);
+        if (l == 0)
+            conv_init_pack_weights(w.data(), img.data());
+        else
+            conv3x3_pack_weights(w.data(), cin, cout, img.data());
+        if (L.w_img == nullptr) HRN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&L.w_img), bytes));
+        if (L.bias == nullptr) HRN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&L.bias), cout * sizeof(float)));
+        HRN_CUDA_OK(cudaMemcpy(L.w_img, img.data(), bytes, cudaMemcpyHostToDevice));
+        HRN_CUDA_OK(cudaMemcpy(L.bias, b.data(), cout * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    // fc1: the reference flattens NCHW (feature c * 256 + y * 16 + x, ShiftNet.py:67); the activations here are NHWC
+    // (feature (y * 16 + x) * 128 + c), so the weight columns are permuted once
+    std::vector<__nv_bfloat16> w1(static_cast<size_t>(FC_N) * FC_K);
+    for (int n = 0; n < FC_N; ++n) {
+        const float* src = h->fc1_w.data() + static_cast<size_t>(n) * FC_K;
+        __nv_bfloat16* dst = w1.data() + static_cast<size_t>(n) * FC_K;
+        for (int c = 0; c < 128; ++c)
+            for (int p = 0; p < 256; ++p) dst[p * 128 + c] = __float2bfloat16_rn(src[c * 256 + p]);
+    }
+    if (h->fc1_w_dev == nullptr) {
+        HRN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->fc1_w_dev), w1.size() * sizeof(__nv_bfloat16)));
+        HRN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->fc1_b_dev), FC_N * sizeof(float)));
+        HRN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->fc2_w_dev), 2 * FC_N * sizeof(float)));
+    }
+    HRN_CUDA_OK(cudaMemcpy(h->fc1_w_dev, w1.data(), w1.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    HRN_CUDA_OK(cudaMemcpy(h->fc1_b_dev, h->fc1_b.data(), FC_N * sizeof(float), cudaMemcpyHostToDevice));
+    HRN_CUDA_OK(cudaMemcpy(h->fc2_w_dev, h->fc2_w.data(), 2 * FC_N * sizeof(float), cudaMemcpyHostToDevice));
+    h->dirty = false;
+    return 0;
+}
+
+int ensure_workspace(hrn_shiftnet* h, int n) {
+    if (static_cast<size_t>(n) <= h->cap_pairs) return 0;
+    auto rel = [](void* p) {
+        if (p != nullptr) cudaFree(p);
+    };
+    rel(h->c0), rel(h->c1), rel(h->partial), rel(h->act[0]), rel(h->act[1]);
+    h->c0 = h->c1 = h->partial = nullptr;
+    h->act[0] = h->act[1] = nullptr;
+    h->cap_pairs = 0;
+    const size_t hw = static_cast<size_t>(SN_SIZE) * SN_SIZE;
+    const size_t m_pad = (static_cast<size_t>(n) + FC_TILE - 1) / FC_TILE * FC_TILE;
+    HRN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->c0), n * hw * sizeof(float)));
+    HRN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->c1), n * hw * sizeof(float)));
+    HRN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->partial), FC_SPLITS * m_pad * FC_N * sizeof(float)));
+    for (int i = 0; i < 2; ++i) HRN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->act[i]), n * hw * 64 * sizeof(__nv_bfloat16)));
+    h->cap_pairs = n;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t hrn_shiftnet_create(int32_t device, hrn_shiftnet** out) {
+    if (out == nullptr) {
+        set_error("hrn_shiftnet_create: null argument");
+        return -1;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        set_error("hrn_shiftnet_create: no CUDA device visible; this library has no CPU fallback");
+        return -1;
+    }
+    if (device < 0 || device >= ndev) {
+        set_error("hrn_shiftnet_create: device %d out of range (0..%d)", device, ndev - 1);
+        return -1;
+    }
+    cudaDeviceProp prop;
+    HRN_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("hrn_shiftnet_create: device %d is sm_%d%d; kernels are built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return -1;
+    }
+    hrn_shiftnet* h = new hrn_shiftnet();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    *out = h;
+    return 0;
+}
+
+void hrn_shiftnet_destroy(hrn_shiftnet* h) {
+    if (h == nullptr) return;
+    cudaSetDevice(h->device);
+    auto rel = [](void* p) {
+        if (p != nullptr) cudaFree(p);
+    };
+    for (auto& L : h->layer) {
+        rel(L.w_img);
+        rel(L.bias);
+    }
+    rel(h->fc1_w_dev), rel(h->fc1_b_dev), rel(h->fc2_w_dev);
+    rel(h->c0), rel(h->c1), rel(h->partial), rel(h->act[0]), rel(h->act[1]);
+    delete h;
+}
+
+int32_t hrn_shiftnet_missing_weights(hrn_shiftnet* h) {
+    return h == nullptr ? -1 : EXPECTED_TENSORS - static_cast<int>(h->have.size());
+}
+
+int32_t hrn_shiftnet_set_weight(hrn_shiftnet* h, const char* key, const float* data, const int64_t* shape, int32_t ndim) {
+    if (h == nullptr || key == nullptr || data == nullptr || shape == nullptr) {
+        set_error("hrn_shiftnet_set_weight: null argument");
+        return -1;
+    }
+    size_t n = 1;
+    for (int i = 0; i < ndim; ++i) n *= static_cast<size_t>(shape[i]);
+    auto want = [&](std::initializer_list<int64_t> dims) {
+        if (ndim != static_cast<int>(dims.size())) return false;
+        int i = 0;
+        for (int64_t d : dims)
+            if (shape[i++] != d) return false;
+        return true;
+    };
+    std::vector<float>* dst = nullptr;
+    const std::string k(key);
+    int l = 0, sub = 0;
+    char what[32] = {};
+    if (sscanf(key, "layer%d.%d.%31s", &l, &sub, what) == 3 && l >= 1 && l <= SN_LAYERS) {
+        Layer& L = h->layer[l - 1];
+        const int cin = SN_CIN[l - 1], cout = SN_COUT[l - 1];
+        const std::string w(what);
+        if (sub == 0 && w == "weight" && want({cout, cin, 3, 3})) dst = &L.w;
+        else if (sub == 0 && w == "bias" && want({cout})) dst = &L.b;
+        else if (sub == 1 && w == "weight" && want({cout})) dst = &L.gamma;
+        else if (sub == 1 && w == "bias" && want({cout})) dst = &L.beta;
+        else if (sub == 1 && w == "running_mean" && want({cout})) dst = &L.mean;
+        else if (sub == 1 && w == "running_var" && want({cout})) dst = &L.var;
+    } else if (k == "fc1.weight" && want({FC_N, FC_K})) {
+        dst = &h->fc1_w;
+    } else if (k == "fc1.bias" && want({FC_N})) {
+        dst = &h->fc1_b;
+    } else if (k == "fc2.weight" && want({2, FC_N})) {
+        dst = &h->fc2_w;
+    }
+    if (dst == nullptr) {
+        set_error("hrn_shiftnet_set_weight: unknown key or wrong shape for '%s' (ShiftNet(in_channel=1) state_dict expected)", key);
+        return -1;
+    }
+    dst->assign(data, data + n);
+    h->have[k] = true;
+    h->dirty = true;
+    return 0;
+}
+
+int32_t hrn_shiftnet_forward(hrn_shiftnet* h, const float* x, int32_t N, int32_t H, int32_t W, float* theta, void* stream) {
+    if (h == nullptr || x == nullptr || theta == nullptr) {
+        set_error("hrn_shiftnet_forward: null argument");
+        return -1;
+    }
+    if (hrn_shiftnet_missing_weights(h) != 0) {
+        set_error("hrn_shiftnet_forward: %d of %d state_dict tensors have not been set", hrn_shiftnet_missing_weights(h), EXPECTED_TENSORS);
+        return -1;
+    }
+    if (N <= 0 || H != SN_SIZE || W != SN_SIZE) {
+        set_error("hrn_shiftnet_forward: need N > 0 pairs of %d x %d crops (got N=%d, %d x %d): fc1 expects 128*16*16 features "
+                  "(ShiftNet.py:45, 67)", SN_SIZE, SN_SIZE, N, H, W);
+        return -1;
+    }
+    HRN_CUDA_OK(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (h->dirty) {
+        HRN_CUDA_OK(cudaStreamSynchronize(s));       // the previous forward may still read the old weights
+        if (fold_and_upload(h)) return -1;
+    }
+    if (ensure_workspace(h, N)) return -1;
+    const int hw = SN_SIZE * SN_SIZE;
+    center_planes_kernel<<<2 * N, CP_THREADS, 0, s>>>(x, hw, h->c0, h->c1);
+    note_launches(1);
+    // layer 1: conv 2 -> 64 on (channel 0 plane, channel 1 plane) = the (view, anchor) pair layout with L = 1
+    if (conv_init_umma_launch(h->c0, h->c1, N, 1, SN_SIZE, SN_SIZE, h->layer[0].w_img, h->layer[0].bias, 0.0f, h->act[0], nullptr,
+                              nullptr, h->sm_count, s))
+        return -1;
+    int cur = 0, size = SN_SIZE;
+    for (int l = 1; l < SN_LAYERS; ++l) {
+        ConvArgs a{};
+        a.n_img = N;
+        a.H = a.W = size;
+        a.cin = SN_CIN[l];
+        a.cout = SN_COUT[l];
+        a.in = h->act[cur];
+        a.in_images = N;
+        a.in_c = SN_CIN[l];
+        a.w_img = h->layer[l].w_img;
+        a.bias = h->layer[l].bias;
+        a.prelu = 0.0f;              // ReLU = PReLU with slope 0
+        a.has_prelu = 1;
+        a.out = h->act[cur ^ 1];
+        a.res_mode = RES_NONE;
+        if (conv3x3_launch(a, h->sm_count, s)) return -1;
+        cur ^= 1;
+        if (SN_POOL[l]) {
+            const size_t work = static_cast<size_t>(N) * (size / 2) * (size / 2) * (SN_COUT[l] / 8);
+            const size_t blocks = (work + 255) / 256;
+            maxpool2_nhwc_kernel<<<static_cast<unsigned>(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, s>>>(h->act[cur], N, size, size, SN_COUT[l],
+                                                                                                             h->act[cur ^ 1]);
+            note_launches(1);
+            cur ^= 1;
+            size /= 2;
+        }
+    }
+    // fc1 (split-K tcgen05 GEMM) + finish
+    const int m_tiles = (N + FC_TILE - 1) / FC_TILE, m_pad = m_tiles * FC_TILE;
+    CUtensorMap a_map, b_map;
+    if (encode_matrix_map(&a_map, h->act[cur], N, FC_K)) return -1;
+    if (encode_matrix_map(&b_map, h->fc1_w_dev, FC_N, FC_K)) return -1;
+    static bool attr_set = false;
+    if (!attr_set) {
+        HRN_CUDA_OK(cudaFuncSetAttribute(fc1_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_BYTES));
+        attr_set = true;
+    }
+    fc1_umma_kernel<<<dim3(FC_N / FC_TILE, FC_SPLITS, m_tiles), FC_THREADS, FC_SMEM_BYTES, s>>>(a_map, b_map, h->partial, m_pad);
+    fc_finish_kernel<<<N, FF_THREADS, 0, s>>>(h->partial, m_pad, h->fc1_b_dev, h->fc2_w_dev, theta);
+    note_launches(2);
+    HRN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -14,7 +14,8 @@ from .hrnet import HRNet  # noqa: E402
 from .lanczos import lanczos_kernel, lanczos_shift, apply_shifts  # noqa: E402
 from .evaluator import cPSNR, shift_cPSNR, shift_cPSNR_argmax, scoring_debug_set  # noqa: E402
 from .losses import get_loss, get_crop_mask  # noqa: E402
+from .shiftnet import ShiftNet, register_batch  # noqa: E402
 from ._lib import library_path, kernel_launch_count  # noqa: E402
 
 __all__ = ["HRNet", "lanczos_kernel", "lanczos_shift", "apply_shifts", "cPSNR", "shift_cPSNR", "shift_cPSNR_argmax", "get_loss", "get_crop_mask",
-           "library_path", "kernel_launch_count", "scoring_debug_set"]
+           "library_path", "kernel_launch_count", "scoring_debug_set", "ShiftNet", "register_batch"]

@@ -171,6 +171,22 @@ int32_t hrn_profile_end(hrn_handle* h, double* ms, double* flops, int64_t* launc
 /* Number of kernels launched by this library (all handles) since load; bench.py reports the delta. */
 int64_t hrn_kernel_launch_count(void);
 
+/* ---- ShiftNet, the registration network on the other side of lanczos_shift in the training graph.
+ * Replaces DeepNetworks.ShiftNet.ShiftNet.forward (src/DeepNetworks/ShiftNet.py:49-75) in EVAL mode: BatchNorm uses its
+ * running statistics (folded into the convs), Dropout is the identity; the caller is train.register_batch
+ * (src/train.py:26-44), which feeds pairs cat([reference, view], 1) of 128 x 128 crops.  Autograd and train-mode batch
+ * statistics are out of scope.  One handle per device; keys and shapes of hrn_shiftnet_set_weight are those of
+ * ShiftNet(in_channel=1).state_dict() (layerK.0.weight/bias, layerK.1.weight/bias/running_mean/running_var for
+ * K = 1..8, fc1.weight, fc1.bias, fc2.weight; num_batches_tracked is not needed), HOST fp32 pointers.
+ * hrn_shiftnet_forward: x (N, 2, 128, 128) fp32 DEVICE -> theta (N, 2) fp32 DEVICE, enqueued on `stream`. */
+typedef struct hrn_shiftnet hrn_shiftnet;
+int32_t hrn_shiftnet_create(int32_t device, hrn_shiftnet** out);
+void hrn_shiftnet_destroy(hrn_shiftnet* h);
+int32_t hrn_shiftnet_set_weight(hrn_shiftnet* h, const char* state_dict_key, const float* host_data, const int64_t* shape,
+                                int32_t ndim);
+int32_t hrn_shiftnet_missing_weights(hrn_shiftnet* h);
+int32_t hrn_shiftnet_forward(hrn_shiftnet* h, const float* x, int32_t N, int32_t H, int32_t W, float* theta, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

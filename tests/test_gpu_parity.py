@@ -801,3 +801,67 @@ def test_forward_host_accepts_raw_u16_views(net, dev):
     a = net.forward_host(torch.from_numpy(raw), torch.from_numpy(alphas), device=dev)
     b = net.forward_host(as_float, torch.from_numpy(alphas), device=dev)
     assert torch.equal(a, b)
+
+
+# ---------------------------------------------------------------------------- ShiftNet
+# bf16 activations / weights with fp32 accumulation through 8 conv layers and a K = 32768 GEMM, against the fp32 reference
+SHIFTNET_GATE = 2e-2      # absolute, on thetas of magnitude ~0.2-0.7 (measured: see DESIGN.md)
+
+
+@pytest.fixture(scope="module")
+def shiftnet(hb, dev):
+    from oracle import shiftnet_oracle
+    net = hb.ShiftNet().eval()
+    net.load_state_dict(shiftnet_oracle.make_params(0), strict=True)
+    return net.to(dev)
+
+
+def test_shiftnet_forward_matches_reference_golden(shiftnet, golden, dev):
+    from oracle import shiftnet_oracle
+    g = golden["shiftnet"]
+    x = torch.from_numpy(shiftnet_oracle.make_pairs(6, 0)).to(dev)
+    theta = shiftnet(x)
+    assert theta.shape == (6, 2) and theta.dtype == torch.float32 and theta.is_cuda
+    err = np.abs(theta.cpu().numpy() - g["theta"]).max()
+    assert err <= SHIFTNET_GATE, err
+    # the differences BETWEEN pairs (what registration is about) survive the bf16 path
+    d_ref = g["theta"] - g["theta"].mean(0)
+    d_got = theta.cpu().numpy() - theta.cpu().numpy().mean(0)
+    assert np.abs(d_got - d_ref).max() <= SHIFTNET_GATE
+    assert torch.equal(shiftnet(x), theta)                                        # deterministic (fixed-order split-K)
+    # batch independence: a pair gives the same theta whatever else is in the batch (bit-exact), also across row tiles
+    big = torch.from_numpy(shiftnet_oracle.make_pairs(150, 2)).to(dev)
+    t_big = shiftnet(big)
+    assert torch.equal(shiftnet(big[140:145]), t_big[140:145])
+    assert torch.equal(shiftnet(big[:1]), t_big[:1])
+
+
+def test_shiftnet_register_batch_matches_reference_golden(hb, shiftnet, golden, dev):
+    from oracle import shiftnet_oracle
+    g = golden["shiftnet"]
+    pairs = shiftnet_oracle.make_pairs(6, 1).reshape(2, 3, 2, 128, 128)
+    lrs = torch.from_numpy(np.ascontiguousarray(pairs[:, :, 1])).to(dev)
+    reference = torch.from_numpy(np.ascontiguousarray(pairs[:, 0, 0][:, None])).to(dev)
+    thetas = hb.register_batch(shiftnet, lrs, reference)
+    assert thetas.shape == (2, 3, 2)
+    assert np.abs(thetas.cpu().numpy() - g["register_thetas"]).max() <= SHIFTNET_GATE
+    # thetas feed transform / apply_shifts (train.py:47-63) like in the reference
+    moved = hb.apply_shifts(shiftnet, lrs, thetas, dev)
+    assert moved.shape == lrs.shape
+
+
+def test_shiftnet_weight_updates_and_error_paths(hb, dev):
+    from oracle import shiftnet_oracle
+    net = hb.ShiftNet().to(dev)
+    x = torch.from_numpy(shiftnet_oracle.make_pairs(2, 3)).to(dev)
+    with pytest.raises(RuntimeError):
+        net(x)                                                                    # training mode: not supported
+    net.eval()
+    assert float(net(x).abs().max()) == 0.0                                       # fc2 starts at zero (ShiftNet.py:48)
+    net.load_state_dict(shiftnet_oracle.make_params(0), strict=True)              # new weights must reach the device copy
+    ref = shiftnet_oracle.shiftnet_forward(shiftnet_oracle.make_params(0), x.cpu().numpy()).numpy()
+    assert np.abs(net(x).cpu().numpy() - ref).max() <= SHIFTNET_GATE
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 2, 64, 64, device=dev))                                # fc1 needs 128 x 128 crops
+    with pytest.raises(ValueError):
+        net(torch.zeros(1, 3, 128, 128, device=dev))

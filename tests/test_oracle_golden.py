@@ -1,6 +1,7 @@
 """CPU suite: the oracle restatement against the fixtures minted from the
 unmodified reference (oracle/make_golden.py).  This is what pins the oracle."""
 import numpy as np
+import torch
 import pytest
 
 from oracle import cases, hrnet_oracle, scoring_oracle
@@ -199,3 +200,34 @@ def test_benchmark_mirror_matches_reference_golden(golden):
     assert list(table.index) == names and list(table["part"]) == [str(p) for p in g["benchmark__part"]]
     for col in ("ESA", "model", "score", "mean_clr", "std_clr"):
         assert np.allclose(table[col].to_numpy(dtype=np.float64), g["benchmark__" + col], rtol=1e-6, atol=0), col
+
+
+def test_shiftnet_oracle_matches_reference_golden(golden):
+    """ShiftNet.forward in eval mode (ShiftNet.py:49-75) and train.register_batch (train.py:26-44) of the reference."""
+    from oracle import shiftnet_oracle
+    g = golden["shiftnet"]
+    params = shiftnet_oracle.make_params(0)
+    theta = shiftnet_oracle.shiftnet_forward(params, shiftnet_oracle.make_pairs(6, 0)).numpy()
+    assert np.abs(theta - g["theta"]).max() <= 1e-5
+    assert np.abs(g["theta"] - g["theta_fp64"]).max() <= 1e-5                     # fp64 arbiter of the reference itself
+    pairs = shiftnet_oracle.make_pairs(6, 1).reshape(2, 3, 2, 128, 128)
+    thetas = shiftnet_oracle.register_batch(params, pairs[:, :, 1], pairs[:, 0, 0][:, None]).numpy()
+    assert thetas.shape == (2, 3, 2) and np.abs(thetas - g["register_thetas"]).max() <= 1e-5
+
+
+def test_shiftnet_mirror_has_the_reference_state_dict(golden):
+    """Same keys in the same order as the reference module, 34,187,648 parameters; a
+    checkpoint of the reference loads with strict=True.  Construction needs no GPU; forward does."""
+    import importlib
+    from oracle import shiftnet_oracle
+    shiftnet = importlib.import_module("highres_net_b200.shiftnet")
+    g = golden["shiftnet"]
+    net = shiftnet.ShiftNet()
+    assert list(net.state_dict().keys()) == [str(k) for k in g["state_dict_keys"]]
+    assert sum(p.numel() for p in net.parameters()) == int(g["n_params"]) == 34187648
+    assert float(net.fc2.weight.abs().max()) == 0.0                               # ShiftNet.py:48
+    net.load_state_dict(shiftnet_oracle.make_params(0), strict=True)
+    with pytest.raises(RuntimeError):
+        net.eval()(torch.zeros(1, 2, 128, 128))                                   # CPU tensor: no fallback
+    with pytest.raises(ValueError):
+        shiftnet.ShiftNet(in_channel=2)
