@@ -56,6 +56,7 @@ SYMBOLS = {
     "hrn_shiftnet_destroy": (None, [c_void_p]),
     "hrn_shiftnet_set_weight": (c_int32, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int32]),
     "hrn_shiftnet_missing_weights": (c_int32, [c_void_p]),
+    "hrn_shiftnet_debug_set": (c_int32, [c_void_p, c_char_p, c_int32]),
     "hrn_shiftnet_forward": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
 }
 

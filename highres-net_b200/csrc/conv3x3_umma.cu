@@ -118,6 +118,9 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
             bool have = walk.next(s);
             ptx::pdl_wait();                 // weights are constants; the activations come from the previous kernel
             uint32_t it = 0;
+            // several narrow images per tile: one box = (W + 2 pixels from x = -1) x G images, segment after segment
+            const int G = geo.img_group;
+            const uint32_t chunk_tx = G > 1 ? static_cast<uint32_t>(G * (a.W + 2) * 128) : static_cast<uint32_t>(CHUNK_TX);
             for (; have; have = walk.next(s)) {
                 int img[2], ch[2];
                 if (a.pair_mode) {
@@ -126,7 +129,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
                     img[1] = b * a.src_views + (a.top - 1 - i);
                     ch[0] = ch[1] = 0;
                 } else {
-                    img[0] = img[1] = s.m;
+                    img[0] = img[1] = s.m * G;
                     ch[0] = 0;
                     ch[1] = 64;
                 }
@@ -138,7 +141,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
                         if (a.debug_flags & 4) {
                             ptx::mbar_arrive(bar_full + 8 * slot);
                         } else {
-                            ptx::mbar_expect_tx(bar_full + 8 * slot, CHUNK_TX);
+                            ptx::mbar_expect_tx(bar_full + 8 * slot, chunk_tx);
                             ptx::tma_load_4d(ring_s + slot * CHUNK_BYTES, &in_map, ch[c], s.xt * TILE_M - 1,
                                              s.y0 - 1 + q, img[c], bar_full + 8 * slot);
                         }
@@ -334,8 +337,14 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
         ptx::pdl_wait();                         // residual reads and output writes touch the previous kernel's tensors
         uint32_t tile = 0;
         for (; have; have = walk.next(s)) {
-            const int x = s.xt * TILE_M + wq * 32 + lane;
-            const bool valid = x < a.W;
+            int x = s.xt * TILE_M + wq * 32 + lane, m_img = s.m;
+            bool valid = x < a.W;
+            if (geo.img_group > 1) {          // tile row = segment g (image s.m * G + g), pixel x of that image's row
+                const int seg = a.W + 2, g = x / seg;
+                x -= g * seg;
+                m_img = s.m * geo.img_group + g;
+                valid = g < geo.img_group && x < a.W && m_img < a.n_img;
+            }
             const __nv_bfloat16* res_img = nullptr;
             int res_c = 0;
             float scale = 1.0f;
@@ -358,7 +367,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
             const __nv_bfloat162 scale2 = __floats2bfloat162_rn(scale, scale);
             const size_t pix0 = static_cast<size_t>(s.y0) * a.W + x;
             const __nv_bfloat16* rp = res_img + pix0 * res_c;
-            const int out_img = a.out_in_stack ? (s.m / a.half) * a.src_views + s.m % a.half : s.m;
+            const int out_img = a.out_in_stack ? (s.m / a.half) * a.src_views + s.m % a.half : m_img;
             __nv_bfloat16* op = a.out + (static_cast<size_t>(out_img) * a.H * a.W + pix0) * a.cout + co0;
             const size_t r_step = static_cast<size_t>(a.W) * res_c, o_step = static_cast<size_t>(a.W) * a.cout;
             for (int i = 0; i < s.rows; ++i, ++tile, rp += r_step, op += o_step) {
@@ -461,7 +470,16 @@ int conv3x3_launch(const ConvArgs& a, int sm_count, cudaStream_t stream) {
     Geometry g;
     g.n_parts = a.cout / NT;
     g.x_tiles = (a.W + TILE_M - 1) / TILE_M;
-    g.total_rows = static_cast<long long>(a.n_img) * g.x_tiles * a.H;
+    // Narrow images (W + 2 <= 64): an M tile of 128 pixels would be mostly empty, so G = 128 / (W + 2) images share one
+    // tile, each with its own zero halo column on both sides (3 images at W = 32, 7 at W = 16).  Every output pixel
+    // still sees exactly the same products in the same order, so results are bit-identical to G = 1.  Plain layers only
+    // (no live-work list, pair gather, residual or in-stack output): that is what the ShiftNet path needs.
+    g.img_group = 1;
+    if (a.W + 2 <= TILE_M / 2 && a.n_img > 1 && !a.no_img_group && a.live_list == nullptr && !a.pair_mode &&
+        a.res_mode == RES_NONE && !a.out_in_stack)
+        g.img_group = TILE_M / (a.W + 2);
+    const int n_groups = (a.n_img + g.img_group - 1) / g.img_group;
+    g.total_rows = static_cast<long long>(n_groups) * g.x_tiles * a.H;
     int ctas = a.max_ctas > 0 ? std::min(a.max_ctas, sm_count) : sm_count;
     ctas = std::max(g.n_parts, (ctas / g.n_parts) * g.n_parts);
     g.groups = static_cast<int>(std::min<long long>(ctas / g.n_parts, g.total_rows));
@@ -469,7 +487,7 @@ int conv3x3_launch(const ConvArgs& a, int sm_count, cudaStream_t stream) {
     g.split = a.strip_split > 0 ? a.strip_split : 1;
 
     CUtensorMap map;
-    if (encode_nhwc_map(&map, a.in, a.in_c, a.W, a.H, a.in_images, SLOT_PIX)) return -1;
+    if (encode_nhwc_map(&map, a.in, a.in_c, a.W, a.H, a.in_images, g.img_group > 1 ? a.W + 2 : SLOT_PIX, 1, g.img_group)) return -1;
     return a.cin == 64 ? launch_impl<64>(a, map, g, ctas, stream) : launch_impl<128>(a, map, g, ctas, stream);
 }
 

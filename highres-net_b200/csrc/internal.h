@@ -60,6 +60,7 @@ struct ConvArgs {
     // of 0 .. n_img; both device pointers, nullptr = dense
     const int* live_list;
     const int* live_count;
+    int no_img_group;         // test knob: 1 = never put several narrow images into one M tile (see conv3x3_launch)
 };
 int conv3x3_bytes_per_weight_image(int cin, int cout);
 // Repack OIHW fp32 (cout, cin, 3, 3) host weights into the pre-swizzled bf16 smem image (host memory).

@@ -418,6 +418,7 @@ int resblock64_launch(const ConvArgs& a1, const float* bias1_host, const uint8_t
     const int ctas = a1.max_ctas > 0 ? std::min(a1.max_ctas, sm_count) : sm_count;
     g.groups = static_cast<int>(std::min<long long>(ctas, g.total_rows));
     g.split = a1.strip_split > 0 ? a1.strip_split : 1;
+    g.img_group = 1;
     CUtensorMap map;
     if (encode_nhwc_map(&map, a1.in, 64, a1.W, a1.H, a1.in_images, SLOT_PIX)) return -1;
     static bool attr_set = false;

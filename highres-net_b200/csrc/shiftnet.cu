@@ -238,6 +238,7 @@ struct hrn_shiftnet {
     std::vector<float> fc1_w, fc1_b, fc2_w;
     std::map<std::string, bool> have;
     bool dirty = true;                                   // host weights changed since the last fold / upload
+    int no_img_group = 0;                                // test knob: one image row per conv tile even for narrow images
     __nv_bfloat16* fc1_w_dev = nullptr;                  // [1024][32768] bf16, columns in NHWC flatten order
     float *fc1_b_dev = nullptr, *fc2_w_dev = nullptr;
     // workspace
@@ -411,6 +412,15 @@ int32_t hrn_shiftnet_set_weight(hrn_shiftnet* h, const char* key, const float* d
     return 0;
 }
 
+int32_t hrn_shiftnet_debug_set(hrn_shiftnet* h, const char* knob, int32_t value) {
+    if (h != nullptr && knob != nullptr && strcmp(knob, "img_group") == 0) {
+        h->no_img_group = value == 0;
+        return 0;
+    }
+    set_error("hrn_shiftnet_debug_set: unknown knob");
+    return -1;
+}
+
 int32_t hrn_shiftnet_forward(hrn_shiftnet* h, const float* x, int32_t N, int32_t H, int32_t W, float* theta, void* stream) {
     if (h == nullptr || x == nullptr || theta == nullptr) {
         set_error("hrn_shiftnet_forward: null argument");
@@ -455,6 +465,7 @@ int32_t hrn_shiftnet_forward(hrn_shiftnet* h, const float* x, int32_t N, int32_t
         a.has_prelu = 1;
         a.out = h->act[cur ^ 1];
         a.res_mode = RES_NONE;
+        a.no_img_group = h->no_img_group;
         if (conv3x3_launch(a, h->sm_count, s)) return -1;
         cur ^= 1;
         if (SN_POOL[l]) {

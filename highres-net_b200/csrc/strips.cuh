@@ -11,6 +11,8 @@ struct Geometry {
     int x_tiles;      // ceil(W / 128)
     long long total_rows;   // n_img * x_tiles * H
     int split;        // ranges per CTA group (round-robin), >= 1
+    int img_group;    // images per M tile: 1 = 128 pixels of one image row; G > 1 = the rows of G narrow images side by
+                      // side, (W + 2)-pixel segments (conv3x3_umma only; the "images" the walker sees are then groups)
 };
 
 struct Strip {

@@ -33,7 +33,7 @@ inline EncodeTiledFn get_encode_fn() {
 // 4-D map over a bf16 NHWC tensor (dims fastest first: C, W, H, N); box = 64 channels x box_pixels x 1 x 1,
 // SWIZZLE_128B, out-of-bounds elements read as zero (that is the conv padding).
 inline int encode_nhwc_map(CUtensorMap* map, const void* base, int channels, int W, int H, int images, int box_pixels,
-                           int image_stride = 1) {
+                           int image_stride = 1, int box_images = 1) {
     EncodeTiledFn encode = get_encode_fn();
     if (encode == nullptr) {
         set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -43,7 +43,7 @@ inline int encode_nhwc_map(CUtensorMap* map, const void* base, int channels, int
                                 static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(images)};
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(channels) * 2, static_cast<cuuint64_t>(W) * channels * 2,
                                    static_cast<cuuint64_t>(H) * W * channels * 2 * image_stride};
-    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_pixels), 1, 1};
+    const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_pixels), 1, static_cast<cuuint32_t>(box_images)};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

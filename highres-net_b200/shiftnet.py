@@ -79,6 +79,11 @@ class ShiftNet(nn.Module):
         except Exception:
             pass
 
+    def debug_set(self, device, knob: str, value: int) -> None:
+        """Bring-up knobs of the native handle (hrn_shiftnet_debug_set)."""
+        _lib.check(_lib.load().hrn_shiftnet_debug_set(self._handle_for(torch.device(device)), knob.encode(), int(value)),
+                   "hrn_shiftnet_debug_set")
+
     def forward(self, x):
         """x (N, 2, 128, 128): pairs cat([reference, view], 1) -> (N, 2) translation parameters (dx, dy)."""
         _lib.require_cuda_tensor(x, "x")

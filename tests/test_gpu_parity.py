@@ -832,6 +832,12 @@ def test_shiftnet_forward_matches_reference_golden(shiftnet, golden, dev):
     # batch independence: a pair gives the same theta whatever else is in the batch (bit-exact), also across row tiles
     big = torch.from_numpy(shiftnet_oracle.make_pairs(150, 2)).to(dev)
     t_big = shiftnet(big)
+    # the 32 x 32 and 16 x 16 layers put 3 / 7 images into one MMA tile: same thetas as one image row per tile
+    for n in (150, 5, 1):
+        shiftnet.debug_set(dev, "img_group", 0)
+        plain = shiftnet(big[:n])
+        shiftnet.debug_set(dev, "img_group", 1)
+        assert torch.equal(plain, t_big[:n]), n
     assert torch.equal(shiftnet(big[140:145]), t_big[140:145])
     assert torch.equal(shiftnet(big[:1]), t_big[:1])
 
