@@ -128,9 +128,16 @@ lanczos_shift7_kernel(const float* __restrict__ img, const float* __restrict__ t
         // all 22 loads are issued before the first use (memory-level parallelism), then 16 outputs are formed
         float col[L7_SEG + 6];
         if (y_interior) {                       // no reflection needed in y for this block (10 of 12 row tiles at 384)
+            // xx is clamped into the image, so the loads are unconditional (a column outside the zero ring is cleared
+            // afterwards) and the row offsets are 32-bit: a predicated load with a size_t product rebuilt the whole
+            // 64-bit address per element, and address arithmetic was a third of all issued instructions.
             const float* base_ptr = src + static_cast<size_t>(y0 + r0 - L7_HALF) * W + xx;
 #pragma unroll
-            for (int t = 0; t < L7_SEG + 6; ++t) col[t] = okx ? __ldg(base_ptr + static_cast<size_t>(t) * W) : 0.0f;
+            for (int t = 0; t < L7_SEG + 6; ++t) col[t] = __ldg(base_ptr + t * W);
+            if (!okx) {
+#pragma unroll
+                for (int t = 0; t < L7_SEG + 6; ++t) col[t] = 0.0f;
+            }
         } else {
 #pragma unroll
             for (int t = 0; t < L7_SEG + 6; ++t) {

@@ -238,6 +238,7 @@ struct hrn_shiftnet {
     std::vector<float> fc1_w, fc1_b, fc2_w;
     std::map<std::string, bool> have;
     bool dirty = true;                                   // host weights changed since the last fold / upload
+    bool fc1_dirty = true;                               // fc1.weight (134 MB on the host) is dropped once it is uploaded
     int no_img_group = 0;                                // test knob: one image row per conv tile even for narrow images
     __nv_bfloat16* fc1_w_dev = nullptr;                  // [1024][32768] bf16, columns in NHWC flatten order
     float *fc1_b_dev = nullptr, *fc2_w_dev = nullptr;
@@ -278,6 +279,12 @@ int fold_and_upload(hrn_shiftnet* h) {
     }
     // fc1: the reference flattens NCHW (feature c * 256 + y * 16 + x, ShiftNet.py:67); the activations here are NHWC
     // (feature (y * 16 + x) * 128 + c), so the weight columns are permuted once
+    if (h->fc1_w_dev == nullptr) {
+        HRN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->fc1_w_dev), static_cast<size_t>(FC_N) * FC_K * sizeof(__nv_bfloat16)));
+        HRN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->fc1_b_dev), FC_N * sizeof(float)));
+        HRN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->fc2_w_dev), 2 * FC_N * sizeof(float)));
+    }
+    if (h->fc1_dirty) {
     std::vector<__nv_bfloat16> w1(static_cast<size_t>(FC_N) * FC_K);
     for (int n = 0; n < FC_N; ++n) {
         const float* src = h->fc1_w.data() + static_cast<size_t>(n) * FC_K;
@@ -285,12 +292,10 @@ int fold_and_upload(hrn_shiftnet* h) {
         for (int c = 0; c < 128; ++c)
             for (int p = 0; p < 256; ++p) dst[p * 128 + c] = __float2bfloat16_rn(src[c * 256 + p]);
     }
-    if (h->fc1_w_dev == nullptr) {
-        HRN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->fc1_w_dev), w1.size() * sizeof(__nv_bfloat16)));
-        HRN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->fc1_b_dev), FC_N * sizeof(float)));
-        HRN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->fc2_w_dev), 2 * FC_N * sizeof(float)));
-    }
     HRN_CUDA_OK(cudaMemcpy(h->fc1_w_dev, w1.data(), w1.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    std::vector<float>().swap(h->fc1_w);
+    h->fc1_dirty = false;
+    }
     HRN_CUDA_OK(cudaMemcpy(h->fc1_b_dev, h->fc1_b.data(), FC_N * sizeof(float), cudaMemcpyHostToDevice));
     HRN_CUDA_OK(cudaMemcpy(h->fc2_w_dev, h->fc2_w.data(), 2 * FC_N * sizeof(float), cudaMemcpyHostToDevice));
     h->dirty = false;
@@ -397,6 +402,7 @@ int32_t hrn_shiftnet_set_weight(hrn_shiftnet* h, const char* key, const float* d
         else if (sub == 1 && w == "running_var" && want({cout})) dst = &L.var;
     } else if (k == "fc1.weight" && want({FC_N, FC_K})) {
         dst = &h->fc1_w;
+        h->fc1_dirty = true;
     } else if (k == "fc1.bias" && want({FC_N})) {
         dst = &h->fc1_b;
     } else if (k == "fc2.weight" && want({2, FC_N})) {
