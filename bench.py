@@ -139,7 +139,7 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline(l, s, seconds_budget=25.0, max_sets=4, threads=None):
+def cpu_baseline(l, s, seconds_budget=8.0, max_sets=24, threads=None):
     """Oracle port (torch CPU fp32) timed on the host cores; bounded sample of the same workload."""
     import torch
     from oracle import hrnet_oracle
@@ -150,7 +150,7 @@ def cpu_baseline(l, s, seconds_budget=25.0, max_sets=4, threads=None):
     t0 = time.perf_counter()
     hrnet_oracle.hrnet_forward(params, lrs, alphas)          # warm-up, also sizes the sample
     once = time.perf_counter() - t0
-    n_sets = int(max(1, min(max_sets, seconds_budget // max(once, 1e-3))))
+    n_sets = int(max(1, min(max_sets, seconds_budget // max(once, 1e-3))))      # x 2 repetitions: 10-20 s of CPU work
     lrs, alphas = synthetic_batch(n_sets, l, s, seed=100)
     best = float("inf")
     for _ in range(2):
@@ -176,9 +176,12 @@ def run_reference(args, rank, world, out):
     l, s = args.views, args.size
     sets_per_step = 2
     lrs, alphas = synthetic_batch(sets_per_step, l, s, seed=100)
-    for _ in range(min(args.warmup, 1)):
+    t0 = time.perf_counter()
+    hrnet_oracle.hrnet_forward(params, lrs, alphas)          # one untimed warm-up step, also sizes the run
+    once = time.perf_counter() - t0
+    for _ in range(max(0, min(args.warmup, 3) - 1)):
         hrnet_oracle.hrnet_forward(params, lrs, alphas)
-    steps = min(args.steps, 5)
+    steps = max(1, min(args.steps, int(150.0 / max(once, 1e-3))))   # all K steps unless that would take more than ~2.5 min
     t0 = time.perf_counter()
     for _ in range(steps):
         hrnet_oracle.hrnet_forward(params, lrs, alphas)
@@ -188,7 +191,7 @@ def run_reference(args, rank, world, out):
               f"torch CPU fp32 (oneDNN)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(1, min(args.warmup, 3)), "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"HRNet inference n_views={l} batch={args.batch}/GPU {s}x{s}->{3 * s}x{3 * s} "
                                f"(BASELINE.json configs[1]); reference arm times a bounded sample on host cores"},
