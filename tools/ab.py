@@ -37,7 +37,7 @@ def t(fn, n=10):
     torch.cuda.synchronize(); e0.record()
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1) / n
-print(json.dumps({"ms_per_step": ms, "burst3_ms": min(bursts), "conv64": p["conv3x3_umma<64>"]["ms"] / 5, "conv128": p["conv3x3_umma<128>"]["ms"] / 5,
+print(json.dumps({"ms_per_step": ms, "burst3_ms": min(bursts), "conv64": p["conv3x3_umma<64>"]["ms"] / 5, "resblock64": p["resblock64_umma"]["ms"] / 5, "conv128": p["conv3x3_umma<128>"]["ms"] / 5,
                   "conv_init": p["conv_init"]["ms"] / 5, "decoder": p["decoder"]["ms"] / 5,
                   "lanczos512": t(lambda: hb.lanczos_shift(sr[None], sh, p=5)), "cpsnr512": t(lambda: hb.shift_cPSNR_argmax(sr, hr, hm))}))
 ''' % ROOT
