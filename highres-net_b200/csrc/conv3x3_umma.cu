@@ -421,12 +421,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
 template <int CIN>
 int launch_impl(const ConvArgs& a, const CUtensorMap& map, const Geometry& g, int ctas, cudaStream_t stream) {
     using C = Cfg<CIN>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        HRN_CUDA_OK(cudaFuncSetAttribute(conv3x3_umma_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::SMEM_BYTES));
-        attr_set = true;
-    }
+    static bool attr_set[64] = {};
+    if (allow_dynamic_smem(conv3x3_umma_kernel<CIN>, C::SMEM_BYTES, attr_set)) return -1;
     HRN_CUDA_OK(launch_pdl(conv3x3_umma_kernel<CIN>, ctas, NUM_THREADS, C::SMEM_BYTES, stream, map, a, g));
     note_launches(1);
     return 0;

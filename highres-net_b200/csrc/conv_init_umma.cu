@@ -277,11 +277,8 @@ int conv_init_umma_launch(const float* lrs, const float* anchor, int B, int L, i
     a.bias = bias;
     a.prelu = prelu;
     a.out = out;
-    static bool attr_set = false;
-    if (!attr_set) {
-        HRN_CUDA_OK(cudaFuncSetAttribute(conv_init_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
-    }
+    static bool attr_set[64] = {};
+    if (allow_dynamic_smem(conv_init_umma_kernel, SMEM_BYTES, attr_set)) return -1;
     const int ctas = static_cast<int>(a.tiles < static_cast<uint32_t>(sm_count) ? a.tiles : sm_count);
     HRN_CUDA_OK(launch_pdl(conv_init_umma_kernel, ctas, NUM_THREADS, SMEM_BYTES, s, a));
     note_launches(1);

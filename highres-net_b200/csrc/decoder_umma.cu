@@ -206,11 +206,8 @@ int decoder_umma_launch(const __nv_bfloat16* in, int B, int image_stride, int H,
     a.out = out;
     CUtensorMap map;
     if (encode_nhwc_map(&map, in, 64, W, H, B, TILE_M, image_stride)) return -1;
-    static bool attr_set = false;
-    if (!attr_set) {
-        HRN_CUDA_OK(cudaFuncSetAttribute(decoder_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
-    }
+    static bool attr_set[64] = {};
+    if (allow_dynamic_smem(decoder_umma_kernel, SMEM_BYTES, attr_set)) return -1;
     const int ctas = static_cast<int>(a.tiles < sm_count ? a.tiles : sm_count);
     HRN_CUDA_OK(launch_pdl(decoder_umma_kernel, ctas, NUM_THREADS, SMEM_BYTES, s, map, a));
     note_launches(1);

@@ -421,11 +421,8 @@ int resblock64_launch(const ConvArgs& a1, const float* bias1_host, const uint8_t
     g.img_group = 1;
     CUtensorMap map;
     if (encode_nhwc_map(&map, a1.in, 64, a1.W, a1.H, a1.in_images, SLOT_PIX)) return -1;
-    static bool attr_set = false;
-    if (!attr_set) {
-        HRN_CUDA_OK(cudaFuncSetAttribute(resblock64_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
-    }
+    static bool attr_set[64] = {};
+    if (allow_dynamic_smem(resblock64_umma_kernel, SMEM_BYTES, attr_set)) return -1;
     HRN_CUDA_OK(launch_pdl(resblock64_umma_kernel, g.groups, NUM_THREADS, SMEM_BYTES, stream, map, r, g));
     note_launches(1);
     return 0;

@@ -489,11 +489,8 @@ int32_t hrn_shiftnet_forward(hrn_shiftnet* h, const float* x, int32_t N, int32_t
     CUtensorMap a_map, b_map;
     if (encode_matrix_map(&a_map, h->act[cur], N, FC_K)) return -1;
     if (encode_matrix_map(&b_map, h->fc1_w_dev, FC_N, FC_K)) return -1;
-    static bool attr_set = false;
-    if (!attr_set) {
-        HRN_CUDA_OK(cudaFuncSetAttribute(fc1_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_BYTES));
-        attr_set = true;
-    }
+    static bool attr_set[64] = {};
+    if (allow_dynamic_smem(fc1_umma_kernel, FC_SMEM_BYTES, attr_set)) return -1;
     fc1_umma_kernel<<<dim3(FC_N / FC_TILE, FC_SPLITS, m_tiles), FC_THREADS, FC_SMEM_BYTES, s>>>(a_map, b_map, h->partial, m_pad);
     fc_finish_kernel<<<N, FF_THREADS, 0, s>>>(h->partial, m_pad, h->fc1_b_dev, h->fc2_w_dev, theta);
     note_launches(2);

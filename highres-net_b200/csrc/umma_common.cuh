@@ -55,6 +55,23 @@ inline int encode_nhwc_map(CUtensorMap* map, const void* base, int channels, int
     return 0;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device setting: one flag per device and call site, so a process
+// that drives several GPUs (one handle per device) opts every one of them in.
+template <typename K>
+inline int allow_dynamic_smem(K kernel, int bytes, bool (&done)[64]) {
+    int dev = 0;
+    HRN_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) {
+        set_error("device index %d out of range", dev);
+        return -1;
+    }
+    if (!done[dev]) {
+        HRN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        done[dev] = true;
+    }
+    return 0;
+}
+
 // Launch with programmatic dependent launch enabled: the kernel's prologue (barrier init, TMEM allocation, weight
 // loads) overlaps the tail of the previous kernel in the stream; the kernel itself calls ptx::pdl_wait() before it
 // reads or writes any tensor the previous kernel may still be using.

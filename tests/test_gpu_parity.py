@@ -871,3 +871,34 @@ def test_shiftnet_weight_updates_and_error_paths(hb, dev):
         net(torch.zeros(1, 2, 64, 64, device=dev))                                # fc1 needs 128 x 128 crops
     with pytest.raises(ValueError):
         net(torch.zeros(1, 3, 128, 128, device=dev))
+
+
+# ---------------------------------------------------------------------------- several GPUs driven by ONE process
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two visible GPUs")
+def test_one_process_two_devices(hb):
+    """One handle per device: the same module / functions used on cuda:0 and cuda:1 from one process give identical
+    results (per-device kernel attributes, memory pools, handles and streams)."""
+    from oracle import shiftnet_oracle
+    d0, d1 = torch.device("cuda:0"), torch.device("cuda:1")
+    g = torch.Generator().manual_seed(77)
+    lrs, al = torch.rand(3, 4, 64, 64, generator=g), torch.ones(3, 4)
+    pairs = torch.from_numpy(shiftnet_oracle.make_pairs(5, 4))
+    sr_, hr_, hm_ = torch.rand(2, 96, 96, generator=g), torch.rand(2, 96, 96, generator=g), (torch.rand(2, 96, 96, generator=g) > 0.1).float()
+    outs = []
+    for dev in (d1, d0, d1):                       # cuda:1 first: nothing may rely on device 0 having been set up
+        net = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval()
+        net.load_state_dict(hrnet_oracle.make_params(cases.WEIGHT_SEED))
+        net = net.to(dev)
+        sn = hb.ShiftNet().eval()
+        sn.load_state_dict(shiftnet_oracle.make_params(0))
+        sn = sn.to(dev)
+        sr = net(lrs.to(dev), al.to(dev))
+        host = net.forward_host(lrs.pin_memory(), al.pin_memory(), device=dev)
+        theta = sn(pairs.to(dev))
+        moved = hb.lanczos_shift(sr_.to(dev)[None], torch.tensor([[0.3, -0.6], [1.0, 0.0]], device=dev), p=5)
+        best, xy, tab = hb.shift_cPSNR_argmax(sr_.to(dev), hr_.to(dev), hm_.to(dev))
+        assert sr.device == dev and theta.device == dev and tab.device == dev
+        outs.append([t.cpu() for t in (sr, host, theta, moved, tab, xy)])
+    for o in outs[1:]:
+        for a, b in zip(o, outs[0]):
+            assert torch.equal(a, b)
