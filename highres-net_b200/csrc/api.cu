@@ -212,7 +212,8 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
                   H, W);
         return -1;
     }
-    HRN_CUDA_OK(cudaSetDevice(h->device));
+    hrn::DeviceGuard on_device(h->device);
+    if (!on_device.ok) return -1;
     const size_t hw = static_cast<size_t>(H) * W;
     const size_t n_img = static_cast<size_t>(B) * L;
     const size_t act_bytes = n_img * hw * 64 * sizeof(__nv_bfloat16);
@@ -421,7 +422,8 @@ int32_t hrn_create(const hrn_config* cfg, int32_t device, hrn_handle** out) {
                   prop.minor);
         return -1;
     }
-    HRN_CUDA_OK(cudaSetDevice(device));
+    hrn::DeviceGuard on_device(device);
+    if (!on_device.ok) return -1;
     hrn_handle* h = new hrn_handle();
     h->cfg = c;
     h->device = device;
@@ -442,7 +444,7 @@ int32_t hrn_create(const hrn_config* cfg, int32_t device, hrn_handle** out) {
 
 void hrn_destroy(hrn_handle* h) {
     if (h == nullptr) return;
-    cudaSetDevice(h->device);
+    hrn::DeviceGuard on_device(h->device);
     auto rel = [](void* p) {
         if (p != nullptr) cudaFree(p);
     };
@@ -495,7 +497,8 @@ int32_t hrn_set_weight(hrn_handle* h, const char* key, const float* data, const 
         set_error("hrn_set_weight: null argument");
         return -1;
     }
-    HRN_CUDA_OK(cudaSetDevice(h->device));
+    hrn::DeviceGuard on_device(h->device);
+    if (!on_device.ok) return -1;
     const std::string k(key);
     int rc = -2;
     int r = 0, j = 0;
@@ -625,7 +628,8 @@ static int forward_host_impl(hrn_handle* h, const float* lrs_host, const uint16_
         set_error("hrn_forward_host: empty input");
         return -1;
     }
-    HRN_CUDA_OK(cudaSetDevice(h->device));
+    hrn::DeviceGuard on_device(h->device);
+    if (!on_device.ok) return -1;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t set_in = static_cast<size_t>(L) * H * W, set_out = static_cast<size_t>(9) * H * W;
     if (grow(reinterpret_cast<void**>(&h->io[0]), &h->io_cap[0], B * set_in * 4)) return -1;
@@ -707,7 +711,8 @@ int32_t hrn_forward_host_submit(hrn_handle* h, const float* lrs_host, const floa
         set_error("hrn_forward_host_submit: empty input");
         return -1;
     }
-    HRN_CUDA_OK(cudaSetDevice(h->device));
+    hrn::DeviceGuard on_device(h->device);
+    if (!on_device.ok) return -1;
     if (ensure_copy_streams(h)) return -1;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     hrn_handle::HostSlot& sl = h->slots[h->next_ticket & 1];
@@ -753,7 +758,8 @@ int32_t hrn_forward_host_wait(hrn_handle* h, int64_t ticket) {
     }
     hrn_handle::HostSlot& sl = h->slots[ticket & 1];
     if (sl.ticket != ticket) return 0;      // already retired by a later submit (or waited before): sr_host is complete
-    HRN_CUDA_OK(cudaSetDevice(h->device));
+    hrn::DeviceGuard on_device(h->device);
+    if (!on_device.ok) return -1;
     HRN_CUDA_OK(cudaEventSynchronize(sl.ev_out));
     sl.ticket = 0;
     return 0;
@@ -841,7 +847,8 @@ int32_t hrn_profile_end(hrn_handle* h, double* ms, double* flops, int64_t* launc
         return -1;
     }
     h->profiling = false;
-    HRN_CUDA_OK(cudaSetDevice(h->device));
+    hrn::DeviceGuard on_device(h->device);
+    if (!on_device.ok) return -1;
     HRN_CUDA_OK(cudaDeviceSynchronize());
     for (int c = 0; c < HRN_PROF_CLASSES; ++c) {
         ms[c] = 0.0;

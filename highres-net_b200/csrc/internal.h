@@ -21,6 +21,22 @@ void note_launches(int n);   // feeds hrn_kernel_launch_count()
         }                                                                                      \
     } while (0)
 
+// Entry points that take a handle run on the handle's device and leave the caller's current device as they found it.
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(device) == cudaSuccess;
+        if (!ok) set_error("cudaSetDevice(%d) failed", device);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 // ------------------------------------------------------------------ conv3x3 (tcgen05)
 // Residual / merge modes of the conv epilogue.
 enum ResMode : int {

@@ -355,7 +355,7 @@ int32_t hrn_shiftnet_create(int32_t device, hrn_shiftnet** out) {
 
 void hrn_shiftnet_destroy(hrn_shiftnet* h) {
     if (h == nullptr) return;
-    cudaSetDevice(h->device);
+    hrn::DeviceGuard on_device(h->device);
     auto rel = [](void* p) {
         if (p != nullptr) cudaFree(p);
     };
@@ -441,7 +441,8 @@ int32_t hrn_shiftnet_forward(hrn_shiftnet* h, const float* x, int32_t N, int32_t
                   "(ShiftNet.py:45, 67)", SN_SIZE, SN_SIZE, N, H, W);
         return -1;
     }
-    HRN_CUDA_OK(cudaSetDevice(h->device));
+    hrn::DeviceGuard on_device(h->device);
+    if (!on_device.ok) return -1;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (h->dirty) {
         HRN_CUDA_OK(cudaStreamSynchronize(s));       // the previous forward may still read the old weights

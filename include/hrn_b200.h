@@ -7,7 +7,9 @@
  * non-zero = error, message via hrn_last_error()), no exceptions across the ABI,
  * caller-owned buffers, handle-owned weights and workspace, all work enqueued on
  * the CUDA stream passed in (a cudaStream_t cast to void*; NULL = default stream).
- * One handle per device; a handle is not thread-safe.  There is NO CPU fallback:
+ * One handle per device; a handle is not thread-safe.  Functions that take a handle run on
+ * the handle's device and restore the caller's current device before they return; the
+ * handle-less scoring functions run on the current device.  There is NO CPU fallback:
  * every function fails with an error if no sm_100 device is usable.
  */
 #ifndef HRN_B200_H

@@ -902,3 +902,17 @@ def test_one_process_two_devices(hb):
     for o in outs[1:]:
         for a, b in zip(o, outs[0]):
             assert torch.equal(a, b)
+    # the C entry points run on the handle's device and restore the caller's current device
+    import ctypes
+    from highres_net_b200 import _lib
+    torch.cuda.set_device(0)
+    net = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval().to(d1)
+    handle = net._handle_for(d1)                                   # hrn_create + hrn_set_weight on device 1
+    assert torch.cuda.current_device() == 0
+    x1, a1 = lrs.to(d1), al.to(d1)
+    out1 = torch.empty(3, 1, 192, 192, device=d1)
+    torch.cuda.synchronize(d1)
+    _lib.check(_lib.load().hrn_forward(handle, x1.data_ptr(), a1.data_ptr(), 3, 4, 64, 64, out1.data_ptr(), None), "hrn_forward")
+    assert torch.cuda.current_device() == 0
+    torch.cuda.synchronize(d1)
+    assert torch.equal(out1.cpu(), net(x1, a1).cpu())
