@@ -78,6 +78,7 @@ struct hrn_handle {
     } slots[2];
     int64_t next_ticket = 1;
     int debug_flags = 0;
+    bool work_enqueued = false;        // a forward may still be running: hrn_set_weight drains the device before it overwrites weights
     // optional per-launch timing (hrn_profile_begin / hrn_profile_end)
     bool profiling = false;
     struct Span { cudaEvent_t e0, e1; int cls; double flops; };
@@ -214,6 +215,7 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
     }
     hrn::DeviceGuard on_device(h->device);
     if (!on_device.ok) return -1;
+    h->work_enqueued = true;
     const size_t hw = static_cast<size_t>(H) * W;
     const size_t n_img = static_cast<size_t>(B) * L;
     const size_t act_bytes = n_img * hw * 64 * sizeof(__nv_bfloat16);
@@ -499,6 +501,10 @@ int32_t hrn_set_weight(hrn_handle* h, const char* key, const float* data, const 
     }
     hrn::DeviceGuard on_device(h->device);
     if (!on_device.ok) return -1;
+    if (h->work_enqueued) {            // forwards are asynchronous and may run on non-blocking streams
+        HRN_CUDA_OK(cudaDeviceSynchronize());
+        h->work_enqueued = false;
+    }
     const std::string k(key);
     int rc = -2;
     int r = 0, j = 0;

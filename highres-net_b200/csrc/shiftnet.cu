@@ -445,7 +445,7 @@ int32_t hrn_shiftnet_forward(hrn_shiftnet* h, const float* x, int32_t N, int32_t
     if (!on_device.ok) return -1;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (h->dirty) {
-        HRN_CUDA_OK(cudaStreamSynchronize(s));       // the previous forward may still read the old weights
+        HRN_CUDA_OK(cudaDeviceSynchronize());        // a previous forward (on any stream) may still read the old weights
         if (fold_and_upload(h)) return -1;
     }
     if (ensure_workspace(h, N)) return -1;
