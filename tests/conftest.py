@@ -17,4 +17,4 @@ def golden():
     import numpy as np
 
     gdir = os.path.join(ROOT, "tests", "golden")
-    return {name: np.load(os.path.join(gdir, name + ".npz")) for name in ("hrnet_forward", "lanczos", "cpsnr", "predict", "loss", "apply_shifts", "evaluate", "shiftnet")}
+    return {name: np.load(os.path.join(gdir, name + ".npz")) for name in ("hrnet_forward", "lanczos", "cpsnr", "predict", "loss", "apply_shifts", "evaluate", "shiftnet", "trainstep")}

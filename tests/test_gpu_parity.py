@@ -916,3 +916,31 @@ def test_one_process_two_devices(hb):
     assert torch.cuda.current_device() == 0
     torch.cuda.synchronize(d1)
     assert torch.equal(out1.cpu(), net(x1, a1).cpu())
+
+
+# ---------------------------------------------------------------------------- the training-step forward, end to end
+def test_trainstep_forward_value_through_every_drop_in(hb, shiftnet, golden, dev):
+    """train.py:174-187 without autograd: fusion model -> register_batch on the 128 x 128 centre crops -> apply_shifts ->
+    -get_loss('cPSNR') with get_crop_mask -> + lambda * mean(shifts)^2, every piece being the B200 drop-in, against the
+    value the unmodified reference computes (oracle/make_golden_trainstep.py)."""
+    from oracle.make_golden_trainstep import inputs
+    g = golden["trainstep"]
+    lrs, alphas = inputs()
+    fusion = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval()
+    fusion.load_state_dict(hrnet_oracle.make_params(cases.WEIGHT_SEED))
+    fusion = fusion.to(dev)
+    hrs, hr_maps = torch.from_numpy(g["hr"]).to(dev), torch.from_numpy(g["hr_map"]).to(dev)
+    off, patch = int(g["offset"]), 64
+    torch_mask = hb.get_crop_mask(patch_size=patch, crop_size=int(g["crop"]))
+    srs = fusion(torch.from_numpy(lrs).to(dev), torch.from_numpy(alphas).to(dev))                       # train.py:174
+    assert np.abs(srs.cpu().numpy() - g["srs"]).max() <= SR_REGRESSION_GATE
+    shifts = hb.register_batch(shiftnet, srs[:, :, off:off + 128, off:off + 128].contiguous(),
+                               reference=hrs[:, off:off + 128, off:off + 128].reshape(-1, 1, 128, 128))   # :177-179
+    assert np.abs(shifts.cpu().numpy() - g["shifts"]).max() <= SHIFTNET_GATE
+    srs_shifted = hb.apply_shifts(shiftnet, srs, shifts, dev)[:, 0]                                      # :180
+    assert np.abs(srs_shifted.cpu().numpy() - g["srs_shifted"]).max() <= 5e-3
+    cropped_mask = torch_mask[0].to(dev) * hr_maps                                                       # :183
+    loss = -hb.get_loss(srs_shifted, hrs, cropped_mask, metric="cPSNR")                                  # :185
+    assert np.abs(loss.cpu().numpy() - g["loss"]).max() <= 0.05                                          # dB
+    total = loss.mean() + float(g["lam"]) * shifts.mean() ** 2                                           # :186-187
+    assert abs(float(total) - float(g["total"])) <= 0.05

@@ -231,3 +231,25 @@ def test_shiftnet_mirror_has_the_reference_state_dict(golden):
         net.eval()(torch.zeros(1, 2, 128, 128))                                   # CPU tensor: no fallback
     with pytest.raises(ValueError):
         shiftnet.ShiftNet(in_channel=2)
+
+
+def test_trainstep_forward_oracle_matches_reference_golden(golden):
+    """Forward value of the reference training step (train.py:174-187: HRNet -> register_batch on the centre crops ->
+    apply_shifts -> -cPSNR loss with the crop mask + lambda * mean(shift)^2), composed from the oracle pieces."""
+    from oracle import shiftnet_oracle
+    from oracle.make_golden_trainstep import inputs
+    g = golden["trainstep"]
+    lrs, alphas = inputs()
+    off = int(g["offset"])
+    srs = hrnet_oracle.hrnet_forward(hrnet_oracle.make_params(cases.WEIGHT_SEED), lrs, alphas).numpy()
+    assert np.abs(srs - g["srs"]).max() <= 2e-6
+    shifts = shiftnet_oracle.register_batch(shiftnet_oracle.make_params(0), srs[:, :, off:off + 128, off:off + 128],
+                                            g["hr"][:, off:off + 128, off:off + 128][:, None]).numpy()
+    assert np.abs(shifts - g["shifts"]).max() <= 1e-5
+    shifted = scoring_oracle.apply_shifts(srs, shifts)[:, 0]
+    assert np.abs(shifted - g["srs_shifted"]).max() <= 1e-5
+    mask = scoring_oracle.crop_mask(64, int(g["crop"]))[0] * g["hr_map"]
+    loss = -scoring_oracle.clear_loss(shifted, g["hr"], mask, "cPSNR")
+    assert np.abs(loss - g["loss"]).max() <= 1e-3
+    total = loss.mean() + float(g["lam"]) * shifts.mean() ** 2
+    assert abs(total - float(g["total"])) <= 1e-3
