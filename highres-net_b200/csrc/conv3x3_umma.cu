@@ -60,7 +60,7 @@ struct Cfg {
     static_assert(16 * RING + 16 * ACC_SLOTS + 8 + 8 <= 512, "barrier block overflows into the bias array");
 };
 
-template <int CIN>
+template <int CIN, bool POOL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a, const Geometry geo) {
     using C = Cfg<CIN>;
@@ -370,6 +370,12 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
             const int out_img = a.out_in_stack ? (s.m / a.half) * a.src_views + s.m % a.half : m_img;
             __nv_bfloat16* op = a.out + (static_cast<size_t>(out_img) * a.H * a.W + pix0) * a.cout + co0;
             const size_t r_step = static_cast<size_t>(a.W) * res_c, o_step = static_cast<size_t>(a.W) * a.cout;
+            // fused MaxPool2d(2): rows come in pairs (2k, 2k + 1) because every range starts on an even row; the pooled
+            // pixel (y / 2, x / 2) is written by the even-x lane of the odd row
+            __nv_bfloat16* pp = nullptr;
+            uint32_t prev[16];
+            if (POOL)
+                pp = a.out + ((static_cast<size_t>(out_img) * (a.H / 2) + s.y0 / 2) * (a.W / 2) + x / 2) * a.cout + co0;
             for (int i = 0; i < s.rows; ++i, ++tile, rp += r_step, op += o_step) {
                 const uint32_t acc = tile % ACC_SLOTS, aph = (tile / ACC_SLOTS) & 1;
                 uint32_t rv[2][8];
@@ -403,7 +409,27 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
                     if (use_res) y = __hfma2(scale2, y, *reinterpret_cast<const __nv_bfloat162*>(&rv[e >> 3][e & 7]));
                     o[e >> 3][e & 7] = *reinterpret_cast<const uint32_t*>(&y);
                 }
-                if (valid && !(a.debug_flags & 2)) {
+                if (POOL) {
+                    if (((s.y0 + i) & 1) == 0) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) prev[e] = o[e >> 3][e & 7];
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            __nv_bfloat162 m = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&prev[e]),
+                                                       *reinterpret_cast<const __nv_bfloat162*>(&o[e >> 3][e & 7]));
+                            uint32_t mu = *reinterpret_cast<const uint32_t*>(&m);
+                            const uint32_t nu = __shfl_xor_sync(0xffffffffu, mu, 1);       // pixel x ^ 1 of the same rows
+                            m = __hmax2(m, *reinterpret_cast<const __nv_bfloat162*>(&nu));
+                            o[e >> 3][e & 7] = *reinterpret_cast<const uint32_t*>(&m);
+                        }
+                        if (valid && (x & 1) == 0) {
+                            ptx::stg_v8(pp, o[0]);
+                            ptx::stg_v8(pp + 16, o[1]);
+                        }
+                        pp += static_cast<size_t>(a.W / 2) * a.cout;
+                    }
+                } else if (valid && !(a.debug_flags & 2)) {
                     ptx::stg_v8(op, o[0]);
                     ptx::stg_v8(op + 16, o[1]);
                 }
@@ -418,12 +444,12 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
 }
 
 // ---------------------------------------------------------------- host side
-template <int CIN>
+template <int CIN, bool POOL>
 int launch_impl(const ConvArgs& a, const CUtensorMap& map, const Geometry& g, int ctas, cudaStream_t stream) {
     using C = Cfg<CIN>;
     static bool attr_set[64] = {};
-    if (allow_dynamic_smem(conv3x3_umma_kernel<CIN>, C::SMEM_BYTES, attr_set)) return -1;
-    HRN_CUDA_OK(launch_pdl(conv3x3_umma_kernel<CIN>, ctas, NUM_THREADS, C::SMEM_BYTES, stream, map, a, g));
+    if (allow_dynamic_smem(conv3x3_umma_kernel<CIN, POOL>, C::SMEM_BYTES, attr_set)) return -1;
+    HRN_CUDA_OK(launch_pdl(conv3x3_umma_kernel<CIN, POOL>, ctas, NUM_THREADS, C::SMEM_BYTES, stream, map, a, g));
     note_launches(1);
     return 0;
 }
@@ -463,7 +489,12 @@ int conv3x3_launch(const ConvArgs& a, int sm_count, cudaStream_t stream) {
         set_error("conv3x3: empty problem");
         return -1;
     }
+    if (a.pool && ((a.H | a.W) & 1 || a.live_list != nullptr || a.pair_mode || a.res_mode != RES_NONE || a.out_in_stack)) {
+        set_error("conv3x3: the fused max pool needs even H and W and a plain layer (no list, pair gather, residual, in-stack output)");
+        return -1;
+    }
     Geometry g;
+    g.even_rows = a.pool ? 1 : 0;
     g.n_parts = a.cout / NT;
     g.x_tiles = (a.W + TILE_M - 1) / TILE_M;
     // Narrow images (W + 2 <= 64): an M tile of 128 pixels would be mostly empty, so G = 128 / (W + 2) images share one
@@ -484,7 +515,8 @@ int conv3x3_launch(const ConvArgs& a, int sm_count, cudaStream_t stream) {
 
     CUtensorMap map;
     if (encode_nhwc_map(&map, a.in, a.in_c, a.W, a.H, a.in_images, g.img_group > 1 ? a.W + 2 : SLOT_PIX, 1, g.img_group)) return -1;
-    return a.cin == 64 ? launch_impl<64>(a, map, g, ctas, stream) : launch_impl<128>(a, map, g, ctas, stream);
+    if (a.pool) return a.cin == 64 ? launch_impl<64, true>(a, map, g, ctas, stream) : launch_impl<128, true>(a, map, g, ctas, stream);
+    return a.cin == 64 ? launch_impl<64, false>(a, map, g, ctas, stream) : launch_impl<128, false>(a, map, g, ctas, stream);
 }
 
 }  // namespace hrn

@@ -419,6 +419,7 @@ int resblock64_launch(const ConvArgs& a1, const float* bias1_host, const uint8_t
     g.groups = static_cast<int>(std::min<long long>(ctas, g.total_rows));
     g.split = a1.strip_split > 0 ? a1.strip_split : 1;
     g.img_group = 1;
+    g.even_rows = 0;
     CUtensorMap map;
     if (encode_nhwc_map(&map, a1.in, 64, a1.W, a1.H, a1.in_images, SLOT_PIX)) return -1;
     static bool attr_set[64] = {};

@@ -240,6 +240,7 @@ struct hrn_shiftnet {
     bool dirty = true;                                   // host weights changed since the last fold / upload
     bool fc1_dirty = true;                               // fc1.weight (134 MB on the host) is dropped once it is uploaded
     int no_img_group = 0;                                // test knob: one image row per conv tile even for narrow images
+    int no_fused_pool = 0;                               // test knob: MaxPool2d(2) as its own launch instead of the conv epilogue
     __nv_bfloat16* fc1_w_dev = nullptr;                  // [1024][32768] bf16, columns in NHWC flatten order
     float *fc1_b_dev = nullptr, *fc2_w_dev = nullptr;
     // workspace
@@ -423,6 +424,10 @@ int32_t hrn_shiftnet_debug_set(hrn_shiftnet* h, const char* knob, int32_t value)
         h->no_img_group = value == 0;
         return 0;
     }
+    if (h != nullptr && knob != nullptr && strcmp(knob, "fused_pool") == 0) {
+        h->no_fused_pool = value == 0;
+        return 0;
+    }
     set_error("hrn_shiftnet_debug_set: unknown knob");
     return -1;
 }
@@ -473,9 +478,12 @@ int32_t hrn_shiftnet_forward(hrn_shiftnet* h, const float* x, int32_t N, int32_t
         a.out = h->act[cur ^ 1];
         a.res_mode = RES_NONE;
         a.no_img_group = h->no_img_group;
+        a.pool = (SN_POOL[l] && !h->no_fused_pool) ? 1 : 0;
         if (conv3x3_launch(a, h->sm_count, s)) return -1;
         cur ^= 1;
-        if (SN_POOL[l]) {
+        if (a.pool) {
+            size /= 2;
+        } else if (SN_POOL[l]) {
             const size_t work = static_cast<size_t>(N) * (size / 2) * (size / 2) * (SN_COUT[l] / 8);
             const size_t blocks = (work + 255) / 256;
             maxpool2_nhwc_kernel<<<static_cast<unsigned>(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, s>>>(h->act[cur], N, size, size, SN_COUT[l],

@@ -189,7 +189,8 @@ int32_t hrn_shiftnet_set_weight(hrn_shiftnet* h, const char* state_dict_key, con
 int32_t hrn_shiftnet_missing_weights(hrn_shiftnet* h);
 int32_t hrn_shiftnet_forward(hrn_shiftnet* h, const float* x, int32_t N, int32_t H, int32_t W, float* theta, void* stream);
 /* Test knob: "img_group" = 0 makes the conv layers on narrow feature maps (32 x 32, 16 x 16) use one image row per MMA
- * tile instead of several images side by side (default 1); thetas must be bit-identical either way. */
+ * tile instead of several images side by side (default 1); "fused_pool" = 0 runs MaxPool2d(2) as its own launch instead of
+ * inside the conv epilogue (default 1); thetas must be bit-identical either way. */
 int32_t hrn_shiftnet_debug_set(hrn_shiftnet* h, const char* knob, int32_t value);
 
 #ifdef __cplusplus

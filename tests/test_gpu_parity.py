@@ -838,6 +838,16 @@ def test_shiftnet_forward_matches_reference_golden(shiftnet, golden, dev):
         plain = shiftnet(big[:n])
         shiftnet.debug_set(dev, "img_group", 1)
         assert torch.equal(plain, t_big[:n]), n
+    # MaxPool2d(2) inside the conv epilogue (row pairs + a lane shuffle) against the stand-alone pooling launch
+    for n in (150, 5, 1):
+        for grouped in (1, 0):
+            shiftnet.debug_set(dev, "img_group", grouped)
+            shiftnet.debug_set(dev, "fused_pool", 0)
+            unfused = shiftnet(big[:n])
+            shiftnet.debug_set(dev, "fused_pool", 1)
+            assert torch.equal(unfused, shiftnet(big[:n])), (n, grouped)
+            assert torch.equal(unfused, t_big[:n]), (n, grouped)
+    shiftnet.debug_set(dev, "img_group", 1)
     assert torch.equal(shiftnet(big[140:145]), t_big[140:145])
     assert torch.equal(shiftnet(big[:1]), t_big[:1])
 

@@ -16,8 +16,9 @@ print(json.dumps({"pairs": 16, "theta_max_abs": float(np.abs(ref).max()), "max_a
                   "spread_between_pairs": float((ref - ref.mean(0)).std())}), flush=True)
 FLOP_PER_PAIR = 2 * (18 * 64 * 16384 + 576 * 64 * 16384 + 2 * 576 * 64 * 4096 + 576 * 128 * 1024 + 1152 * 128 * 1024
                      + 2 * 1152 * 128 * 256 + 32768 * 1024 + 2048)
-for n, grouped in ((32, 1), (128, 1), (512, 1), (512, 0)):
+for n, grouped, pool in ((32, 1, 1), (128, 1, 1), (512, 1, 1), (512, 1, 0), (512, 0, 0)):
     net.debug_set(dev, "img_group", grouped)
+    net.debug_set(dev, "fused_pool", pool)
     xs = torch.rand(n, 2, 128, 128, device=dev)
     t0 = time.time()
     while time.time() - t0 < 1.0:
@@ -30,5 +31,5 @@ for n, grouped in ((32, 1), (128, 1), (512, 1), (512, 0)):
         for _ in range(10): net(xs)
         e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) / 10)
-    print(json.dumps({"pairs": n, "img_group": grouped, "ms": round(best, 4), "pairs_per_s": round(n / best * 1e3, 1),
+    print(json.dumps({"pairs": n, "img_group": grouped, "fused_pool": pool, "ms": round(best, 4), "pairs_per_s": round(n / best * 1e3, 1),
                       "model_tflops": round(FLOP_PER_PAIR * n / best / 1e9, 1)}), flush=True)
