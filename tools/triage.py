@@ -14,4 +14,4 @@ for flags in [int(x) for x in (sys.argv[1:] or ["0", "1", "2", "3", "4", "8", "1
     net.profile_begin(dev)
     for _ in range(4): net(lrs, al)
     p = net.profile_end(dev)
-    print(f"flags={flags:2d} conv64 {p['conv3x3_umma<64>']['ms']/4:.3f} ms  conv128 {p['conv3x3_umma<128>']['ms']/4:.3f} ms", flush=True)
+    print(f"flags={flags:2d} conv64 {(p['conv3x3_umma<64>']['ms'] + p['resblock64_umma']['ms'])/4:.3f} ms  conv128 {p['conv3x3_umma<128>']['ms']/4:.3f} ms", flush=True)
