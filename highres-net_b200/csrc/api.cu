@@ -64,6 +64,7 @@ struct hrn_handle {
     size_t io_u16_cap = 0;
     int max_ctas = 0;                  // 0 = one CTA per SM (test knob)
     int strip_split = 0;               // ranges of the row space per CTA (0/1 = one contiguous range)
+    int mcast = 1;                     // 128 -> 128 convs as cluster pairs with multicast A rows (0: plain launch, test knob)
     int fuse_resblock = 1;             // encoder ResidualBlocks as one launch each (resblock64_umma.cu) when W <= 128
     int host_chunks = 0;               // hrn_forward_host pipeline depth (0 = automatic)
     long long workspace_mb = 65536;    // cap on the activation workspace; larger batches are run in slices
@@ -191,6 +192,7 @@ int run_conv(hrn_handle* h, const hrn::ConvLayer& l, hrn::ConvArgs a, cudaStream
     a.max_ctas = h->max_ctas;
     a.strip_split = h->strip_split;
     a.debug_flags = h->debug_flags;
+    a.mcast = h->mcast;
     return hrn::conv3x3_launch(a, h->sm_count, s);
 }
 
@@ -886,6 +888,7 @@ int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value) {
     else if (strcmp(knob, "skip_dead_views") == 0) h->skip_dead = value != 0;
     else if (strcmp(knob, "strip_split") == 0) h->strip_split = value;
     else if (strcmp(knob, "fuse_resblock") == 0) h->fuse_resblock = value != 0;
+    else if (strcmp(knob, "mcast") == 0) h->mcast = value != 0;
     else {
         set_error("hrn_debug_set: unknown knob '%s'", knob);
         return -1;

@@ -60,7 +60,11 @@ struct Cfg {
     static_assert(16 * RING + 16 * ACC_SLOTS + 8 + 8 <= 512, "barrier block overflows into the bias array");
 };
 
-template <int CIN, bool POOL>
+// MCAST (128 -> 128 layers): the two CTAs that compute the two 64-channel output halves of the same rows form a cluster;
+// each loads one of the two K chunks of every input row and multicasts it to both, so every A row crosses L2 -> SM once
+// instead of twice.  A slot may be overwritten only when BOTH CTAs have consumed it: the MMA threads multicast their
+// "slot free" commits to both CTAs and the empty barriers count two arrivals.
+template <int CIN, bool POOL, bool MCAST>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a, const Geometry geo) {
     using C = Cfg<CIN>;
@@ -87,7 +91,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::RING; ++i) {
             ptx::mbar_init(bar_full + 8 * i, 1);
-            ptx::mbar_init(bar_empty + 8 * i, 1);
+            ptx::mbar_init(bar_empty + 8 * i, MCAST ? 2 : 1);
         }
         for (int i = 0; i < ACC_SLOTS; ++i) {
             ptx::mbar_init(bar_tfull + 8 * i, 1);
@@ -103,6 +107,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
+    if (MCAST) ptx::cluster_sync();          // the peer's barriers exist before anything is multicast into this CTA
     const uint32_t tmem_base = *tmem_slot_gen;
 
     if (warp == 0) {
@@ -142,8 +147,12 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
                             ptx::mbar_arrive(bar_full + 8 * slot);
                         } else {
                             ptx::mbar_expect_tx(bar_full + 8 * slot, chunk_tx);
-                            ptx::tma_load_4d(ring_s + slot * CHUNK_BYTES, &in_map, ch[c], s.xt * TILE_M - 1,
-                                             s.y0 - 1 + q, img[c], bar_full + 8 * slot);
+                            if (!MCAST)
+                                ptx::tma_load_4d(ring_s + slot * CHUNK_BYTES, &in_map, ch[c], s.xt * TILE_M - 1,
+                                                 s.y0 - 1 + q, img[c], bar_full + 8 * slot);
+                            else if (c == part)          // chunk c is fetched by cluster rank c for both CTAs
+                                ptx::tma_load_4d_mcast(ring_s + slot * CHUNK_BYTES, &in_map, ch[c], s.xt * TILE_M - 1,
+                                                       s.y0 - 1 + q, img[c], bar_full + 8 * slot, 0x3);
                         }
                     }
                 }
@@ -238,7 +247,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
                                     if (step == 7) early();
                                 }
                             }
-                            ptx::umma_commit(bar_empty + 8 * slot);
+                            if (MCAST) ptx::umma_commit_mcast(bar_empty + 8 * slot, 0x3); else ptx::umma_commit(bar_empty + 8 * slot);
                             if (c == C::CHUNKS - 1) ptx::umma_commit(bar_tfull + 8 * sl);
                         }
                         continue;
@@ -309,7 +318,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
                                 }
                             }
                         }
-                        ptx::umma_commit(bar_empty + 8 * slot);                 // this (row, chunk) buffer is consumed
+                        if (MCAST) ptx::umma_commit_mcast(bar_empty + 8 * slot, 0x3); else ptx::umma_commit(bar_empty + 8 * slot);                 // this (row, chunk) buffer is consumed
                         if (c == C::CHUNKS - 1 && ky_hi == 2)                   // output row q-2 has all 9 taps
                             ptx::umma_commit(bar_tfull + 8 * ((tile0 + q - 2) % ACC_SLOTS));
                     }
@@ -440,16 +449,17 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap in_map, const ConvArgs a
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
+    if (MCAST) ptx::cluster_sync();          // no CTA leaves while its peer may still multicast into it
     if (warp == 2) ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 // ---------------------------------------------------------------- host side
-template <int CIN, bool POOL>
+template <int CIN, bool POOL, bool MCAST = false>
 int launch_impl(const ConvArgs& a, const CUtensorMap& map, const Geometry& g, int ctas, cudaStream_t stream) {
     using C = Cfg<CIN>;
     static bool attr_set[64] = {};
-    if (allow_dynamic_smem(conv3x3_umma_kernel<CIN, POOL>, C::SMEM_BYTES, attr_set)) return -1;
-    HRN_CUDA_OK(launch_pdl(conv3x3_umma_kernel<CIN, POOL>, ctas, NUM_THREADS, C::SMEM_BYTES, stream, map, a, g));
+    if (allow_dynamic_smem(conv3x3_umma_kernel<CIN, POOL, MCAST>, C::SMEM_BYTES, attr_set)) return -1;
+    HRN_CUDA_OK(launch_pdl(conv3x3_umma_kernel<CIN, POOL, MCAST>, ctas, NUM_THREADS, C::SMEM_BYTES, stream, MCAST ? 2 : 1, map, a, g));
     note_launches(1);
     return 0;
 }
@@ -516,6 +526,8 @@ int conv3x3_launch(const ConvArgs& a, int sm_count, cudaStream_t stream) {
     CUtensorMap map;
     if (encode_nhwc_map(&map, a.in, a.in_c, a.W, a.H, a.in_images, g.img_group > 1 ? a.W + 2 : SLOT_PIX, 1, g.img_group)) return -1;
     if (a.pool) return a.cin == 64 ? launch_impl<64, true>(a, map, g, ctas, stream) : launch_impl<128, true>(a, map, g, ctas, stream);
+    // 128 -> 128: cluster pairs with multicast A rows (knob: ConvArgs::mcast, set by the handle)
+    if (a.cin == 128 && a.cout == 128 && a.mcast && !(a.debug_flags & 4)) return launch_impl<128, false, true>(a, map, g, ctas, stream);
     return a.cin == 64 ? launch_impl<64, false>(a, map, g, ctas, stream) : launch_impl<128, false>(a, map, g, ctas, stream);
 }
 

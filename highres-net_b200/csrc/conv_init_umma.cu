@@ -280,7 +280,7 @@ int conv_init_umma_launch(const float* lrs, const float* anchor, int B, int L, i
     static bool attr_set[64] = {};
     if (allow_dynamic_smem(conv_init_umma_kernel, SMEM_BYTES, attr_set)) return -1;
     const int ctas = static_cast<int>(a.tiles < static_cast<uint32_t>(sm_count) ? a.tiles : sm_count);
-    HRN_CUDA_OK(launch_pdl(conv_init_umma_kernel, ctas, NUM_THREADS, SMEM_BYTES, s, a));
+    HRN_CUDA_OK(launch_pdl(conv_init_umma_kernel, ctas, NUM_THREADS, SMEM_BYTES, s, 1, a));
     note_launches(1);
     return 0;
 }

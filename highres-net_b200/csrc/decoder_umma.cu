@@ -209,7 +209,7 @@ int decoder_umma_launch(const __nv_bfloat16* in, int B, int image_stride, int H,
     static bool attr_set[64] = {};
     if (allow_dynamic_smem(decoder_umma_kernel, SMEM_BYTES, attr_set)) return -1;
     const int ctas = static_cast<int>(a.tiles < sm_count ? a.tiles : sm_count);
-    HRN_CUDA_OK(launch_pdl(decoder_umma_kernel, ctas, NUM_THREADS, SMEM_BYTES, s, map, a));
+    HRN_CUDA_OK(launch_pdl(decoder_umma_kernel, ctas, NUM_THREADS, SMEM_BYTES, s, 1, map, a));
     note_launches(1);
     return 0;
 }

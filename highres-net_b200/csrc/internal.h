@@ -76,6 +76,7 @@ struct ConvArgs {
     // of 0 .. n_img; both device pointers, nullptr = dense
     const int* live_list;
     const int* live_count;
+    int mcast;                // 1: 128 -> 128 layers run as cluster pairs that multicast the A rows (see conv3x3_umma.cu)
     int pool;                 // 1: MaxPool2d(2) fused into the epilogue; `out` is (n_img, H / 2, W / 2, cout).  Plain layers only.
     int no_img_group;         // test knob: 1 = never put several narrow images into one M tile (see conv3x3_launch)
 };

@@ -424,7 +424,7 @@ int resblock64_launch(const ConvArgs& a1, const float* bias1_host, const uint8_t
     if (encode_nhwc_map(&map, a1.in, 64, a1.W, a1.H, a1.in_images, SLOT_PIX)) return -1;
     static bool attr_set[64] = {};
     if (allow_dynamic_smem(resblock64_umma_kernel, SMEM_BYTES, attr_set)) return -1;
-    HRN_CUDA_OK(launch_pdl(resblock64_umma_kernel, g.groups, NUM_THREADS, SMEM_BYTES, stream, map, r, g));
+    HRN_CUDA_OK(launch_pdl(resblock64_umma_kernel, g.groups, NUM_THREADS, SMEM_BYTES, stream, 1, map, r, g));
     note_launches(1);
     return 0;
 }

@@ -76,17 +76,24 @@ inline int allow_dynamic_smem(K kernel, int bytes, bool (&done)[64]) {
 // loads) overlaps the tail of the previous kernel in the stream; the kernel itself calls ptx::pdl_wait() before it
 // reads or writes any tensor the previous kernel may still be using.
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args&&... args) {
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, int cluster, Args&&... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(block);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (cluster > 1) {                      // thread-block clusters of `cluster` consecutive CTAs
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = cluster;
+        attr[1].val.clusterDim.y = 1;
+        attr[1].val.clusterDim.z = 1;
+        cfg.numAttrs = 2;
+    }
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 

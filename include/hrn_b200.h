@@ -149,7 +149,9 @@ int32_t hrn_forward_dump(hrn_handle* h, const float* lrs, const float* alphas, i
  * hrn_forward_host (0 = automatic, 1 = no overlap).  "workspace_mb" caps the activation workspace (default 65536 MB);
  * batches that need more are run as consecutive slices with identical results.  "skip_dead_views" = 0 makes the forward
  * compute every view and pair even when alpha = 0 padding keeps it from reaching the output (default 1: skipped; the
- * super-resolved image is bit-identical either way).  "debug_flags" disables parts of the conv kernel for
+ * super-resolved image is bit-identical either way).  "mcast" = 0 launches the 128 -> 128 convolutions of the fusion stage
+ * as independent CTAs instead of cluster pairs that multicast their input rows, "fuse_resblock" = 0 runs an encoder
+ * ResidualBlock as two launches instead of one (defaults 1; bit-identical either way).  "debug_flags" disables parts of the conv kernel for
  * performance triage (results are then garbage). */
 int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value);
 /* Process-wide test knobs of the scoring entry points (they take no handle).  "cpsnr_generic" = 1 makes hrn_shift_cpsnr use

@@ -321,6 +321,29 @@ def test_fused_resblock_is_bit_identical_to_two_launches(hb, dev, b, l, s):
     assert np.abs(outs[0].cpu().numpy() - ref).max() <= SR_GATE
 
 
+@pytest.mark.parametrize("b,l,s", [(1, 2, 8), (2, 3, 33), (2, 4, 128), (1, 5, 100), (3, 2, 1), (1, 16, 64), (2, 8, 256)])
+def test_multicast_cluster_pairs_are_bit_identical(hb, dev, b, l, s):
+    """The 128 -> 128 convs of the fusion stage run as clusters of two CTAs (the two 64-channel output halves of the same
+    rows) that each fetch one K chunk of every input row and multicast it to both; the plain launch ("mcast" = 0) must
+    give the same image bit for bit, for any CTA count and with dead views skipped through the live-work lists."""
+    model = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval()
+    model.load_state_dict(hrnet_oracle.make_params(cases.WEIGHT_SEED))
+    model = model.to(dev)
+    g = torch.Generator().manual_seed(2000 + 10 * s + l)
+    lrs = torch.rand(b, l, s, s, generator=g).to(dev)
+    al = (torch.rand(b, l, generator=g) > 0.25).float()
+    al[:, 0] = 1.0
+    al = al.to(dev)
+    outs = []
+    for mc in (1, 0):
+        for ctas in (0, 6, 37):
+            model.debug_set(dev, "mcast", mc)
+            model.debug_set(dev, "max_ctas", ctas)
+            outs.append(model(lrs, al).clone())
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+
+
 def test_forward_host_equals_device_path(net, dev):
     lrs, alphas = cases.hrnet_inputs("b2_l4_s32")
     a = net(torch.from_numpy(lrs).to(dev), torch.from_numpy(alphas).to(dev)).cpu()
