@@ -46,7 +46,8 @@ def synthetic_batch(b, l, s, seed, device=None, pin=False):
 
 
 def _ncu_tag(kernel_class):
-    return kernel_class.replace("conv3x3_umma", "conv3x3_umma_kernel").replace("resblock64_umma", "resblock64_umma_kernel")
+    # conv3x3_umma<128> -> "conv3x3_umma_kernel<128" (the kernel has further template arguments: <CIN, POOL, MCAST>)
+    return kernel_class.replace("conv3x3_umma", "conv3x3_umma_kernel").replace("resblock64_umma", "resblock64_umma_kernel").rstrip(">")
 
 
 def ncu_traffic_per_launch(kernel_class):
