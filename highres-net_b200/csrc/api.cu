@@ -888,7 +888,7 @@ int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value) {
     else if (strcmp(knob, "skip_dead_views") == 0) h->skip_dead = value != 0;
     else if (strcmp(knob, "strip_split") == 0) h->strip_split = value;
     else if (strcmp(knob, "fuse_resblock") == 0) h->fuse_resblock = value != 0;
-    else if (strcmp(knob, "mcast") == 0) h->mcast = value != 0;
+    else if (strcmp(knob, "mcast") == 0) h->mcast = value;        // 0 = plain, 1 = cluster pairs if they fit, 2 = required
     else {
         set_error("hrn_debug_set: unknown knob '%s'", knob);
         return -1;

@@ -466,6 +466,36 @@ int launch_impl(const ConvArgs& a, const CUtensorMap& map, const Geometry& g, in
 
 }  // namespace
 
+// How many two-CTA clusters of the multicast kernel can be resident on this device (queried once per device).
+static bool cluster_pairs_fit(int pairs) {
+    static int max_pairs[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    if (max_pairs[dev] == 0) {
+        using C = Cfg<128>;
+        static bool attr_set[64] = {};
+        if (allow_dynamic_smem(conv3x3_umma_kernel<128, false, true>, C::SMEM_BYTES, attr_set)) return false;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * 148);
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = C::SMEM_BYTES;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, conv3x3_umma_kernel<128, false, true>, &cfg) != cudaSuccess) {
+            cudaGetLastError();
+            n = -1;
+        }
+        max_pairs[dev] = n > 0 ? n : -1;
+    }
+    return max_pairs[dev] >= pairs;
+}
+
 int conv3x3_bytes_per_weight_image(int cin, int cout) { return 9 * cin * cout * 2; }
 
 // OIHW fp32 -> per 64-channel output part: [kx][chunk][block = 2 - ky][n = 64 co][k = 64 ci] bf16, each
@@ -526,8 +556,16 @@ int conv3x3_launch(const ConvArgs& a, int sm_count, cudaStream_t stream) {
     CUtensorMap map;
     if (encode_nhwc_map(&map, a.in, a.in_c, a.W, a.H, a.in_images, g.img_group > 1 ? a.W + 2 : SLOT_PIX, 1, g.img_group)) return -1;
     if (a.pool) return a.cin == 64 ? launch_impl<64, true>(a, map, g, ctas, stream) : launch_impl<128, true>(a, map, g, ctas, stream);
-    // 128 -> 128: cluster pairs with multicast A rows (knob: ConvArgs::mcast, set by the handle)
-    if (a.cin == 128 && a.cout == 128 && a.mcast && !(a.debug_flags & 4)) return launch_impl<128, false, true>(a, map, g, ctas, stream);
+    // 128 -> 128: cluster pairs with multicast A rows (knob: ConvArgs::mcast, set by the handle) -- provided every pair
+    // can be resident at once (one CTA per SM, a pair per TPC); otherwise a second wave would cost far more than the
+    // multicast saves, and the plain launch is used.
+    if (a.cin == 128 && a.cout == 128 && a.mcast && !(a.debug_flags & 4)) {
+        if (cluster_pairs_fit(ctas / 2)) return launch_impl<128, false, true>(a, map, g, ctas, stream);
+        if (a.mcast == 2) {              // test knob: the cluster path is REQUIRED
+            set_error("conv3x3: %d cluster pairs cannot be resident at once on this device", ctas / 2);
+            return -1;
+        }
+    }
     return a.cin == 64 ? launch_impl<64, false>(a, map, g, ctas, stream) : launch_impl<128, false>(a, map, g, ctas, stream);
 }
 

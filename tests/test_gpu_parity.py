@@ -342,6 +342,9 @@ def test_multicast_cluster_pairs_are_bit_identical(hb, dev, b, l, s):
             outs.append(model(lrs, al).clone())
     for o in outs[1:]:
         assert torch.equal(o, outs[0])
+    model.debug_set(dev, "max_ctas", 0)
+    model.debug_set(dev, "mcast", 2)            # "required": errors out if the cluster path were silently skipped on this GPU
+    assert torch.equal(model(lrs, al), outs[0])
 
 
 def test_forward_host_equals_device_path(net, dev):
