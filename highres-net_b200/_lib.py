@@ -30,6 +30,7 @@ SYMBOLS = {
     "hrn_set_weight": (c_int32, [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int32]),
     "hrn_missing_weights": (c_int32, [c_void_p]),
     "hrn_forward": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "hrn_reserve": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32]),
     "hrn_forward_host": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                    c_void_p]),
     "hrn_forward_host_u16": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,

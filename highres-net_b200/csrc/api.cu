@@ -81,7 +81,10 @@ struct hrn_handle {
     int debug_flags = 0;
     bool work_enqueued = false;        // a forward may still be running: hrn_set_weight drains the device before it overwrites weights
     // optional per-launch timing (hrn_profile_begin / hrn_profile_end)
-    bool profiling = false;
+    bool profiling = false, prof_error = false;
+    cudaEvent_t ev_fwd_done = nullptr;  // recorded after the last kernel of every forward (the workspace is shared)
+    cudaStream_t last_stream = nullptr;
+    bool have_last = false;
     struct Span { cudaEvent_t e0, e1; int cls; double flops; };
     std::vector<Span> spans;
 };
@@ -159,6 +162,28 @@ int maybe_dump(Dump* d, int stage, const __nv_bfloat16* t, int n, int H, int W, 
     return hrn::nhwc_bf16_to_nchw_f32_launch(t, n, H, W, C, group, stride, d->dst, s);
 }
 
+// Sizes the handle-owned workspace (five bf16 NHWC activation buffers, the anchor plane, the live-work lists) for a
+// (B, L, H, W) forward.  Growing frees and reallocates, which synchronises the device: callers that must never stall
+// mid-stream size the workspace up front with hrn_reserve().
+int ensure_workspace(hrn_handle* h, int B, int L, int H, int W) {
+    const size_t hw = static_cast<size_t>(H) * W;
+    const size_t n_img = static_cast<size_t>(B) * L;
+    const size_t act_bytes = n_img * hw * 64 * sizeof(__nv_bfloat16);
+    if (act_bytes > h->act_cap) {
+        for (int i = 0; i < 5; ++i) {
+            if (h->act[i] != nullptr) HRN_CUDA_OK(cudaFree(h->act[i]));
+            h->act[i] = nullptr;
+        }
+        h->act_cap = 0;
+        for (int i = 0; i < 5; ++i) HRN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->act[i]), act_bytes));
+        h->act_cap = act_bytes;
+    }
+    if (grow(reinterpret_cast<void**>(&h->anchor), &h->anchor_cap, static_cast<size_t>(B) * hw * sizeof(float))) return -1;
+    if (grow(reinterpret_cast<void**>(&h->lists), &h->lists_cap, hrn::live_lists_ints(B, L) * sizeof(int))) return -1;
+    if (grow(reinterpret_cast<void**>(&h->live_scratch), &h->live_scratch_cap, hrn::live_scratch_bytes(B, L))) return -1;
+    return 0;
+}
+
 // Brackets one kernel launch with CUDA events on its own stream when profiling is on.
 struct SpanGuard {
     hrn_handle* h;
@@ -169,13 +194,24 @@ struct SpanGuard {
         if (!on) return;
         sp.cls = cls;
         sp.flops = flops;
-        cudaEventCreate(&sp.e0);
-        cudaEventCreate(&sp.e1);
-        cudaEventRecord(sp.e0, s);
+        sp.e0 = sp.e1 = nullptr;
+        // a failed event call must not pass silently: hrn_profile_end reports it instead of returning bogus times
+        if (cudaEventCreate(&sp.e0) != cudaSuccess || cudaEventCreate(&sp.e1) != cudaSuccess ||
+            cudaEventRecord(sp.e0, s) != cudaSuccess) {
+            h->prof_error = true;
+            if (sp.e0 != nullptr) cudaEventDestroy(sp.e0);
+            if (sp.e1 != nullptr) cudaEventDestroy(sp.e1);
+            on = false;
+        }
     }
     ~SpanGuard() {
         if (!on) return;
-        cudaEventRecord(sp.e1, s);
+        if (cudaEventRecord(sp.e1, s) != cudaSuccess) {
+            h->prof_error = true;
+            cudaEventDestroy(sp.e0);
+            cudaEventDestroy(sp.e1);
+            return;
+        }
         h->spans.push_back(sp);
     }
 };
@@ -220,26 +256,22 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
     h->work_enqueued = true;
     const size_t hw = static_cast<size_t>(H) * W;
     const size_t n_img = static_cast<size_t>(B) * L;
-    const size_t act_bytes = n_img * hw * 64 * sizeof(__nv_bfloat16);
-    if (act_bytes > h->act_cap) {
-        for (int i = 0; i < 5; ++i) {
-            if (h->act[i] != nullptr) HRN_CUDA_OK(cudaFree(h->act[i]));
-            h->act[i] = nullptr;
-        }
-        h->act_cap = 0;
-        for (int i = 0; i < 5; ++i) HRN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->act[i]), act_bytes));
-        h->act_cap = act_bytes;
-    }
-    if (grow(reinterpret_cast<void**>(&h->anchor), &h->anchor_cap, static_cast<size_t>(B) * hw * sizeof(float))) return -1;
+    if (ensure_workspace(h, B, L, H, W)) return -1;
+    // The activation workspace and the live-work lists belong to the handle: a forward on another stream than the
+    // previous one must not start before that one has finished (same-stream calls are ordered anyway).
+    if (h->ev_fwd_done == nullptr) HRN_CUDA_OK(cudaEventCreateWithFlags(&h->ev_fwd_done, cudaEventDisableTiming));
+    if (h->have_last && h->last_stream != s) HRN_CUDA_OK(cudaStreamWaitEvent(s, h->ev_fwd_done, 0));
+    SpanGuard whole(h, s, HRN_PROF_FORWARD, 0.0);
 
     // ---- live-work lists: views / pairs that cannot reach the output (alpha = 0 padding) are not computed at all.
     // The stage-dump hook asks for dense lists so that every intermediate tensor is defined.  Must stay the first
     // launch of the pass (see live_lists_launch).
-    if (grow(reinterpret_cast<void**>(&h->lists), &h->lists_cap, hrn::live_lists_ints(B, L) * sizeof(int))) return -1;
-    if (grow(reinterpret_cast<void**>(&h->live_scratch), &h->live_scratch_cap, hrn::live_scratch_bytes(B, L))) return -1;
-    if (hrn::live_lists_launch(alphas, B, L, (dump == nullptr && h->skip_dead) ? 1 : 0, h->cfg.rec_alpha_residual ? 1 : 0,
-                               h->live_scratch, h->lists, s))
-        return -1;
+    {
+        SpanGuard guard(h, s, HRN_PROF_LIVE_LISTS, 0.0);
+        if (hrn::live_lists_launch(alphas, B, L, (dump == nullptr && h->skip_dead) ? 1 : 0, h->cfg.rec_alpha_residual ? 1 : 0,
+                                   h->live_scratch, h->lists, s))
+            return -1;
+    }
     const int* enc_list = h->lists + 16;
     const int* enc_count = h->lists;
 
@@ -383,6 +415,9 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
         set_error("hrn_forward_dump: stage 0x%x does not exist for L=%d", dump->stage, L);
         return -1;
     }
+    HRN_CUDA_OK(cudaEventRecord(h->ev_fwd_done, s));
+    h->last_stream = s;
+    h->have_last = true;
     return 0;
 }
 
@@ -471,6 +506,11 @@ void hrn_destroy(hrn_handle* h) {
     rel(h->live_scratch);
     for (auto* p : h->io) rel(p);
     rel(h->io_u16);
+    if (h->ev_fwd_done != nullptr) cudaEventDestroy(h->ev_fwd_done);
+    for (auto& sp : h->spans) {
+        cudaEventDestroy(sp.e0);
+        cudaEventDestroy(sp.e1);
+    }
     for (auto& sl : h->slots) {
         rel(sl.lrs);
         rel(sl.alphas);
@@ -600,6 +640,24 @@ static int forward_sliced(hrn_handle* h, const float* lrs, const float* alphas, 
         if (forward_impl(h, lrs + b0 * set_in, alphas + b0 * L, nb, L, H, W, sr + b0 * set_out, s, nullptr)) return -1;
     }
     return 0;
+}
+
+int32_t hrn_reserve(hrn_handle* h, int32_t B, int32_t L, int32_t H, int32_t W) {
+    if (h == nullptr) {
+        set_error("null handle");
+        return -1;
+    }
+    if (B <= 0 || L <= 0 || H <= 0 || W <= 0) {
+        set_error("hrn_reserve: empty shape (B=%d L=%d H=%d W=%d)", B, L, H, W);
+        return -1;
+    }
+    hrn::DeviceGuard on_device(h->device);
+    if (!on_device.ok) return -1;
+    // same slicing rule as hrn_forward: a batch above the workspace cap runs in slices of this many imagesets
+    const double per_set = 5.0 * L * static_cast<double>(H) * W * 128.0;
+    long long slice = static_cast<long long>(static_cast<double>(h->workspace_mb) * 1048576.0 / per_set);
+    slice = slice < 1 ? 1 : (slice > B ? B : slice);
+    return ensure_workspace(h, static_cast<int>(slice), L, H, W);
 }
 
 int32_t hrn_forward(hrn_handle* h, const float* lrs, const float* alphas, int32_t B, int32_t L, int32_t H, int32_t W,
@@ -846,6 +904,7 @@ int32_t hrn_profile_begin(hrn_handle* h) {
     }
     h->spans.clear();
     h->profiling = true;
+    h->prof_error = false;
     return 0;
 }
 
@@ -873,6 +932,10 @@ int32_t hrn_profile_end(hrn_handle* h, double* ms, double* flops, int64_t* launc
         cudaEventDestroy(sp.e1);
     }
     h->spans.clear();
+    if (h->prof_error) {
+        set_error("hrn_profile_end: a CUDA event call failed while profiling; the times are incomplete");
+        return -1;
+    }
     return 0;
 }
 

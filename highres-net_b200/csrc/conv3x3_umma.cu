@@ -471,10 +471,11 @@ static bool cluster_pairs_fit(int pairs) {
     static int max_pairs[64] = {};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    using C = Cfg<128>;
+    static bool attr_set[64] = {};
+    if (allow_dynamic_smem(conv3x3_umma_kernel<128, false, true>, C::SMEM_BYTES, attr_set)) return false;
+    std::lock_guard<std::mutex> lock(lazy_init_mutex());
     if (max_pairs[dev] == 0) {
-        using C = Cfg<128>;
-        static bool attr_set[64] = {};
-        if (allow_dynamic_smem(conv3x3_umma_kernel<128, false, true>, C::SMEM_BYTES, attr_set)) return false;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(2 * 148);
         cfg.blockDim = dim3(NUM_THREADS);

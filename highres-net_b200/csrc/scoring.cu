@@ -566,6 +566,106 @@ __global__ void cpsnr_finalize_kernel(const double* __restrict__ partial, CpGeom
     }
 }
 
+// ------------------------------------------------------------------ any border_w (Evaluator.py:52 takes any): one block per
+// (site, imageset) walks the whole crop; same fp32 element arithmetic, fp64 sums in a fixed order.  Slow path for
+// border_w > 3 only (the reference's own callers always use 3).
+constexpr int CA_THREADS = 256;
+template <int PASS>
+__global__ void __launch_bounds__(CA_THREADS)
+cpsnr_any_pass_kernel(const float* __restrict__ sr, const float* __restrict__ hr, const float* __restrict__ hm, CpGeom g,
+                      int clip_sr, const float* __restrict__ bias, double* __restrict__ partial) {
+    __shared__ double red[2][CA_THREADS / 32];
+    const int site = blockIdx.x, set = blockIdx.y, sites = g.S * g.S;
+    const int x = site / g.S, y = site % g.S;
+    const size_t plane = static_cast<size_t>(g.H) * g.W;
+    const float* srp = sr + set * plane + static_cast<size_t>(g.border) * g.W + g.border;
+    const float* hrp = hr + set * plane + static_cast<size_t>(x) * g.W + y;
+    const float* hmp = hm + set * plane + static_cast<size_t>(x) * g.W + y;
+    const float b = PASS == 2 ? bias[set * sites + site] : 0.0f;
+    double a0 = 0.0, a1 = 0.0;
+    for (int i = 0; i < g.size; ++i) {
+        float p0 = 0.0f, p1 = 0.0f;
+        for (int j = threadIdx.x; j < g.size; j += CA_THREADS) {
+            const size_t off = static_cast<size_t>(i) * g.W + j;
+            float sv = __ldg(srp + off);
+            if (clip_sr) sv = fminf(fmaxf(sv, 0.0f), 1.0f);
+            const float m = __ldg(hmp + off), d = __ldg(hrp + off) - sv;
+            if (PASS == 1) {
+                p0 += m;
+                p1 += d * m;
+            } else {
+                const float t = (d - b) * m;
+                p0 += t * t;
+            }
+        }
+        a0 += static_cast<double>(p0);
+        a1 += static_cast<double>(p1);
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = a0;
+        red[1][threadIdx.x >> 5] = a1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r0 = 0.0, r1 = 0.0;
+        for (int w = 0; w < CA_THREADS / 32; ++w) {
+            r0 += red[0][w];
+            r1 += red[1][w];
+        }
+        partial[(static_cast<size_t>(set) * sites + site) * 2] = r0;
+        partial[(static_cast<size_t>(set) * sites + site) * 2 + 1] = PASS == 1 ? r1 : 0.0;
+    }
+}
+
+// One block per imageset; MODE 1: bias and n_clear per site; MODE 2: scores + first-maximum argmax (NaN wins, like numpy).
+template <int MODE>
+__global__ void __launch_bounds__(CA_THREADS)
+cpsnr_any_finalize_kernel(const double* __restrict__ partial, int sites, float* __restrict__ bias, double* __restrict__ nclear,
+                          float* __restrict__ best_db, int32_t* __restrict__ best_site, float* __restrict__ site_db) {
+    __shared__ float bv[CA_THREADS];
+    __shared__ int bi[CA_THREADS];
+    const int set = blockIdx.x;
+    auto better = [](float av, int ai, float cv, int ci) {
+        const bool an = av != av, cn = cv != cv;
+        if (an || cn) return (an && cn) ? ai < ci : an;
+        if (av != cv) return av > cv;
+        return ai < ci;
+    };
+    float v = -INFINITY;
+    int arg = 0x7fffffff;
+    for (int site = threadIdx.x; site < sites; site += CA_THREADS) {
+        const double a0 = partial[(static_cast<size_t>(set) * sites + site) * 2];
+        const double a1 = partial[(static_cast<size_t>(set) * sites + site) * 2 + 1];
+        if (MODE == 1) {
+            nclear[set * sites + site] = a0;
+            bias[set * sites + site] = static_cast<float>(a1 / a0);
+        } else {
+            const float sc = static_cast<float>(-10.0 * log10(a0 / nclear[set * sites + site]));
+            if (site_db != nullptr) site_db[set * sites + site] = sc;
+            if (arg == 0x7fffffff || better(sc, site, v, arg)) {
+                v = sc;
+                arg = site;
+            }
+        }
+    }
+    if (MODE == 2) {
+        bv[threadIdx.x] = v;
+        bi[threadIdx.x] = arg;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int t = 1; t < CA_THREADS; ++t)
+                if (bi[t] != 0x7fffffff && better(bv[t], bi[t], v, arg)) {
+                    v = bv[t];
+                    arg = bi[t];
+                }
+            best_db[set] = v;
+            best_site[set] = arg;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ clear loss (train.py:66-87 without autograd)
 // metric 0: masked_MSE = mean over ALL pixels of (m*sr - m*hr)^2
 // metric 1: cMSE       = sum(m * (sr + b - hr)^2) / sum(m),  b = sum(m * (hr - sr)) / sum(m)   (weight m, not m^2)
@@ -728,8 +828,12 @@ int shift_cpsnr_launch(const float* sr, const float* hr, const float* hm, int B,
         set_error("shift_cpsnr: square images only (got %d x %d), like Evaluator.py:64", H, W);
         return -1;
     }
-    if (border < 0 || 2 * border + 1 > CP_MAXS || W - 2 * border <= 0) {
-        set_error("shift_cpsnr: border_w=%d unsupported for %d x %d (0 <= border_w <= 3)", border, H, W);
+    if (border < 0 || W - 2 * border <= 0) {
+        set_error("shift_cpsnr: border_w=%d leaves no crop of a %d x %d image", border, H, W);
+        return -1;
+    }
+    if (2 * border + 1 > 255) {
+        set_error("shift_cpsnr: border_w=%d: more than 255 x 255 shifts are not supported", border);
         return -1;
     }
     if (B <= 0 || B > 65535) {
@@ -742,6 +846,28 @@ int shift_cpsnr_launch(const float* sr, const float* hr, const float* hm, int B,
     g.border = border;
     g.S = 2 * border + 1;
     g.size = W - 2 * border;
+    if (g.S > CP_MAXS) {
+        // border_w > 3: no caller of the reference uses it, but Evaluator.py:52 accepts it -> one block per (site, imageset)
+        g.col_blocks = g.band_rows = g.blocks_per_set = 1;
+        g.vec_ok = 0;
+        const int sites = g.S * g.S;
+        const size_t partial_bytes = static_cast<size_t>(B) * sites * 2 * sizeof(double);
+        const size_t nclear_bytes = static_cast<size_t>(B) * sites * sizeof(double);
+        uint8_t* ws = nullptr;
+        if (scratch_alloc(reinterpret_cast<void**>(&ws), partial_bytes + nclear_bytes + static_cast<size_t>(B) * sites * sizeof(float), s)) return -1;
+        double* partial = reinterpret_cast<double*>(ws);
+        double* nclear = reinterpret_cast<double*>(ws + partial_bytes);
+        float* bias = reinterpret_cast<float*>(ws + partial_bytes + nclear_bytes);
+        dim3 grid(sites, B);
+        cpsnr_any_pass_kernel<1><<<grid, CA_THREADS, 0, s>>>(sr, hr, hm, g, clip_sr, nullptr, partial);
+        cpsnr_any_finalize_kernel<1><<<B, CA_THREADS, 0, s>>>(partial, sites, bias, nclear, nullptr, nullptr, nullptr);
+        cpsnr_any_pass_kernel<2><<<grid, CA_THREADS, 0, s>>>(sr, hr, hm, g, clip_sr, bias, partial);
+        cpsnr_any_finalize_kernel<2><<<B, CA_THREADS, 0, s>>>(partial, sites, bias, nclear, best_db, best_site, site_db);
+        note_launches(4);
+        HRN_CUDA_OK(cudaGetLastError());
+        HRN_CUDA_OK(cudaFreeAsync(ws, s));
+        return 0;
+    }
     g.vec_ok = (W % 4 == 0) && (((reinterpret_cast<uintptr_t>(sr) | reinterpret_cast<uintptr_t>(hr) | reinterpret_cast<uintptr_t>(hm)) & 15) == 0);
     // border_w = 3 on 16-byte aligned rows (every case the reference produces) takes the 49-site window kernel
     const bool window = g.S == CW_S && g.vec_ok && g_cpsnr_generic == 0;

@@ -4,6 +4,7 @@
 #include "internal.h"
 #include "ptx.cuh"
 
+#include <mutex>
 #include <utility>
 
 namespace hrn {
@@ -17,7 +18,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// Guards the lazily initialised per-device statics below (two handles on two host threads are legal).
+inline std::mutex& lazy_init_mutex() {
+    static std::mutex mu;
+    return mu;
+}
+
 inline EncodeTiledFn get_encode_fn() {
+    std::lock_guard<std::mutex> lock(lazy_init_mutex());
     static EncodeTiledFn fn = nullptr;
     if (fn == nullptr) {
         void* p = nullptr;
@@ -65,6 +73,7 @@ inline int allow_dynamic_smem(K kernel, int bytes, bool (&done)[64]) {
         set_error("device index %d out of range", dev);
         return -1;
     }
+    std::lock_guard<std::mutex> lock(lazy_init_mutex());
     if (!done[dev]) {
         HRN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         done[dev] = true;

@@ -22,10 +22,10 @@ def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
 
 
 def shard_batch(lrs: torch.Tensor, alphas: torch.Tensor, rank: Optional[int] = None,
-                world_size: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor, Tuple[int, int]]:
-    """The slice of a global batch this rank owns (views, no copy)."""
-    rank = dist.get_rank() if rank is None else rank
-    world_size = dist.get_world_size() if world_size is None else world_size
+                world_size: Optional[int] = None, group=None) -> Tuple[torch.Tensor, torch.Tensor, Tuple[int, int]]:
+    """The slice of a global batch this rank owns (views, no copy).  rank / world_size default to those of `group`."""
+    rank = dist.get_rank(group) if rank is None else rank
+    world_size = dist.get_world_size(group) if world_size is None else world_size
     lo, hi = shard_range(lrs.shape[0], rank, world_size)
     return lrs[lo:hi], alphas[lo:hi], (lo, hi)
 
@@ -53,13 +53,21 @@ def sharded_forward_and_score(model, lrs, alphas, hrs=None, hr_maps=None, gather
     through the shifted-cPSNR search; returns (sr, scores, best_xy) in GLOBAL batch order (gathered).  `model` and the
     scorer are injected so that the host logic can be exercised on CPU with stand-ins."""
     n = lrs.shape[0]
-    l_lrs, l_alphas, (lo, hi) = shard_batch(lrs, alphas)
-    sr_local = model(l_lrs, l_alphas)
+    l_lrs, l_alphas, (lo, hi) = shard_batch(lrs, alphas, group=group)
+    if hi > lo:
+        sr_local = model(l_lrs, l_alphas)
+    else:
+        # fewer imagesets than ranks: this rank owns nothing, but it still takes part in the collectives below
+        sr_local = torch.zeros((0, 1, 3 * lrs.shape[2], 3 * lrs.shape[3]), dtype=torch.float32, device=lrs.device)
     sr = gather_batch(sr_local, n, group) if gather_sr else sr_local
     if hrs is None:
         return sr, None, None
-    from .evaluator import shift_cPSNR_argmax
-    best, xy, _ = shift_cPSNR_argmax(sr_local[:, 0], hrs[lo:hi], hr_maps[lo:hi], clip_sr=True)
-    packed = torch.cat([torch.as_tensor(best).reshape(-1, 1).float(), torch.as_tensor(xy).reshape(-1, 2).float()], 1)
-    packed = gather_batch(packed.to(sr_local.device), n, group)
+    if hi > lo:
+        from .evaluator import shift_cPSNR_argmax
+        best, xy, _ = shift_cPSNR_argmax(sr_local[:, 0], hrs[lo:hi], hr_maps[lo:hi], clip_sr=True)
+        packed = torch.cat([torch.as_tensor(best).reshape(-1, 1).float(), torch.as_tensor(xy).reshape(-1, 2).float()], 1)
+        packed = packed.to(sr_local.device)
+    else:
+        packed = torch.zeros((0, 3), dtype=torch.float32, device=sr_local.device)
+    packed = gather_batch(packed, n, group)
     return sr, packed[:, 0], packed[:, 1:].to(torch.int64)

@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from ._native import NativeHandleMixin
 
 
 def _container(**children) -> nn.Module:
@@ -31,7 +32,7 @@ def _conv_prelu_pair(c: int, k: int) -> nn.Sequential:
     return nn.Sequential(nn.Conv2d(c, c, k, padding=k // 2), nn.PReLU(), nn.Conv2d(c, c, k, padding=k // 2), nn.PReLU())
 
 
-class HRNet(nn.Module):
+class HRNet(NativeHandleMixin, nn.Module):
     """HRNet(config) with config = the "network" block of config/config.json."""
 
     def __init__(self, config):
@@ -60,12 +61,9 @@ class HRNet(nn.Module):
                                                     stride=d["stride"]), nn.PReLU()),
             final=nn.Conv2d(fin["in_channels"], fin["out_channels"], fin["kernel_size"],
                             padding=fin["kernel_size"] // 2))
-        self._handles = {}        # device index -> (c_void_p handle, weight fingerprint)
+        self._native_init()       # device index -> [native handle address, weight fingerprint] (see _native.py)
 
     # ------------------------------------------------------------------ native handle
-    def _fingerprint(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
-
     def _handle_for(self, device: torch.device) -> ctypes.c_void_p:
         lib = _lib.load()
         idx = device.index if device.index is not None else torch.cuda.current_device()
@@ -74,24 +72,29 @@ class HRNet(nn.Module):
         if entry is None:
             handle = ctypes.c_void_p()
             _lib.check(lib.hrn_create(ctypes.byref(self._cfg), idx, ctypes.byref(handle)), "hrn_create")
-            entry = [handle, None]
+            entry = [handle.value, None]
             self._handles[idx] = entry
         if entry[1] != fp:
             for key, tensor in self.state_dict().items():
                 host = tensor.detach().to("cpu", torch.float32).contiguous()
                 shape = (ctypes.c_int64 * host.dim())(*host.shape)
-                _lib.check(lib.hrn_set_weight(entry[0], key.encode(), ctypes.c_void_p(host.data_ptr()), shape,
-                                              host.dim()), f"hrn_set_weight({key})")
+                _lib.check(lib.hrn_set_weight(ctypes.c_void_p(entry[0]), key.encode(), ctypes.c_void_p(host.data_ptr()),
+                                              shape, host.dim()), f"hrn_set_weight({key})")
             entry[1] = fp
-        return entry[0]
+        return ctypes.c_void_p(entry[0])
 
     def __del__(self):
         try:
             lib = _lib.load()
-            for handle, _ in self._handles.values():
-                lib.hrn_destroy(handle)
+            self._destroy_handles(lambda addr: lib.hrn_destroy(ctypes.c_void_p(addr)))
         except Exception:
             pass
+
+    def reserve(self, device, b: int, l: int, h: int, w: int) -> None:
+        """Sizes the native workspace for forwards of up to (b, l, h, w) now (hrn_reserve), so that no later forward has
+        to reallocate it in the middle of the stream."""
+        _lib.check(_lib.load().hrn_reserve(self._handle_for(torch.device(device)), int(b), int(l), int(h), int(w)),
+                   "hrn_reserve")
 
     def debug_set(self, device, knob: str, value: int) -> None:
         """Bring-up knobs of the native handle (see hrn_debug_set in include/hrn_b200.h)."""
@@ -99,7 +102,7 @@ class HRNet(nn.Module):
         _lib.check(_lib.load().hrn_debug_set(handle, knob.encode(), int(value)), "hrn_debug_set")
 
     PROFILE_CLASSES = ("conv3x3_umma<64>", "conv3x3_umma<128>", "conv_init", "decoder", "median_anchor",
-                       "resblock64_umma")
+                       "resblock64_umma", "live_lists", "forward_span", "fuse_wave")
 
     def profile_begin(self, device) -> None:
         """Arm per-launch CUDA-event timing of the following forward calls (hrn_profile_begin)."""

@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from ._native import NativeHandleMixin
 from . import lanczos as _lanczos
 
 
@@ -25,7 +26,7 @@ def _block(cin, cout, pool):
     return nn.Sequential(*layers)
 
 
-class ShiftNet(nn.Module):
+class ShiftNet(NativeHandleMixin, nn.Module):
     """ShiftNet.py:6-75; the torch layers only hold the parameters and buffers (and define the state_dict layout)."""
 
     def __init__(self, in_channel=1):
@@ -44,11 +45,8 @@ class ShiftNet(nn.Module):
         self.fc1 = nn.Linear(128 * 16 * 16, 1024)
         self.activ1 = nn.ReLU()
         self.fc2 = nn.Linear(1024, 2, bias=False)
+        self._native_init()
         self.fc2.weight.data.zero_()                 # ShiftNet.py:48: starts as the identity transformation
-        self._handles = {}
-
-    def _fingerprint(self):
-        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
 
     def _handle_for(self, device):
         lib = _lib.load()
@@ -58,7 +56,7 @@ class ShiftNet(nn.Module):
         if entry is None:
             handle = ctypes.c_void_p()
             _lib.check(lib.hrn_shiftnet_create(idx, ctypes.byref(handle)), "hrn_shiftnet_create")
-            entry = [handle, None]
+            entry = [handle.value, None]
             self._handles[idx] = entry
         if entry[1] != fp:
             for key, tensor in self.state_dict().items():
@@ -66,16 +64,16 @@ class ShiftNet(nn.Module):
                     continue
                 host = tensor.detach().to("cpu", torch.float32).contiguous()
                 shape = (ctypes.c_int64 * host.dim())(*host.shape)
-                _lib.check(lib.hrn_shiftnet_set_weight(entry[0], key.encode(), ctypes.c_void_p(host.data_ptr()), shape,
-                                                       host.dim()), f"hrn_shiftnet_set_weight({key})")
+                _lib.check(lib.hrn_shiftnet_set_weight(ctypes.c_void_p(entry[0]), key.encode(),
+                                                       ctypes.c_void_p(host.data_ptr()), shape, host.dim()),
+                           f"hrn_shiftnet_set_weight({key})")
             entry[1] = fp
-        return entry[0]
+        return ctypes.c_void_p(entry[0])
 
     def __del__(self):
         try:
             lib = _lib.load()
-            for handle, _ in self._handles.values():
-                lib.hrn_shiftnet_destroy(handle)
+            self._destroy_handles(lambda addr: lib.hrn_shiftnet_destroy(ctypes.c_void_p(addr)))
         except Exception:
             pass
 

@@ -72,6 +72,11 @@ int32_t hrn_missing_weights(const hrn_handle* h);
  * nothing synchronises with the host. */
 int32_t hrn_forward(hrn_handle* h, const float* lrs, const float* alphas, int32_t B, int32_t L, int32_t H,
                     int32_t W, float* sr, void* stream);
+/* Sizes the handle's workspace for forwards of up to (B, L, H, W) now, so that no later hrn_forward* call has to free and
+ * reallocate it (which synchronises the device in the middle of the caller's stream).  Optional: without it the first
+ * call of a larger shape grows the workspace itself.  Replaces nothing in the reference (PyTorch's caching allocator
+ * plays this role behind HRNet.forward, HRNet.py:186-211). */
+int32_t hrn_reserve(hrn_handle* h, int32_t B, int32_t L, int32_t H, int32_t W);
 
 /* Same with HOST buffers (the train.py:200-208 / predict.py:36-40 pattern: H2D of
  * lrs/alphas, forward, D2H of sr), synchronous.  The batch is cut into chunks whose copies overlap the
@@ -168,7 +173,10 @@ int32_t hrn_scoring_debug_set(const char* knob, int32_t value);
 #define HRN_PROF_DECODER 3    /* deconv + PReLU + 1x1             */
 #define HRN_PROF_MEDIAN 4     /* median anchor                    */
 #define HRN_PROF_RESBLOCK64 5 /* fused encoder ResidualBlock (two 64 -> 64 convs in one launch) */
-#define HRN_PROF_CLASSES 6
+#define HRN_PROF_LIVE_LISTS 6 /* live-work lists (first launch of every forward) */
+#define HRN_PROF_FORWARD 7    /* one span around the whole forward: FORWARD - sum(classes 0..6) = gaps between launches */
+#define HRN_PROF_FUSE_WAVE 8  /* fused fusion level (three convs of one level in one wavefront launch) */
+#define HRN_PROF_CLASSES 9
 int32_t hrn_profile_begin(hrn_handle* h);
 int32_t hrn_profile_end(hrn_handle* h, double* ms, double* flops, int64_t* launches);
 

@@ -114,3 +114,46 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "/root/reference" not in text, f
+
+
+def test_module_copies_and_pickles_without_its_native_handles():
+    """The reference module supports copy.deepcopy / torch.save(model) (best-model snapshots, EMA copies); the native
+    handles are process-local pointers and must stay out of the copied state (a copy makes its own lazily)."""
+    import copy
+    import io
+    import highres_net_b200 as hb
+    from oracle import hrnet_oracle
+    for net in (hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG), hb.ShiftNet()):
+        net._handles[0] = [0xdeadbeef, ("fingerprint",)]          # what a first forward on cuda:0 would have stored
+        twin = copy.deepcopy(net)
+        assert twin._handles == {} and net._handles[0][0] == 0xdeadbeef
+        assert all(torch.equal(a, b) for a, b in zip(twin.state_dict().values(), net.state_dict().values()))
+        buf = io.BytesIO()
+        torch.save(net, buf)
+        buf.seek(0)
+        loaded = torch.load(buf, weights_only=False)
+        assert loaded._handles == {} and list(loaded.state_dict()) == list(net.state_dict())
+        net._handles.clear()                                      # nothing real to destroy
+
+
+def test_weight_refresh_rule_sees_what_torch_can_and_cannot_signal():
+    """`.data` edits bump neither data_ptr nor _version: invalidate_weights() or verify_weights cover them."""
+    import highres_net_b200 as hb
+    from oracle import hrnet_oracle
+    net = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG)
+    fp0 = net._fingerprint()
+    with torch.no_grad():
+        net.encode.final[0].bias.add_(1.0)                        # version bump: seen
+    fp1 = net._fingerprint()
+    assert fp1 != fp0
+    net.encode.final[0].bias.data.mul_(2.0)                       # .data edit: invisible to the cheap rule ...
+    assert net._fingerprint() == fp1
+    net.invalidate_weights()                                      # ... so the caller says so,
+    fp2 = net._fingerprint()
+    assert fp2 != fp1
+    net.verify_weights = True                                     # or asks for the checksum rule
+    fp3 = net._fingerprint()
+    net.encode.final[0].bias.data.mul_(0.5)
+    assert net._fingerprint() != fp3
+    net.load_state_dict(hrnet_oracle.make_params(0))              # wholesale rewrites invalidate by themselves
+    assert net._fingerprint()[0] > fp3[0]

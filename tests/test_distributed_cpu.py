@@ -25,6 +25,7 @@ def _worker(rank, world, port, n_items, results):
         alphas = torch.ones(n_items, 3)
 
         def fake_model(x, a):                       # stand-in with the HRNet signature: (b, L, H, W) -> (b, 1, 3H, 3W)
+            assert x.shape[0] > 0, "hrn_forward rejects an empty batch: ranks without work must not call the model"
             return (x * a[:, :, None, None]).sum(1, keepdim=True).repeat_interleave(3, 2).repeat_interleave(3, 3)
 
         l_lrs, l_alphas, (lo, hi) = hd.shard_batch(lrs, alphas)
@@ -32,6 +33,10 @@ def _worker(rank, world, port, n_items, results):
         sr, scores, xy = hd.sharded_forward_and_score(fake_model, lrs, alphas)
         assert scores is None and xy is None
         ref = fake_model(lrs, alphas)
+        # a sub-group that holds only this rank: the shard must follow the GROUP's rank / size, not the global ones
+        solo = [dist.new_group([r]) for r in range(world)][rank]
+        sr_solo, _, _ = hd.sharded_forward_and_score(fake_model, lrs, alphas, group=solo)
+        assert torch.equal(sr_solo, ref)
         results[rank] = bool(torch.equal(sr, ref)) and sr.shape[0] == n_items
         row = torch.arange(lo, hi, dtype=torch.float32).reshape(-1, 1)
         gathered = hd.gather_batch(row, n_items)

@@ -458,6 +458,64 @@ def test_two_handles_on_two_streams(hb, dev):
             assert torch.equal(o, refs[k])
 
 
+def test_one_handle_two_streams_are_ordered(hb, dev):
+    """two forwards of ONE module on different torch streams share the handle's workspace; the handle orders
+    them with an event, so both results must equal the single-stream results."""
+    model = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval()
+    model.load_state_dict(hrnet_oracle.make_params(cases.WEIGHT_SEED))
+    model = model.to(dev)
+    g = torch.Generator().manual_seed(77)
+    a = (torch.rand(4, 8, 96, 96, generator=g).to(dev), torch.ones(4, 8, device=dev))
+    b = (torch.rand(4, 8, 96, 96, generator=g).to(dev), torch.ones(4, 8, device=dev))
+    ref_a, ref_b = model(*a), model(*b)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    for _ in range(5):
+        with torch.cuda.stream(s1):
+            out_a = model(*a)
+        with torch.cuda.stream(s2):
+            out_b = model(*b)
+        torch.cuda.synchronize()
+        assert torch.equal(out_a, ref_a) and torch.equal(out_b, ref_b)
+
+
+def test_reserve_presizes_the_workspace(hb, dev):
+    model = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval()
+    model.load_state_dict(hrnet_oracle.make_params(cases.WEIGHT_SEED))
+    model = model.to(dev)
+    model.reserve(dev, 4, 8, 64, 64)
+    free0, _ = torch.cuda.mem_get_info(dev)
+    lrs, alphas = torch.rand(4, 8, 64, 64, device=dev), torch.ones(4, 8, device=dev)
+    sr = model(lrs, alphas)
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info(dev)
+    assert free0 - free1 < 5 * 4 * 8 * 64 * 64 * 128 // 2          # the forward did not allocate the activation buffers again
+    assert torch.isfinite(sr).all()
+    with pytest.raises(RuntimeError):
+        model.reserve(dev, 0, 8, 64, 64)
+
+
+def test_data_edits_need_invalidate_or_verify(hb, dev):
+    """in-place edits through .data do not bump torch's version counter; invalidate_weights() (or
+    verify_weights) makes the next forward upload the new values."""
+    model = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval()
+    model.load_state_dict(hrnet_oracle.make_params(cases.WEIGHT_SEED))
+    model = model.to(dev)
+    lrs, alphas = torch.rand(1, 4, 32, 32, device=dev), torch.ones(1, 4, device=dev)
+    base = model(lrs, alphas).clone()
+    model.decode.final.bias.data.add_(0.25)
+    model.invalidate_weights()
+    moved = model(lrs, alphas)
+    assert torch.allclose(moved, base + 0.25, atol=1e-6)
+    model.verify_weights = True
+    model(lrs, alphas)
+    model.decode.final.bias.data.sub_(0.25)
+    assert torch.allclose(model(lrs, alphas), base, atol=1e-6)
+    import copy
+    twin = copy.deepcopy(model)                                    # after a forward: the handles stay behind
+    assert torch.equal(twin(lrs, alphas), model(lrs, alphas))
+
+
 def test_forward_rejects_bad_inputs(hb, net, dev):
     with pytest.raises(RuntimeError):
         net(torch.rand(1, 2, 16, 16), torch.ones(1, 2))                  # CPU tensors: no fallback
@@ -620,7 +678,25 @@ def test_shift_cpsnr_rejects_bad_arguments(hb, dev):
         hb.shift_cPSNR(sr, sr, sr)                                              # non-square
     sq = torch.rand(1, 20, 20, device=dev)
     with pytest.raises(RuntimeError):
-        hb.shift_cPSNR(sq, sq, sq, border_w=4)                                  # more than 7x7 shifts
+        hb.shift_cPSNR(sq, sq, sq, border_w=10)                                 # nothing left of a 20 x 20 image
+
+
+@pytest.mark.parametrize("border_w,s", [(4, 24), (5, 40), (8, 33)])
+def test_shift_cpsnr_any_border_matches_oracle(hb, dev, border_w, s):
+    """Evaluator.py:52 accepts any border_w; above 3 the search takes the one-block-per-site kernels."""
+    rng = np.random.RandomState(100 + border_w)
+    b = 3
+    sr = rng.rand(b, s, s).astype(np.float32)
+    hr = np.clip(np.roll(sr, (2, -1), (1, 2)) + 0.01 * rng.randn(b, s, s), 0, 1).astype(np.float32)
+    hm = (rng.rand(b, s, s) > 0.2).astype(np.float32)
+    best, xy, tab = hb.shift_cPSNR_argmax(torch.from_numpy(sr).to(dev), torch.from_numpy(hr).to(dev), torch.from_numpy(hm).to(dev),
+                                          border_w=border_w)
+    span = 2 * border_w + 1
+    for i in range(b):
+        ref_max, ref_arg, ref_sites = scoring_oracle.shift_cpsnr(sr[i], hr[i], hm[i], border_w=border_w)
+        assert abs(float(best[i]) - float(ref_max)) <= CPSNR_KERNEL_GATE_DB
+        assert int(xy[i, 0]) * span + int(xy[i, 1]) == int(ref_arg)
+        assert np.abs(tab[i].cpu().numpy() - np.asarray(ref_sites).T.reshape(-1)).max() <= CPSNR_KERNEL_GATE_DB
 
 
 # ---------------------------------------------------------------------------- the composite path (C4)
@@ -650,6 +726,80 @@ def test_full_scoring_path_against_oracle(hb, net, dev):
     for i in range(b):
         assert abs(best[i] - ref_scores[i][0]) <= CPSNR_GATE_DB
         assert xy[i, 0] * 7 + xy[i, 1] == ref_scores[i][1] == (3 + rolls[i, 0]) * 7 + (3 + rolls[i, 1])
+
+
+def test_c4_full_batch_scoring_path(hb, net, dev):
+    """BASELINE.json configs[3] at FULL batch: 32 imagesets of 16 views, 128^2 -> 384^2, HRNet -> lanczos_shift -> clip ->
+    shift_cPSNR(border 3).  The oracle runs the whole chain for a sample of the batch (CPU time); for every imageset
+    the known roll must be the winning shift (HR is built from the device SR for the others).
+    Gates: SR 1e-2 max-abs, cPSNR 0.01 dB, argmax exact (sigma = 0.01 construction)."""
+    b, l, s = 32, 16, 128
+    rng = np.random.RandomState(41)
+    lrs = rng.rand(b, l, s, s).astype(np.float32)
+    alphas = np.ones((b, l), dtype=np.float32)
+    shift = rng.uniform(-1, 1, size=(b, 2)).astype(np.float32)
+    rolls = rng.randint(-3, 4, size=(b, 2))
+    params = hrnet_oracle.make_params(cases.WEIGHT_SEED)
+    sample = [0, 17, 31]
+    sr_ref = hrnet_oracle.hrnet_forward(params, lrs[sample], alphas[sample]).numpy()[:, 0]
+    moved_ref = np.clip(scoring_oracle.lanczos_shift(sr_ref[None], shift[sample], p=5)[0], 0, 1)
+
+    sr = net(torch.from_numpy(lrs).to(dev), torch.from_numpy(alphas).to(dev))[:, 0]
+    assert np.abs(sr[sample].cpu().numpy() - sr_ref).max() <= SR_REGRESSION_GATE
+    moved = hb.lanczos_shift(sr[None], torch.from_numpy(shift).to(dev), p=5, a=3, N=7)[0]
+    assert np.abs(moved[sample].cpu().numpy().clip(0, 1) - moved_ref).max() <= SR_REGRESSION_GATE
+    # HR: from the oracle's chain for the sampled imagesets, from the device chain for the rest
+    base = moved.clamp(0, 1).cpu().numpy()
+    for k, i in enumerate(sample):
+        base[i] = moved_ref[k]
+    hr = np.stack([np.roll(base[i], tuple(rolls[i]), (0, 1)) for i in range(b)])
+    hr = np.clip(hr + 0.02 + 0.01 * rng.randn(*hr.shape), 0, 1).astype(np.float32)
+    hm = (rng.rand(*hr.shape) > 0.1).astype(np.float32)
+    best, xy, _ = hb.shift_cPSNR_argmax(moved, torch.from_numpy(hr).to(dev), torch.from_numpy(hm).to(dev), clip_sr=True)
+    best, xy = best.cpu().numpy(), xy.cpu().numpy()
+    assert np.array_equal(xy[:, 0] * 7 + xy[:, 1], (3 + rolls[:, 0]) * 7 + (3 + rolls[:, 1]))
+    for k, i in enumerate(sample):
+        ref_max, ref_arg, _ = scoring_oracle.shift_cpsnr(moved_ref[k], hr[i], hm[i])
+        assert abs(best[i] - ref_max) <= CPSNR_GATE_DB, (best[i], ref_max)
+        assert xy[i, 0] * 7 + xy[i, 1] == ref_arg
+    # kernel parity on the device tensors themselves (same SR in, strict gate) for two more imagesets
+    moved_np = moved.clamp(0, 1).cpu().numpy()
+    for i in (5, 23):
+        ref_max, ref_arg, _ = scoring_oracle.shift_cpsnr(moved_np[i], hr[i], hm[i])
+        assert abs(best[i] - ref_max) <= CPSNR_KERNEL_GATE_DB and xy[i, 0] * 7 + xy[i, 1] == ref_arg
+
+
+def test_c3_shard_shape_one_imageset_vs_oracle(net, dev):
+    """BASELINE.json configs[2], the per-rank shard: 32 imagesets x 32 views of 128 x 128 (five fusion levels, 10 GiB of
+    workspace).  One imageset of the full batch against the oracle, plus batch independence at that size."""
+    b, l, s = 32, 32, 128
+    g = torch.Generator().manual_seed(32)
+    lrs = torch.rand(b, l, s, s, generator=g)
+    alphas = torch.ones(b, l)
+    tl, ta = lrs.to(dev), alphas.to(dev)
+    sr = net(tl, ta)
+    assert tuple(sr.shape) == (b, 1, 3 * s, 3 * s) and torch.isfinite(sr).all()
+    params = hrnet_oracle.make_params(cases.WEIGHT_SEED)
+    ref = hrnet_oracle.hrnet_forward(params, lrs[7:8].numpy(), alphas[7:8].numpy()).numpy()
+    err = np.abs(sr[7:8].cpu().numpy() - ref).max()
+    assert err <= SR_GATE and err <= 2e-3, err                 # five levels of bf16 rounding: 1.1e-3 measured
+    assert torch.equal(net(tl[7:8], ta[7:8])[0], sr[7])
+
+
+def test_c5_large_tile_one_imageset_vs_oracle(net, dev):
+    """BASELINE.json configs[4]: 512 x 512 LR (four 128-pixel column tiles per row), 8 views, batch 8 -> 1536 x 1536."""
+    b, l, s = 8, 8, 512
+    g = torch.Generator().manual_seed(512)
+    lrs = torch.rand(b, l, s, s, generator=g)
+    alphas = torch.ones(b, l)
+    tl, ta = lrs.to(dev), alphas.to(dev)
+    sr = net(tl, ta)
+    assert tuple(sr.shape) == (b, 1, 3 * s, 3 * s) and torch.isfinite(sr).all()
+    params = hrnet_oracle.make_params(cases.WEIGHT_SEED)
+    ref = hrnet_oracle.hrnet_forward(params, lrs[3:4].numpy(), alphas[3:4].numpy()).numpy()
+    err = np.abs(sr[3:4].cpu().numpy() - ref).max()
+    assert err <= SR_GATE and err <= SR_REGRESSION_GATE, err
+    assert torch.equal(net(tl[3:4], ta[3:4])[0], sr[3])
 
 
 # ---------------------------------------------------------------------------- the caller (SURVEY.md section 8f N1/N2)
@@ -980,3 +1130,50 @@ def test_trainstep_forward_value_through_every_drop_in(hb, shiftnet, golden, dev
     assert np.abs(loss.cpu().numpy() - g["loss"]).max() <= 0.05                                          # dB
     total = loss.mean() + float(g["lam"]) * shifts.mean() ** 2                                           # :186-187
     assert abs(float(total) - float(g["total"])) <= 0.05
+
+
+# ---------------------------------------------------------------------------- N > 1: the design's only collective on NCCL
+def _nccl_worker(rank, world, port, results):
+    import os
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    import highres_net_b200 as hb
+    from highres_net_b200 import distributed as hd
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        model = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval()
+        model.load_state_dict(hrnet_oracle.make_params(cases.WEIGHT_SEED))
+        model = model.to(dev)
+        n = 5                                                   # ragged: 3 + 2 imagesets
+        g = torch.Generator().manual_seed(9)
+        lrs = torch.rand(n, 4, 32, 32, generator=g).to(dev)
+        alphas = torch.ones(n, 4, device=dev)
+        sr_all = model(lrs, alphas)                             # every rank also computes the whole batch as the check
+        hr = (torch.roll(sr_all[:, 0].clamp(0, 1), (1, -2), (1, 2)) + 0.02).clamp(0, 1)
+        hm = (torch.rand(n, 96, 96, generator=g) > 0.1).float().to(dev)
+        best_all, xy_all, _ = hb.shift_cPSNR_argmax(sr_all[:, 0], hr, hm, clip_sr=True)
+        sr, best, xy = hd.sharded_forward_and_score(model, lrs, alphas, hr, hm)
+        ok = torch.equal(sr, sr_all) and torch.equal(best, best_all) and torch.equal(xy, xy_all.to(torch.int64))
+        sr1, best1, _ = hd.sharded_forward_and_score(model, lrs[:1], alphas[:1], hr[:1], hm[:1])   # fewer imagesets than ranks
+        ok = ok and torch.equal(sr1, sr_all[:1]) and torch.equal(best1, best_all[:1])
+        results[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two visible GPUs")
+def test_sharded_forward_and_score_over_nccl():
+    """Two ranks, one GPU each: batch shards through the real kernels, SR and (cPSNR, x, y) gathered with NCCL must be
+    bit-identical to the single-GPU run (imagesets are independent and the kernels deterministic)."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_nccl_worker, args=(2, port, results), nprocs=2, join=True)
+    assert dict(results) == {0: True, 1: True}
