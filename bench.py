@@ -20,6 +20,7 @@ Prints ONE JSON line (see the build contract):
   scoring       Lanczos shift and shifted-cPSNR search: GB/s against the HBM peak, the composite C4 path, CPU baselines
   configs       BASELINE.json configs[2] (per-rank shard) and configs[4]: throughput, fraction of roofline, SR error vs oracle
   gpu_baseline  the reference algorithm through PyTorch eager + cuDNN on the same GPU (TF32 and bf16 autocast)
+  io            16-bit PNG imagesets on disk -> SR PNGs: native threaded decode / encode around the device path
   cpu_baseline  the oracle port (torch CPU fp32, all host threads) on a bounded sample
 """
 from __future__ import annotations
@@ -444,13 +445,13 @@ class Bench:
         n = 512
         big = torch.rand(1, n, 384, 384, device=dev)
         sh = torch.rand(n, 2, device=dev) * 2 - 1
-        ms = self.timed(lambda i: hb.lanczos_shift(big, sh, p=5), 20)
+        ms = self.timed(lambda i: hb.lanczos_shift(big, sh, p=5), 200, warm=20)
         gbps = n * LANCZOS_BYTES / ms / 1e6
         out["lanczos"] = {"GBps": gbps, "frac": gbps / hbm, "ms": ms, "images": n, "bytes_per_image": LANCZOS_BYTES,
                           "traffic": self._scoring_traffic("lanczos_shift7_kernel", n)}
         srb, hrb = big[0], torch.rand(n, 384, 384, device=dev)
         hmb = (torch.rand(n, 384, 384, device=dev) > 0.1).float()
-        ms = self.timed(lambda i: hb.shift_cPSNR_argmax(srb, hrb, hmb), 10)
+        ms = self.timed(lambda i: hb.shift_cPSNR_argmax(srb, hrb, hmb), 40, warm=5)
         gbps = n * CPSNR_BYTES / ms / 1e6
         out["cpsnr"] = {"GBps_algorithmic": gbps, "frac": gbps / hbm, "ms": ms, "imagesets": n,
                         "bytes_per_imageset": CPSNR_BYTES, "imagesets_per_s": n / ms * 1e3,
@@ -503,6 +504,53 @@ class Bench:
         per_call = sum((float(r["rd"]) + float(r["wr"])) * 1e9 for r in rows) / max(1, doc.get("calls", 1) if isinstance(doc, dict) else 1)
         return {"dram_bytes_per_call": per_call, "dram_bytes_per_unit": per_call / (doc.get("units", units) if isinstance(doc, dict) else units),
                 "source": "profiles/r02_ncu_scoring_summary.json"}
+
+    # ---- disk -> SR: the file formats on both ends around the device path
+    def io_leg(self, n_sets=64, l=16, s=128):
+        import shutil
+        import tempfile
+        import numpy as np
+        from highres_net_b200 import imageset_io as io
+        from highres_net_b200.predict import collate_device, img_as_uint_u16
+        torch, dev, net = self.torch, self.dev, self.net
+        root = tempfile.mkdtemp(prefix="hrn_io_")
+        try:
+            rng = np.random.RandomState(0)
+            dirs = []
+            base = (rng.rand(l, s, s) * 0.5 * 65535).astype(np.uint16)
+            qm = np.full((l, s, s), 255, np.uint16)
+            for i in range(n_sets):                     # synthetic Proba-V-shaped imagesets: L views of s x s, 16-bit PNG
+                d = os.path.join(root, f"imgset{i:04d}")
+                os.makedirs(d)
+                views = base + rng.randint(0, 2000, size=(l, 1, 1)).astype(np.uint16)
+                io.write_png_u16([os.path.join(d, f"LR{v:03d}.png") for v in range(l)], views)
+                io.write_png_u16([os.path.join(d, f"QM{v:03d}.png") for v in range(l)], qm)
+                io.write_png_u16([os.path.join(d, "SM.png")], np.full((1, 3 * s, 3 * s), 255, np.uint16))
+                dirs.append(d)
+            io.save_clearance_scores(dirs)
+            ds = io.ImagesetDataset(dirs, {"create_patches": False, "patch_size": 64}, raw16=True)
+            lr_bytes = sum(os.path.getsize(os.path.join(d, f)) for d in dirs for f in os.listdir(d) if f.startswith("LR"))
+            t0 = time.perf_counter()
+            sets = [ds[i] for i in range(n_sets)]       # PNG decode on the native thread pool, clearance order
+            t_read = time.perf_counter() - t0
+            out_dir = os.path.join(root, "sr")
+            os.makedirs(out_dir)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for b0 in range(0, n_sets, 32):
+                group = [ds[i] for i in range(b0, min(n_sets, b0 + 32))]
+                lrs, alphas, _, _, names = collate_device(group, l, dev)
+                sr16 = img_as_uint_u16(net(lrs, alphas)[:, 0]).cpu()
+                io.write_png_u16([os.path.join(out_dir, n + ".png") for n in names], sr16)
+            t_all = time.perf_counter() - t0
+            del sets
+            return {"imagesets": n_sets, "views_per_imageset": l, "lr_png_bytes": lr_bytes, "host_threads": os.cpu_count(),
+                    "png_decode_views_per_s": n_sets * l / t_read, "png_decode_MBps_decoded": n_sets * l * s * s * 2 / t_read / 1e6,
+                    "disk_to_sr_png_imagesets_per_s": n_sets / t_all,
+                    "what": "16-bit PNG views on local disk -> native threaded decode -> pinned uint16 -> hrn_collate -> HRNet -> "
+                            "img_as_uint on the device -> native PNG encode of the 384x384 SR (DataLoader.py:73-148, predict.py:161-194)"}
+        finally:
+            shutil.rmtree(root, ignore_errors=True)
 
     # ---- the reference algorithm through PyTorch eager + cuDNN on this GPU (SURVEY.md sections 2a / 8d)
     def gpu_baseline_leg(self):
@@ -575,6 +623,8 @@ def main():
         extras["scoring"] = bench.scoring_leg()
         if rank == 0:
             extras["gpu_baseline"] = bench.gpu_baseline_leg()
+            if world == 1:
+                extras["io"] = bench.io_leg()
         bench.sync_all()
 
     if rank == 0:

@@ -40,6 +40,13 @@ SYMBOLS = {
     "hrn_forward_host_wait": (c_int32, [c_void_p, c_int64]),
     "hrn_u16_to_unit_float": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),
     "hrn_unit_float_to_u16": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "hrn_collate": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "hrn_png_info": (c_int32, [c_char_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
+    "hrn_png_read_gray_u16": (c_int32, [POINTER(c_char_p), c_int32, c_int32, c_int32, c_void_p, c_int32]),
+    "hrn_png_write_gray_u16": (c_int32, [POINTER(c_char_p), c_int32, c_int32, c_int32, c_void_p, c_int32]),
+    "hrn_clearance_scores": (c_int32, [POINTER(c_char_p), c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "hrn_clearance_order": (c_int32, [c_void_p, c_int32, c_void_p]),
+    "hrn_zip_store": (c_int32, [c_char_p, POINTER(c_char_p), POINTER(c_char_p), c_int32]),
     "hrn_lanczos_shift": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                     c_int32, c_void_p, c_void_p]),
     "hrn_lanczos_taps": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),

@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libhrn_b200.so")
-SOURCES = ["api.cu", "conv3x3_umma.cu", "resblock64_umma.cu", "conv_init_umma.cu", "decoder_umma.cu", "pointwise.cu", "scoring.cu", "shiftnet.cu"]
+SOURCES = ["api.cu", "conv3x3_umma.cu", "resblock64_umma.cu", "conv_init_umma.cu", "decoder_umma.cu", "pointwise.cu", "scoring.cu", "shiftnet.cu", "imageset_io.cu"]
 HEADERS = ["internal.h", "ptx.cuh", "umma_common.cuh", "strips.cuh", os.path.join("..", "..", "include", "hrn_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -62,7 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(res.stdout + res.stderr)
             raise RuntimeError(f"nvcc failed on {src}")
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart"]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart", "-lz"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -847,6 +847,19 @@ int32_t hrn_unit_float_to_u16(const float* src, int64_t n, uint16_t* dst, int32_
     return n == 0 ? 0 : hrn::unit_float_to_u16_launch(src, static_cast<size_t>(n), dst, out_of_range, static_cast<cudaStream_t>(stream));
 }
 
+int32_t hrn_collate(const void* packed, int32_t packed_is_u16, const int32_t* offsets, int32_t B, int32_t min_L, int32_t H,
+                    int32_t W, float* lrs, float* alphas, void* stream) {
+    if (packed == nullptr || offsets == nullptr || lrs == nullptr || alphas == nullptr) {
+        set_error("hrn_collate: null pointer");
+        return -1;
+    }
+    if (B <= 0 || min_L <= 0 || H <= 0 || W <= 0) {
+        set_error("hrn_collate: empty shape (B=%d min_L=%d H=%d W=%d)", B, min_L, H, W);
+        return -1;
+    }
+    return hrn::collate_launch(packed, packed_is_u16, offsets, B, min_L, H, W, lrs, alphas, static_cast<cudaStream_t>(stream));
+}
+
 int32_t hrn_lanczos_shift(const float* img, const float* shift, int32_t Nb, int32_t C, int32_t H, int32_t W, int32_t p,
                           int32_t a, int32_t ntaps, float* out, void* stream) {
     if (img == nullptr || shift == nullptr || out == nullptr) {

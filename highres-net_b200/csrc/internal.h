@@ -110,6 +110,8 @@ int nhwc_bf16_to_nchw_f32_launch(const __nv_bfloat16* in, int n, int H, int W, i
                                  cudaStream_t s);
 int u16_to_unit_float_launch(const uint16_t* in, size_t n, float* out, cudaStream_t s);
 int unit_float_to_u16_launch(const float* in, size_t n, uint16_t* out, int* bad, cudaStream_t s);
+int collate_launch(const void* packed, int is_u16, const int* offsets, int B, int min_L, int H, int W, float* lrs,
+                   float* alphas, cudaStream_t s);
 // live-work lists (see pointwise.cu)
 int live_levels(int L);
 size_t live_scratch_bytes(int B, int L);

@@ -69,6 +69,46 @@ __global__ void unit_float_to_u16_kernel(const float* __restrict__ in, size_t n,
     if (__any_sync(0xffffffffu, any_bad) && (threadIdx.x & 31) == 0 && bad != nullptr) atomicOr(bad, 1);
 }
 
+// ------------------------------------------------------------------ ragged collate (utils.py:63-113) on the device
+// `packed` holds only the REAL views, imageset after imageset (views [offsets[b], offsets[b + 1]) belong to imageset b);
+// the kernel scatters them into the padded (B, min_L, H, W) float32 batch the model takes: the first
+// min(count_b, min_L) views are copied (uint16 views are scaled like DataLoader.py:195-198), the remaining planes are
+// zero-filled and their alpha is 0 (utils.py:89-95).  No padded byte ever crosses PCIe.  One block walks a slice of
+// one (imageset, view) plane; 128-bit stores when the plane size allows.
+template <typename T>
+__global__ void __launch_bounds__(256)
+collate_kernel(const T* __restrict__ packed, const int* __restrict__ offsets, int min_L, size_t hw, float* __restrict__ lrs,
+               float* __restrict__ alphas) {
+    const int v = blockIdx.y, b = blockIdx.z;
+    const int first = offsets[b], count = offsets[b + 1] - first;
+    const bool real = v < count;                                     // v < min_L by the grid
+    if (blockIdx.x == 0 && threadIdx.x == 0) alphas[static_cast<size_t>(b) * min_L + v] = real ? 1.0f : 0.0f;
+    float* dst = lrs + (static_cast<size_t>(b) * min_L + v) * hw;
+    const T* src = packed + static_cast<size_t>(first + (real ? v : 0)) * hw;
+    const size_t step = static_cast<size_t>(gridDim.x) * blockDim.x;
+    if ((hw & 3) == 0) {
+        for (size_t q = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; q < hw / 4; q += step) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (real) {
+                if (sizeof(T) == 4) {
+                    o = __ldg(reinterpret_cast<const float4*>(src) + q);
+                } else {
+                    const ushort4 u = __ldg(reinterpret_cast<const ushort4*>(src) + q);
+                    o = make_float4(__fdiv_rn(static_cast<float>(u.x), 65535.0f), __fdiv_rn(static_cast<float>(u.y), 65535.0f),
+                                    __fdiv_rn(static_cast<float>(u.z), 65535.0f), __fdiv_rn(static_cast<float>(u.w), 65535.0f));
+                }
+            }
+            reinterpret_cast<float4*>(dst)[q] = o;
+        }
+    } else {
+        for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < hw; i += step) {
+            float o = 0.0f;
+            if (real) o = sizeof(T) == 4 ? static_cast<float>(src[i]) : __fdiv_rn(static_cast<float>(src[i]), 65535.0f);
+            dst[i] = o;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ live-work lists
 // Which views and view pairs can reach the output?  HRNet.py:123-128 merges a pair as alice + alpha_bob * fuse(alice, bob),
 // so a pair whose bob has alpha = 0 contributes nothing but alice, and everything that only feeds such pairs (the
@@ -182,6 +222,28 @@ int unit_float_to_u16_launch(const float* in, size_t n, uint16_t* out, int* bad,
     const size_t want = (n + 255) / 256;
     if (bad != nullptr) HRN_CUDA_OK(cudaMemsetAsync(bad, 0, sizeof(int), s));
     unit_float_to_u16_kernel<<<static_cast<unsigned>(want < 148 * 16 ? want : 148 * 16), 256, 0, s>>>(in, n, out, bad);
+    note_launches(1);
+    HRN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int collate_launch(const void* packed, int is_u16, const int* offsets, int B, int min_L, int H, int W, float* lrs,
+                   float* alphas, cudaStream_t s) {
+    const size_t hw = static_cast<size_t>(H) * W;
+    if (B > 65535 || min_L > 65535) {
+        set_error("collate: B and min_L must not exceed 65535");
+        return -1;
+    }
+    if ((reinterpret_cast<uintptr_t>(packed) | reinterpret_cast<uintptr_t>(lrs)) & 15) {
+        set_error("collate: buffers must be 16-byte aligned");
+        return -1;
+    }
+    const size_t per_plane = (hw / 4 + 255) / 256;
+    dim3 grid(static_cast<unsigned>(per_plane < 1 ? 1 : (per_plane > 64 ? 64 : per_plane)), min_L, B);
+    if (is_u16)
+        collate_kernel<uint16_t><<<grid, 256, 0, s>>>(static_cast<const uint16_t*>(packed), offsets, min_L, hw, lrs, alphas);
+    else
+        collate_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(packed), offsets, min_L, hw, lrs, alphas);
     note_launches(1);
     HRN_CUDA_OK(cudaGetLastError());
     return 0;

@@ -1,7 +1,8 @@
 """Device-side mirror of the reference's inference caller (the "next" rows N1/N2 of SURVEY.md section 8f):
 
   * ``collateFunction(min_L)``       -- src/utils.py:49-113: pad / truncate every imageset to ``min_L`` views
-                                        (zero views, alpha = 0) and stack the batch;
+                                        (zero views, alpha = 0) and stack the batch; ``collate_device`` does it on the
+                                        GPU from the packed real views (``hrn_collate``): no padded bytes over PCIe;
   * ``get_sr_and_score(imset, model, min_L=16)`` -- src/predict.py:17-49: collate, HRNet forward, clip, shifted cPSNR;
   * ``load_model``, ``evaluate``, ``benchmark``, ``Model`` -- src/predict.py:83-158, 200-217: the harness around it
                                         (evaluate batches imagesets of equal shape; file readers / writers stay out).
@@ -53,11 +54,68 @@ def img_as_uint_u16(sr):
     return out
 
 
-class collateFunction:
-    """Util class to create padded batches of data (utils.py:49-113)."""
+def _packed_views(batch, min_L):
+    """The real views of a batch, truncated to min_L per imageset and packed back to back: (packed (sum_b n_b, H, W) host
+    tensor in the views' own dtype -- float32 or raw uint16 --, offsets (B + 1) int32)."""
+    views = [torch.as_tensor(imageset["lr"])[:min_L] for imageset in batch]
+    shapes = {tuple(v.shape[1:]) for v in views}
+    dtypes = {v.dtype for v in views}
+    if len(shapes) != 1 or len(dtypes) != 1:
+        raise ValueError("collate: all imagesets of a batch must share one view size and dtype")
+    dtype = dtypes.pop()
+    if dtype not in (torch.float32, torch.uint16):
+        views, dtype = [v.to(torch.float32) for v in views], torch.float32
+    counts = torch.tensor([0] + [v.shape[0] for v in views], dtype=torch.int32)
+    packed = torch.empty((int(counts.sum()),) + shapes.pop(), dtype=dtype, pin_memory=torch.cuda.is_available())
+    torch.cat(views, dim=0, out=packed)
+    return packed, torch.cumsum(counts, 0, dtype=torch.int32)
 
-    def __init__(self, min_L=32):
+
+def _targets(batch):
+    """hr / hr_map / names of a batch with the reference's rule (utils.py:97-111): as soon as one imageset has no 'hr',
+    the hr list stops growing and neither list is stacked."""
+    names = [imageset["name"] for imageset in batch]
+    maps = [torch.as_tensor(imageset["hr_map"]) if imageset["hr_map"] is not None else None for imageset in batch]
+    hrs = []
+    for imageset in batch:
+        if imageset["hr"] is None:
+            return hrs, maps, names
+        hrs.append(torch.as_tensor(imageset["hr"]))
+    return torch.stack(hrs, dim=0), torch.stack(maps, dim=0), names
+
+
+def collate_device(batch, min_L, device):
+    """utils.collateFunction (utils.py:63-113) ON THE DEVICE: only the real views are copied to the GPU (one packed,
+    pinned staging buffer, one H2D copy; float32, or raw uint16 at half the bytes), and ``hrn_collate`` scatters them
+    into the padded (B, min_L, H, W) float32 batch, zero-fills the padding planes and writes the alphas.  Returns
+    (lrs, alphas) on ``device`` plus (hr_batch, hm_batch, names) exactly like ``collateFunction``."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("collate_device needs a CUDA device: the B200 path has no CPU fallback")
+    packed, offsets = _packed_views(batch, min_L)
+    b, (h, w) = len(batch), packed.shape[1:]
+    with torch.cuda.device(device):
+        packed_dev = packed.to(device, non_blocking=True)
+        offsets_dev = offsets.to(device, non_blocking=True)
+        lrs = torch.empty((b, min_L, h, w), dtype=torch.float32, device=device)
+        alphas = torch.empty((b, min_L), dtype=torch.float32, device=device)
+        _lib.check(_lib.load().hrn_collate(packed_dev.data_ptr(), int(packed.dtype == torch.uint16), offsets_dev.data_ptr(),
+                                           b, int(min_L), h, w, lrs.data_ptr(), alphas.data_ptr(),
+                                           _lib.current_stream_ptr(device)), "hrn_collate")
+        packed_dev.record_stream(torch.cuda.current_stream(device))
+    hrs, hr_maps, names = _targets(batch)
+    return lrs, alphas, hrs, hr_maps, names
+
+
+class collateFunction:
+    """Util class to create padded batches of data (utils.py:49-113): same constructor, call convention and return
+    values.  With ``device=None`` (the reference's signature) the padded batch is built on the host -- one zero-initialised
+    (B, min_L, H, W) tensor that the real views are written into; with a CUDA ``device`` the batch is built by
+    ``collate_device`` and never exists on the host."""
+
+    def __init__(self, min_L=32, device=None):
         self.min_L = min_L
+        self.device = device
 
     def __call__(self, batch):
         return self.collateFunction(batch)
@@ -65,31 +123,20 @@ class collateFunction:
     def collateFunction(self, batch):
         """batch: list of imagesets (mappings with 'lr' (L, H, W), 'hr', 'hr_map', 'name') ->
         (padded_lr_batch (B, min_L, H, W), alpha_batch (B, min_L), hr_batch, hm_batch, names)."""
-        lr_batch, alpha_batch, hr_batch, hm_batch, isn_batch = [], [], [], [], []
-        train_batch = True
-        for imageset in batch:
-            lrs = torch.as_tensor(imageset["lr"])
-            n_views, h, w = lrs.shape
-            if n_views >= self.min_L:                               # truncate (utils.py:89-91)
-                lr_batch.append(lrs[:self.min_L])
-                alpha_batch.append(torch.ones(self.min_L))
-            else:                                                   # zero-pad, alpha = 0 (utils.py:92-95)
-                pad = torch.zeros(self.min_L - n_views, h, w, dtype=lrs.dtype)
-                lr_batch.append(torch.cat([lrs, pad], dim=0))
-                alpha_batch.append(torch.cat([torch.ones(n_views), torch.zeros(self.min_L - n_views)], dim=0))
-            hr = imageset["hr"]
-            if train_batch and hr is not None:
-                hr_batch.append(torch.as_tensor(hr))
-            else:
-                train_batch = False
-            hm_batch.append(torch.as_tensor(imageset["hr_map"]) if imageset["hr_map"] is not None else None)
-            isn_batch.append(imageset["name"])
-        padded_lr_batch = torch.stack(lr_batch, dim=0)
-        alpha_batch = torch.stack(alpha_batch, dim=0)
-        if train_batch:
-            hr_batch = torch.stack(hr_batch, dim=0)
-            hm_batch = torch.stack(hm_batch, dim=0)
-        return padded_lr_batch, alpha_batch, hr_batch, hm_batch, isn_batch
+        if self.device is not None:
+            return collate_device(batch, self.min_L, self.device)
+        packed, offsets = _packed_views(batch, self.min_L)
+        if packed.dtype == torch.uint16:
+            packed = packed.to(torch.float32) / 65535.0                 # DataLoader.py:195-198
+        offsets = offsets.tolist()
+        lrs = torch.zeros((len(batch), self.min_L) + tuple(packed.shape[1:]), dtype=packed.dtype)
+        alphas = torch.zeros((len(batch), self.min_L))
+        for i in range(len(batch)):
+            n = offsets[i + 1] - offsets[i]
+            lrs[i, :n] = packed[offsets[i]:offsets[i + 1]]
+            alphas[i, :n] = 1.0
+        hrs, hr_maps, names = _targets(batch)
+        return lrs, alphas, hrs, hr_maps, names
 
 
 def _device_of(model):
@@ -99,15 +146,15 @@ def _device_of(model):
 def get_sr_and_score(imset, model, min_L=16):
     """predict.py:17-49.  imset: one imageset (mapping) or a tuple of batches (lrs, alphas, hrs, hr_maps, names).
     Returns (sr: np.ndarray (3H, 3W) of the FIRST imageset, scPSNR: float or None)."""
+    device = _device_of(model)
+    if device.type != "cuda":
+        raise RuntimeError("the model must live on a CUDA device: the B200 path has no CPU fallback")
     if isinstance(imset, Mapping):
-        lrs, alphas, hrs, hr_maps, names = collateFunction(min_L=min_L)([imset])
+        lrs, alphas, hrs, hr_maps, names = collate_device([imset], min_L, device)
     elif isinstance(imset, tuple):
         lrs, alphas, hrs, hr_maps, names = imset
     else:
         raise TypeError("imset must be an imageset mapping or a tuple of batches")
-    device = _device_of(model)
-    if device.type != "cuda":
-        raise RuntimeError("the model must live on a CUDA device: the B200 path has no CPU fallback")
     sr_dev = model(lrs.float().to(device), alphas.float().to(device))[:, 0]
     sr = sr_dev.detach().cpu().numpy()[0]
     if len(hrs) > 0:
@@ -123,11 +170,11 @@ def get_sr_and_score(imset, model, min_L=16):
 def get_sr_and_score_batch(imsets, model, min_L=16):
     """New capability: all imagesets in ONE forward + ONE scoring launch.
     Returns (srs: np.ndarray (B, 3H, 3W), scores: np.ndarray (B,) float32 or None when there is no ground truth)."""
-    lrs, alphas, hrs, hr_maps, names = collateFunction(min_L=min_L)(list(imsets))
     device = _device_of(model)
     if device.type != "cuda":
         raise RuntimeError("the model must live on a CUDA device: the B200 path has no CPU fallback")
-    sr_dev = model(lrs.float().to(device), alphas.float().to(device))[:, 0]
+    lrs, alphas, hrs, hr_maps, names = collate_device(list(imsets), min_L, device)
+    sr_dev = model(lrs, alphas)[:, 0]
     scores = None
     if len(hrs) > 0:
         scores = shift_cPSNR(sr_dev, hrs.float().to(device), hr_maps.float().to(device), border_w=3, clip_sr=True)
@@ -171,8 +218,8 @@ def evaluate(model, train_dataset, val_dataset, test_dataset, min_L=16, batch_si
         pending = {}                                   # shape key -> imagesets waiting for a full batch
 
         def flush(group):
-            lrs, alphas, hrs, hr_maps, names = collateFunction(min_L=min_L)(group)
-            sr_dev = model(lrs.float().to(device), alphas.float().to(device))[:, 0]
+            lrs, alphas, hrs, hr_maps, names = collate_device(group, min_L, device)
+            sr_dev = model(lrs, alphas)[:, 0]
             if len(hrs) > 0:
                 sc = shift_cPSNR(sr_dev, hrs.float().to(device), hr_maps.float().to(device), border_w=3, clip_sr=True)
                 sc = sc.cpu().numpy().astype(np.float32)

@@ -101,6 +101,14 @@ int32_t hrn_forward_host_wait(hrn_handle* h, int64_t ticket);
 int32_t hrn_forward_host_u16(hrn_handle* h, const uint16_t* lrs_host, const float* alphas_host, int32_t B, int32_t L,
                              int32_t H, int32_t W, float* sr_host, void* stream);
 int32_t hrn_u16_to_unit_float(const uint16_t* src, int64_t n, float* dst, void* stream);
+/* Replaces utils.collateFunction (src/utils.py:63-113) on the device.  `packed` (DEVICE) holds only the real views of the
+ * batch, imageset after imageset: views [offsets[b], offsets[b + 1]) belong to imageset b (`offsets`: B + 1 int32 on the
+ * DEVICE; float32 planes of H * W, or raw uint16 planes when packed_is_u16 != 0, which are scaled like
+ * DataLoader.py:195-198).  Writes lrs (B, min_L, H, W) float32: the first min(count_b, min_L) views of every imageset
+ * (truncation, utils.py:89-91), zero planes after them (utils.py:92-95), and alphas (B, min_L) = 1 for real views, 0 for
+ * padding -- the two arguments of hrn_forward.  Only real views ever cross PCIe. */
+int32_t hrn_collate(const void* packed, int32_t packed_is_u16, const int32_t* offsets, int32_t B, int32_t min_L, int32_t H,
+                    int32_t W, float* lrs, float* alphas, void* stream);
 /* The way out (predict.py:176, generate_submission_file: sr = skimage.img_as_uint(sr) before io.imsave): float32 in
  * [-1, 1] -> uint16 = clip(rint(x * 65535 in fp32), 0, 65535), round half to even, on DEVICE pointers (n elements).
  * *out_of_range (device int32, may be NULL) is set to 1 if any value lies outside [-1, 1] (skimage raises there). */
@@ -179,6 +187,25 @@ int32_t hrn_scoring_debug_set(const char* knob, int32_t value);
 #define HRN_PROF_CLASSES 9
 int32_t hrn_profile_begin(hrn_handle* h);
 int32_t hrn_profile_end(hrn_handle* h, double* ms, double* flops, int64_t* launches);
+
+/* ---- The file formats on both ends of the path; host code, no GPU involved, `threads` = 0 means all
+ * host cores.  PNG: non-interlaced greyscale, bit depth 1/2/4/8/16 (what the Proba-V files are).
+ * hrn_png_info: header of one file.  hrn_png_read_gray_u16: decodes n files of height x width into dst
+ * (n, height, width) uint16 -- caller-owned, e.g. pinned memory that hrn_forward_host_u16 / hrn_collate then take -- with
+ * the sample values as stored (0..65535 for 16-bit views, 0..255 / 0..1 for 8- / 1-bit status maps); replaces the
+ * io.imread loops of DataLoader.py:134-140.  hrn_clearance_scores: sum of every QM status map, replaces
+ * save_clearance.py:13-27.  hrn_clearance_order: the view order of DataLoader.py:128-131, np.argsort(clearances)[::-1]
+ * (equal scores by descending index).  hrn_png_write_gray_u16: n images (n, height, width) uint16 -> 16-bit PNG files,
+ * replaces io.imsave of predict.py:181; hrn_zip_store: the stored archive of predict.py:186-195 (ZipFile(mode='w')). */
+int32_t hrn_png_info(const char* path, int32_t* width, int32_t* height, int32_t* bit_depth, int32_t* color_type);
+int32_t hrn_png_read_gray_u16(const char* const* paths, int32_t n, int32_t height, int32_t width, uint16_t* dst,
+                              int32_t threads);
+int32_t hrn_png_write_gray_u16(const char* const* paths, int32_t n, int32_t height, int32_t width, const uint16_t* src,
+                               int32_t threads);
+int32_t hrn_clearance_scores(const char* const* qm_paths, int32_t n, int32_t height, int32_t width, int32_t threads,
+                             double* scores);
+int32_t hrn_clearance_order(const double* clearances, int32_t n, int32_t* order);
+int32_t hrn_zip_store(const char* zip_path, const char* const* files, const char* const* arcnames, int32_t n);
 
 /* Number of kernels launched by this library (all handles) since load; bench.py reports the delta. */
 int64_t hrn_kernel_launch_count(void);

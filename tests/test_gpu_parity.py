@@ -1177,3 +1177,70 @@ def test_sharded_forward_and_score_over_nccl():
     results = mgr.dict()
     mp.spawn(_nccl_worker, args=(2, port, results), nprocs=2, join=True)
     assert dict(results) == {0: True, 1: True}
+
+
+# ---------------------------------------------------------------------------- N2 / N4: ragged collate on the device, file formats
+@pytest.mark.parametrize("raw16", [False, True])
+@pytest.mark.parametrize("min_l", [1, 4, 9, 16])
+def test_collate_device_equals_host_collate(hb, dev, raw16, min_l):
+    """hrn_collate (utils.py:63-113 on the device, only real views cross PCIe) against the host mirror: bit-exact
+    padded batch and alphas, truncation at min_L, zero planes for the padding, uint16 views scaled like the DataLoader."""
+    from highres_net_b200.predict import collateFunction, collate_device
+    rng = np.random.RandomState(7 + min_l)
+    batch = []
+    for i, n in enumerate((3, 12, 9, 1, 16, 20)):
+        lr = (rng.rand(n, 20, 20) * 65535).astype(np.uint16) if raw16 else rng.rand(n, 20, 20).astype(np.float32)
+        batch.append({"name": f"s{i}", "lr": torch.from_numpy(lr), "hr": torch.rand(60, 60), "hr_map": torch.ones(60, 60)})
+    ref_lrs, ref_alphas, ref_hr, ref_hm, ref_names = collateFunction(min_L=min_l)(batch)
+    before = hb.kernel_launch_count()
+    lrs, alphas, hrs, hms, names = collate_device(batch, min_l, dev)
+    assert hb.kernel_launch_count() == before + 1 and lrs.is_cuda and alphas.is_cuda
+    assert torch.equal(lrs.cpu(), ref_lrs) and torch.equal(alphas.cpu(), ref_alphas)
+    assert torch.equal(hrs, ref_hr) and torch.equal(hms, ref_hm) and names == ref_names
+    via_class = collateFunction(min_L=min_l, device=dev)(batch)
+    assert torch.equal(via_class[0], lrs) and torch.equal(via_class[1], alphas)
+
+
+def test_collate_device_odd_plane_size_and_errors(hb, dev):
+    from highres_net_b200.predict import collateFunction, collate_device
+    batch = [{"name": "a", "lr": torch.rand(2, 5, 7), "hr": None, "hr_map": None},
+             {"name": "b", "lr": torch.rand(4, 5, 7), "hr": None, "hr_map": None}]
+    lrs, alphas, hrs, hms, _ = collate_device(batch, 3, dev)                  # 35 pixels per plane: scalar path
+    ref = collateFunction(min_L=3)(batch)
+    assert torch.equal(lrs.cpu(), ref[0]) and torch.equal(alphas.cpu(), ref[1]) and hrs == [] and hms == [None, None]
+    with pytest.raises(ValueError):
+        collate_device(batch + [{"name": "c", "lr": torch.rand(2, 6, 6), "hr": None, "hr_map": None}], 3, dev)
+    with pytest.raises(RuntimeError):
+        collate_device(batch, 3, "cpu")
+
+
+def test_disk_to_submission_through_every_io_end(hb, net, dev, tmp_path):
+    """The whole N4 chain on the PIL-written fixture: save_clearance -> ImagesetDataset (native PNG decode, clearance
+    order, raw uint16 views) -> collate on the device -> HRNet -> img_as_uint on the device -> native PNG encode ->
+    stored submission.zip; each written image equals img_as_uint of the SR the float32 path gives."""
+    import os
+    import shutil
+    import zipfile
+    from highres_net_b200 import imageset_io as io
+    from highres_net_b200.predict import get_sr_and_score, img_as_uint_u16
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "imgsets")
+    dirs = []
+    for chan, name in (("RED", "imgset0001"), ("RED", "imgset0002"), ("NIR", "imgset0003")):
+        dst = tmp_path / name
+        shutil.copytree(os.path.join(src, chan, name), dst)
+        dirs.append(str(dst))
+    io.save_clearance_scores(dirs)
+    cfg = {"create_patches": False, "patch_size": 8}
+    raw_ds = io.ImagesetDataset(dirs, cfg, raw16=True)
+    f32_ds = io.ImagesetDataset(dirs, cfg)
+    out = str(tmp_path / "submission")
+    archive = io.generate_submission_file(net, raw_ds, out=out, min_L=4, batch_size=2)
+    with zipfile.ZipFile(archive) as z:
+        assert z.testzip() is None and sorted(z.namelist()) == ["imgset0001.png", "imgset0002.png", "imgset0003.png"]
+    for i, d in enumerate(dirs):
+        name = os.path.basename(d)
+        sr, score = get_sr_and_score(f32_ds[i], net, min_L=4)                 # the reference-shaped float32 route
+        want = img_as_uint_u16(torch.from_numpy(sr).to(dev)).cpu().numpy()
+        got = io.read_png_u16([os.path.join(out, name + ".png")], pin=False)[0].numpy()
+        assert got.shape == (72, 72) and np.array_equal(got, want), name
+        assert (score is None) == (name == "imgset0003")
