@@ -893,6 +893,14 @@ int32_t hrn_scoring_debug_set(const char* knob, int32_t value) {
         hrn::g_cpsnr_generic = value != 0;
         return 0;
     }
+    if (knob != nullptr && strcmp(knob, "cpsnr_window_v1") == 0) {
+        hrn::g_cpsnr_window_v1 = value != 0;
+        return 0;
+    }
+    if (knob != nullptr && strcmp(knob, "cpsnr_chunk") == 0) {
+        hrn::g_cpsnr_chunk = value;
+        return 0;
+    }
     set_error("hrn_scoring_debug_set: unknown knob");
     return -1;
 }

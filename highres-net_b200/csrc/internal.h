@@ -125,7 +125,7 @@ int lanczos_shift_launch(const float* img, const float* shift, int nb, int c, in
 int lanczos_taps_launch(const float* d, int n, int a, int ntaps, float* out, cudaStream_t s);
 int clear_loss_launch(const float* sr, const float* hr, const float* hm, int B, int H, int W, int metric, float* out,
                       cudaStream_t s);
-extern int g_cpsnr_generic;   // test knob (hrn_scoring_debug_set)
+extern int g_cpsnr_generic, g_cpsnr_window_v1, g_cpsnr_chunk;   // test knobs (hrn_scoring_debug_set)
 int shift_cpsnr_launch(const float* sr, const float* hr, const float* hm, int B, int H, int W, int border,
                        int clip_sr, float* best_db, int32_t* best_site, float* site_db, cudaStream_t s);
 

@@ -507,6 +507,263 @@ cpsnr_window_kernel(const float* __restrict__ sr, const float* __restrict__ hr, 
     }
 }
 
+// ------------------------------------------------------------------ 49-site window kernel, third generation
+// Same sweep and the same fp32 element arithmetic in the same order as cpsnr_window_kernel (so the site tables are
+// bit-identical for 0/1 status maps), with two changes that attack what ncu showed -- an fp32-issue-bound kernel at 12
+// warps per SM:
+//   * the 7 row shifts are split over TWO one-warp blocks (x in [0, 4) and x in [4, 7), blockIdx.z): 16 / 12 instead of 49
+//     accumulator pairs per lane, 14-16 warps per SM instead of 12, and twice as many blocks for small batches;
+//   * Blackwell's packed fp32 pipe: the column shifts are processed in pairs (y, y + 1) with add/mul/fma.f32x2 (FADD2 /
+//     FMUL2 / FFMA2 -- per-lane IEEE results identical to the scalar instructions), the sr value enters as a broadcast
+//     operand.  y = 7 is a dummy lane of the last pair (its sums are dropped).  3 (pass 1) / 4 (pass 2) issue slots per
+//     TWO (pixel, site) terms instead of 2 / 4 per term.
+using f2 = unsigned long long;
+__device__ __forceinline__ f2 pk(float lo, float hi) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+    f2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+    f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+    f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// All terms of one hr row for the shifts xl in [xlo, xhi] (local to the block) and the columns c < ncol (CPRED) or all four.
+// A pair of adjacent hr / map columns (k, k + 1) is a 64-bit register pair only for even k (the halves of the loaded
+// float4s).  Even columns c therefore pair the shifts (y, y + 1) = (0,1) (2,3) (4,5) (6,7*) and odd columns pair
+// (-1*,0) (1,2) (3,4) (5,6): k = c + y is even in both cases (* = dummy lane, dropped at the flush), and the two kinds of
+// columns keep their own accumulators (acc[x][c & 1][..]), added when the block flushes.
+template <int PASS, int XN, bool CPRED>
+__device__ __forceinline__ void cw2_terms(f2 (&acc)[XN][2][4], f2 (*aux)[2][4], const float (&hw)[12], const float (&mw)[12],
+                                          const float (&svw)[XN][4], int xlo, int xhi, int ncol) {
+#pragma unroll
+    for (int x = 0; x < XN; ++x) {
+        if (x < xlo || x > xhi) continue;                            // warp-uniform: sr crop row h - x lies outside this band
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (CPRED && c >= ncol) continue;
+            const f2 s2 = pk(svw[x][c], svw[x][c]);
+#pragma unroll
+            for (int yp = 0; yp < 4; ++yp) {
+                const int k = (c & ~1) + 2 * yp;                     // even: columns (k, k + 1) <-> y = k - c, k + 1 - c
+                const f2 d2 = sub2(pk(hw[k], hw[k + 1]), s2);        // diff = hr - sr            (Evaluator.py:35)
+                const f2 m2 = pk(mw[k], mw[k + 1]);
+                if (PASS == 1) {
+                    acc[x][c & 1][yp] = fma2(d2, m2, acc[x][c & 1][yp]);      // sum(diff * hr_map)   (Evaluator.py:36)
+                } else {
+                    const f2 t2 = mul2(sub2(d2, aux[x][c & 1][yp]), m2);      // (diff - bias) * hr_map (Evaluator.py:37)
+                    acc[x][c & 1][yp] = fma2(t2, t2, acc[x][c & 1][yp]);
+                }
+            }
+        }
+    }
+}
+
+template <int PASS, int X0, int XN>
+__device__ __forceinline__ void cpsnr_window2_body(const float* __restrict__ sr, const float* __restrict__ hr,
+                                                   const float* __restrict__ hm, const CpGeom& g, int clip_sr,
+                                                   const float* __restrict__ bias, double* __restrict__ partial,
+                                                   float (*stage)[33], float (*edge_n)[32], f2 (*aux)[2][4]) {
+    constexpr int NS = XN * CW_S;                                 // sites of this block: x in [X0, X0 + XN), all y
+    constexpr int NQ = PASS == 1 ? 2 * NS : NS;
+    constexpr int NK = (NQ + 31) / 32;
+    const int lane = threadIdx.x;
+    const int set = blockIdx.y;
+    const int band = blockIdx.x / g.col_blocks, cb = blockIdx.x % g.col_blocks;
+    const int j0 = cb * CW_COLS + lane * 4;                      // first crop column of this lane
+    const int ncol = min(4, g.size - j0);                        // <= 0: idle lane
+    const bool all_full = __all_sync(0xffffffffu, ncol == 4);
+    const size_t plane = static_cast<size_t>(g.H) * g.W;
+    const float* srp = sr + set * plane + static_cast<size_t>(g.border) * g.W + j0;
+    const float* hrp = hr + set * plane + j0;
+    const float* hmp = hm + set * plane + j0;
+    const int i0 = band * g.band_rows, i1 = min(g.size, i0 + g.band_rows);
+    const int h_begin = i0 + X0, h_end = i1 + X0 + XN - 1;       // hr rows that meet sr crop rows [i0, i1) at these shifts
+    const bool q_ok[3] = {j0 + 4 <= g.W, j0 + 8 <= g.W, j0 + 12 <= g.W};
+
+    // acc[x - X0][0][yp] = shifts (2 yp, 2 yp + 1) summed over the even columns, acc[x - X0][1][yp] = shifts (2 yp - 1, 2 yp)
+    // over the odd columns (see cw2_terms).  PASS 2: the sites' biases sit in shared memory as the same pairs (broadcast
+    // LDS.64) instead of 32 more registers per lane.
+    f2 acc[XN][2][4];
+    float n_all[CW_S];                           // PASS 1: sum of rs over the rows that count for every x of this block
+#pragma unroll
+    for (int y = 0; y < CW_S; ++y) n_all[y] = 0.0f;
+#pragma unroll
+    for (int x = 0; x < XN; ++x)
+#pragma unroll
+        for (int yp = 0; yp < 4; ++yp) acc[x][0][yp] = acc[x][1][yp] = pk(0.0f, 0.0f);
+    if (PASS == 2) {
+        if (lane < XN * 8) {
+            const int x = lane >> 3, odd = (lane >> 2) & 1, yp = lane & 3;
+            const int y0 = 2 * yp - odd, y1 = y0 + 1;                // the two shifts of this pair; -1 and 7 are dummies
+            const float* b = bias + (set * CW_S + X0 + x) * CW_S;
+            aux[x][odd][yp] = pk(y0 >= 0 ? b[y0] : 0.0f, y1 < CW_S ? b[y1] : 0.0f);
+        }
+        __syncwarp();
+    }
+    if (PASS == 1) {
+#pragma unroll
+        for (int q = 0; q < NS; ++q) edge_n[q][lane] = 0.0f;
+    }
+    double tot[NK];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) tot[k] = 0.0;
+
+    auto flush = [&]() {
+#pragma unroll
+        for (int x = 0; x < XN; ++x) {
+            float ev[8], od[8];                                      // ev[y] for y = 0..7, od[y + 1] for y = -1..6
+#pragma unroll
+            for (int yp = 0; yp < 4; ++yp) {
+                upk(acc[x][0][yp], ev[2 * yp], ev[2 * yp + 1]);
+                upk(acc[x][1][yp], od[2 * yp], od[2 * yp + 1]);
+                acc[x][0][yp] = acc[x][1][yp] = pk(0.0f, 0.0f);
+            }
+#pragma unroll
+            for (int y = 0; y < CW_S; ++y) {
+                const int q = x * CW_S + y;
+                const float a = ev[y] + od[y + 1];                   // even columns + odd columns
+                if (PASS == 1) {
+                    stage[q * 2][lane] = n_all[y] + edge_n[q][lane];
+                    stage[q * 2 + 1][lane] = a;
+                    edge_n[q][lane] = 0.0f;
+                } else {
+                    stage[q][lane] = a;
+                }
+            }
+        }
+        if (PASS == 1) {
+#pragma unroll
+            for (int y = 0; y < CW_S; ++y) n_all[y] = 0.0f;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+            const int q = lane + 32 * k;
+            if (q < NQ) {
+                double a = 0.0;
+#pragma unroll 8
+                for (int l = 0; l < 32; ++l) a += static_cast<double>(stage[q][l]);
+                tot[k] += a;
+            }
+        }
+        __syncwarp();
+    };
+
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto load_row = [&](int h, CwRow& r) {
+        const size_t off = static_cast<size_t>(h) * g.W;
+        const bool in = h < h_end;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            r.h[q] = (in && q_ok[q]) ? __ldg(reinterpret_cast<const float4*>(hrp + off) + q) : zero4;
+            r.m[q] = (in && q_ok[q]) ? __ldg(reinterpret_cast<const float4*>(hmp + off) + q) : zero4;
+        }
+        const int i = h - X0;                                        // the sr crop row that enters the window with hr row h
+        const bool sin = i < i1;                                     // (i >= i0 by the loop bounds)
+        const size_t soff = static_cast<size_t>(i) * g.W;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) r.s[q] = (sin && q_ok[q]) ? __ldg(reinterpret_cast<const float4*>(srp + soff) + q) : zero4;
+    };
+
+    float svw[XN][4];                                                // svw[x - X0] = sr crop row h - x (columns j0 .. j0 + 3)
+#pragma unroll
+    for (int x = 0; x < XN; ++x)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) svw[x][c] = 0.0f;
+    int since_flush = 0;
+    for (int h = h_begin; h < h_end; ++h) {
+        // No software prefetch here: at 16 one-warp blocks per SM the other warps cover the L1 / L2 latency, and the 32
+        // registers a prefetched row costs would spill.
+        CwRow cur;
+        load_row(h, cur);
+        float hw[12], mw[12];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            hw[4 * q] = cur.h[q].x, hw[4 * q + 1] = cur.h[q].y, hw[4 * q + 2] = cur.h[q].z, hw[4 * q + 3] = cur.h[q].w;
+            mw[4 * q] = cur.m[q].x, mw[4 * q + 1] = cur.m[q].y, mw[4 * q + 2] = cur.m[q].z, mw[4 * q + 3] = cur.m[q].w;
+        }
+#pragma unroll
+        for (int x = XN - 1; x > 0; --x)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) svw[x][c] = svw[x - 1][c];
+        svw[0][0] = cur.s[0].w, svw[0][1] = cur.s[1].x, svw[0][2] = cur.s[1].y, svw[0][3] = cur.s[1].z;   // crop column j0 + c = image column j0 + c + 3
+        if (clip_sr) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) svw[0][c] = fminf(fmaxf(svw[0][c], 0.0f), 1.0f);
+        }
+        // sr crop rows i = h - x of this band: x in [xlo, xhi] (clamped to this block's shifts)
+        const int xlo = max(X0, h - i1 + 1), xhi = min(X0 + XN - 1, h - i0);
+        if (PASS == 1) {
+            float rs[CW_S];                                          // sum of the map over this lane's columns, per column shift
+#pragma unroll
+            for (int y = 0; y < CW_S; ++y) {
+                float r = 0.0f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) r += (all_full || c < ncol) ? mw[c + y] : 0.0f;      // n_clear (Evaluator.py:34)
+                rs[y] = r;
+            }
+            if (xlo == X0 && xhi == X0 + XN - 1) {
+#pragma unroll
+                for (int y = 0; y < CW_S; ++y) n_all[y] += rs[y];
+            } else {
+                for (int x = xlo; x <= xhi; ++x)
+#pragma unroll
+                    for (int y = 0; y < CW_S; ++y) edge_n[(x - X0) * CW_S + y][lane] += rs[y];
+            }
+        }
+        if (all_full)
+            cw2_terms<PASS, XN, false>(acc, aux, hw, mw, svw, xlo - X0, xhi - X0, 4);
+        else
+            cw2_terms<PASS, XN, true>(acc, aux, hw, mw, svw, xlo - X0, xhi - X0, ncol);
+        if (++since_flush == CW_FLUSH) {
+            flush();
+            since_flush = 0;
+        }
+    }
+    if (since_flush > 0) flush();
+    double* dst = partial + ((static_cast<size_t>(set) * g.blocks_per_set + blockIdx.x) * CW_SITES + X0 * CW_S) * 2;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+        const int q = lane + 32 * k;
+        if (q < NQ) {
+            if (PASS == 1) {
+                dst[q] = tot[k];
+            } else {
+                dst[2 * q] = tot[k];
+                dst[2 * q + 1] = 0.0;
+            }
+        }
+    }
+}
+
+constexpr int CW2_X_SPLIT = 4;                 // blockIdx.z = 0: x in [0, 4); 1: x in [4, 7)
+template <int PASS>
+__global__ void __launch_bounds__(32, 16)
+cpsnr_window2_kernel(const float* __restrict__ sr, const float* __restrict__ hr, const float* __restrict__ hm, CpGeom g,
+                     int clip_sr, const float* __restrict__ bias, double* __restrict__ partial) {
+    constexpr int NQ_MAX = (PASS == 1 ? 2 : 1) * CW2_X_SPLIT * CW_S;
+    __shared__ float stage[NQ_MAX][33];
+    __shared__ float edge_n[PASS == 1 ? CW2_X_SPLIT * CW_S : 1][32];
+    __shared__ f2 aux[CW2_X_SPLIT][2][4];
+    if (blockIdx.z == 0)
+        cpsnr_window2_body<PASS, 0, CW2_X_SPLIT>(sr, hr, hm, g, clip_sr, bias, partial, stage, edge_n, aux);
+    else
+        cpsnr_window2_body<PASS, CW2_X_SPLIT, CW_S - CW2_X_SPLIT>(sr, hr, hm, g, clip_sr, bias, partial, stage, edge_n, aux);
+}
+
 // One block per imageset, one thread per site.  MODE 1: bias = sum(d*m) / n.  MODE 2: scores + argmax.
 template <int MODE>
 __global__ void cpsnr_finalize_kernel(const double* __restrict__ partial, CpGeom g, float* __restrict__ bias,
@@ -821,6 +1078,10 @@ int lanczos_taps_launch(const float* d, int n, int a, int ntaps, float* out, cud
 }
 
 int g_cpsnr_generic = 0;
+int g_cpsnr_window_v1 = 0;     // test knob: 1 = second-generation window kernel (scalar fp32, all 49 sites per warp)
+int g_cpsnr_chunk = 0;         // test knob: imagesets per pass-1 / pass-2 round trip (0 = automatic, by L2 size)
+constexpr size_t CP_L2_BUDGET = 56ull << 20;   // bytes of sr + hr + map per chunk that pass 2 should still find in the 126 MB L2
+constexpr int CW2_TARGET_WARPS = 148 * 14;
 
 int shift_cpsnr_launch(const float* sr, const float* hr, const float* hm, int B, int H, int W, int border,
                        int clip_sr, float* best_db, int32_t* best_site, float* site_db, cudaStream_t s) {
@@ -871,10 +1132,21 @@ int shift_cpsnr_launch(const float* sr, const float* hr, const float* hm, int B,
     g.vec_ok = (W % 4 == 0) && (((reinterpret_cast<uintptr_t>(sr) | reinterpret_cast<uintptr_t>(hr) | reinterpret_cast<uintptr_t>(hm)) & 15) == 0);
     // border_w = 3 on 16-byte aligned rows (every case the reference produces) takes the 49-site window kernel
     const bool window = g.S == CW_S && g.vec_ok && g_cpsnr_generic == 0;
+    const bool window2 = window && g_cpsnr_window_v1 == 0;
+    // Both passes read sr, hr and the map.  A batch that does not fit in L2 is therefore processed in chunks of imagesets:
+    // pass 1 -> bias -> pass 2 of one chunk run back to back, so that pass 2 finds the chunk's 3 planes per imageset in
+    // L2 and every byte comes from HBM once (512 imagesets in one go read everything twice: ncu, profiles/).
+    const size_t set_bytes = 3 * static_cast<size_t>(H) * W * sizeof(float);
+    int chunk = B;
+    if (g_cpsnr_chunk > 0) chunk = g_cpsnr_chunk;
+    else if (window && set_bytes * B > CP_L2_BUDGET) chunk = static_cast<int>(CP_L2_BUDGET / set_bytes);
+    chunk = chunk < 1 ? 1 : (chunk > B ? B : chunk);
+    const int per_pass = chunk < B ? chunk : B;            // imagesets per launch: sizes the row bands
     if (window) {
         g.col_blocks = (g.size + CW_COLS - 1) / CW_COLS;
         // one-warp blocks, at most one full wave of them when the batch is small; a band is at least 8 rows
-        int want = CW_TARGET_WARPS / (B * g.col_blocks);
+        const int target = window2 ? CW2_TARGET_WARPS / 2 : CW_TARGET_WARPS;
+        int want = target / (per_pass * g.col_blocks);
         want = want < 1 ? 1 : (want > (g.size + 7) / 8 ? (g.size + 7) / 8 : want);
         g.band_rows = (g.size + want - 1) / want;
     } else {
@@ -892,25 +1164,38 @@ int shift_cpsnr_launch(const float* sr, const float* hr, const float* hm, int B,
     const size_t bias_bytes = static_cast<size_t>(B) * sites * sizeof(float);
     uint8_t* ws = nullptr;
     if (scratch_alloc(reinterpret_cast<void**>(&ws), partial_bytes + nclear_bytes + bias_bytes, s)) return -1;
-    double* partial = reinterpret_cast<double*>(ws);
-    double* nclear = reinterpret_cast<double*>(ws + partial_bytes);
-    float* bias = reinterpret_cast<float*>(ws + partial_bytes + nclear_bytes);
-    dim3 grid(g.blocks_per_set, B), block(CP_LANES, g.S);
-    if (window)
-        cpsnr_window_kernel<1><<<grid, 32, 0, s>>>(sr, hr, hm, g, clip_sr, nullptr, partial);
-    else if (g.S == 7)
-        cpsnr_pass_kernel<1, 7><<<grid, block, 0, s>>>(sr, hr, hm, g, clip_sr, nullptr, partial);
-    else
-        cpsnr_pass_kernel<1, 0><<<grid, block, 0, s>>>(sr, hr, hm, g, clip_sr, nullptr, partial);
-    cpsnr_finalize_kernel<1><<<B, 64, 0, s>>>(partial, g, bias, nclear, nullptr, nullptr, nullptr);
-    if (window)
-        cpsnr_window_kernel<2><<<grid, 32, 0, s>>>(sr, hr, hm, g, clip_sr, bias, partial);
-    else if (g.S == 7)
-        cpsnr_pass_kernel<2, 7><<<grid, block, 0, s>>>(sr, hr, hm, g, clip_sr, bias, partial);
-    else
-        cpsnr_pass_kernel<2, 0><<<grid, block, 0, s>>>(sr, hr, hm, g, clip_sr, bias, partial);
-    cpsnr_finalize_kernel<2><<<B, 64, 0, s>>>(partial, g, bias, nclear, best_db, best_site, site_db);
-    note_launches(4);
+    double* partial_all = reinterpret_cast<double*>(ws);
+    double* nclear_all = reinterpret_cast<double*>(ws + partial_bytes);
+    float* bias_all = reinterpret_cast<float*>(ws + partial_bytes + nclear_bytes);
+    const size_t plane = static_cast<size_t>(H) * W;
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = b0 + chunk <= B ? chunk : B - b0;
+        const float *sr_c = sr + b0 * plane, *hr_c = hr + b0 * plane, *hm_c = hm + b0 * plane;
+        double* partial = partial_all + static_cast<size_t>(b0) * g.blocks_per_set * sites * 2;
+        double* nclear = nclear_all + static_cast<size_t>(b0) * sites;
+        float* bias = bias_all + static_cast<size_t>(b0) * sites;
+        float* site_c = site_db != nullptr ? site_db + static_cast<size_t>(b0) * sites : nullptr;
+        dim3 grid(g.blocks_per_set, nb), grid2(g.blocks_per_set, nb, 2), block(CP_LANES, g.S);
+        if (window2)
+            cpsnr_window2_kernel<1><<<grid2, 32, 0, s>>>(sr_c, hr_c, hm_c, g, clip_sr, nullptr, partial);
+        else if (window)
+            cpsnr_window_kernel<1><<<grid, 32, 0, s>>>(sr_c, hr_c, hm_c, g, clip_sr, nullptr, partial);
+        else if (g.S == 7)
+            cpsnr_pass_kernel<1, 7><<<grid, block, 0, s>>>(sr_c, hr_c, hm_c, g, clip_sr, nullptr, partial);
+        else
+            cpsnr_pass_kernel<1, 0><<<grid, block, 0, s>>>(sr_c, hr_c, hm_c, g, clip_sr, nullptr, partial);
+        cpsnr_finalize_kernel<1><<<nb, 64, 0, s>>>(partial, g, bias, nclear, nullptr, nullptr, nullptr);
+        if (window2)
+            cpsnr_window2_kernel<2><<<grid2, 32, 0, s>>>(sr_c, hr_c, hm_c, g, clip_sr, bias, partial);
+        else if (window)
+            cpsnr_window_kernel<2><<<grid, 32, 0, s>>>(sr_c, hr_c, hm_c, g, clip_sr, bias, partial);
+        else if (g.S == 7)
+            cpsnr_pass_kernel<2, 7><<<grid, block, 0, s>>>(sr_c, hr_c, hm_c, g, clip_sr, bias, partial);
+        else
+            cpsnr_pass_kernel<2, 0><<<grid, block, 0, s>>>(sr_c, hr_c, hm_c, g, clip_sr, bias, partial);
+        cpsnr_finalize_kernel<2><<<nb, 64, 0, s>>>(partial, g, bias, nclear, best_db + b0, best_site + b0, site_c);
+        note_launches(4);
+    }
     HRN_CUDA_OK(cudaGetLastError());
     HRN_CUDA_OK(cudaFreeAsync(ws, s));
     return 0;

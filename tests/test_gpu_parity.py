@@ -656,9 +656,22 @@ def test_shift_cpsnr_window_kernel_vs_generic_and_oracle(hb, dev, b, s, kind):
         best_g, xy_g, tab_g = hb.shift_cPSNR_argmax(*args)
     finally:
         hb.scoring_debug_set("cpsnr_generic", 0)
+    # the second-generation window kernel (scalar fp32, 49 sites per warp) and the chunked pass-1 / pass-2 schedule
+    hb.scoring_debug_set("cpsnr_window_v1", 1)
+    try:
+        best_1, xy_1, tab_1 = hb.shift_cPSNR_argmax(*args)
+    finally:
+        hb.scoring_debug_set("cpsnr_window_v1", 0)
+    hb.scoring_debug_set("cpsnr_chunk", 2)
+    try:
+        best_c, xy_c, tab_c = hb.shift_cPSNR_argmax(*args)
+    finally:
+        hb.scoring_debug_set("cpsnr_chunk", 0)
+    assert torch.equal(xy_c, xy_w) and torch.equal(xy_1, xy_w)
+    assert np.abs(np.nan_to_num(tab_c.cpu().numpy() - tab_w.cpu().numpy(), nan=0.0, posinf=0.0, neginf=0.0)).max() <= CPSNR_KERNEL_GATE_DB
     ref_max, ref_arg, ref_sites = scoring_oracle.shift_cpsnr(sr, hr, hm)
-    tab_w, tab_g, ref_sites = tab_w.cpu().numpy(), tab_g.cpu().numpy(), ref_sites.T
-    for tab in (tab_w, tab_g):
+    tab_w, tab_g, tab_1, ref_sites = tab_w.cpu().numpy(), tab_g.cpu().numpy(), tab_1.cpu().numpy(), ref_sites.T
+    for tab in (tab_w, tab_g, tab_1):
         assert np.array_equal(np.isnan(tab), np.isnan(ref_sites))
         assert np.array_equal(np.isposinf(tab), np.isposinf(ref_sites))
         fin = np.isfinite(ref_sites)

@@ -1,0 +1,35 @@
+"""Same-box A/B of the shifted-cPSNR search: second-generation window kernel (scalar fp32, 49 sites per warp) against the
+third generation (x split over two warps, packed fp32x2), and the pass-1/pass-2 chunk size (L2 residency of pass 2).
+    python tools/cpsnr_ab2.py"""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import highres_net_b200 as hb
+dev = torch.device("cuda:0")
+def timed(fn, n):
+    for _ in range(5): fn()
+    torch.cuda.synchronize()
+    best = 1e9
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(4):
+        e0.record()
+        for _ in range(n): fn()
+        e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / n)
+    return best
+for n in (512, 32):
+    sr = torch.rand(n, 384, 384, device=dev); hr = torch.rand(n, 384, 384, device=dev); hm = (torch.rand(n, 384, 384, device=dev) > 0.1).float()
+    ref = None
+    for v1 in (1, 0):
+        for chunk in ((0, n, 12, 16, 24, 32, 48, 64) if n == 512 else (0,)):
+            hb.scoring_debug_set("cpsnr_window_v1", v1); hb.scoring_debug_set("cpsnr_chunk", chunk)
+            best, xy, tab = hb.shift_cPSNR_argmax(sr, hr, hm)
+            if ref is None: ref = (xy.clone(), tab.clone())
+            ms = timed(lambda: hb.shift_cPSNR_argmax(sr, hr, hm), 20 if n == 512 else 100)
+            print(json.dumps({"n": n, "kernel": "v2 scalar" if v1 else "v3 packed", "chunk": chunk, "ms": round(ms, 4),
+                              "GBps_alg": round(n * 1769472 / ms / 1e6, 1), "argmax_same": bool(torch.equal(xy, ref[0])),
+                              "max_db_diff": float((tab - ref[1]).abs().max())}), flush=True)
+hb.scoring_debug_set("cpsnr_window_v1", 0); hb.scoring_debug_set("cpsnr_chunk", 0)
+big = torch.rand(1, 512, 384, 384, device=dev); sh = torch.rand(512, 2, device=dev) * 2 - 1
+ms = timed(lambda: hb.lanczos_shift(big, sh, p=5), 100)
+print(json.dumps({"lanczos_512_ms": ms, "GBps": 512 * 1179648 / ms / 1e6}), flush=True)
