@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <set>
 #include <string>
 #include <vector>
@@ -66,6 +67,13 @@ struct hrn_handle {
     int strip_split = 0;               // ranges of the row space per CTA (0/1 = one contiguous range)
     int mcast = 1;                     // 128 -> 128 convs as cluster pairs with multicast A rows (0: plain launch, test knob)
     int fuse_resblock = 1;             // encoder ResidualBlocks as one launch each (resblock64_umma.cu) when W <= 128
+    int fuse_wave = 1;                 // fusion levels as one wavefront launch each (fuse_wave_umma.cu) when W <= 128
+    int wave_ring_rows = 16;           // rows per stream ring of the wavefront schedule (test knob, >= 8)
+    int wave_streams = 0;              // streams of the wavefront schedule (0 = sm_count / 5; test knob)
+    __nv_bfloat16* wave_ring[2] = {nullptr, nullptr};
+    size_t wave_ring_cap[2] = {0, 0};
+    uint32_t* wave_flags = nullptr;    // 16 levels x fuse_wave_flag_bytes()
+    size_t wave_flags_cap = 0;
     int host_chunks = 0;               // hrn_forward_host pipeline depth (0 = automatic)
     long long workspace_mb = 65536;    // cap on the activation workspace; larger batches are run in slices
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H streams of hrn_forward_host
@@ -181,8 +189,20 @@ int ensure_workspace(hrn_handle* h, int B, int L, int H, int W) {
     if (grow(reinterpret_cast<void**>(&h->anchor), &h->anchor_cap, static_cast<size_t>(B) * hw * sizeof(float))) return -1;
     if (grow(reinterpret_cast<void**>(&h->lists), &h->lists_cap, hrn::live_lists_ints(B, L) * sizeof(int))) return -1;
     if (grow(reinterpret_cast<void**>(&h->live_scratch), &h->live_scratch_cap, hrn::live_scratch_bytes(B, L))) return -1;
+    if (h->fuse_wave && W <= 128 && hrn::fuse_wave_streams(h->sm_count) >= 1) {
+        const size_t ring = hrn::fuse_wave_ring_bytes(h->sm_count, h->wave_ring_rows, W);
+        for (int i = 0; i < 2; ++i)
+            if (grow(reinterpret_cast<void**>(&h->wave_ring[i]), &h->wave_ring_cap[i], ring)) return -1;
+        if (grow(reinterpret_cast<void**>(&h->wave_flags), &h->wave_flags_cap, 16 * hrn::fuse_wave_flag_bytes(h->sm_count))) return -1;
+    }
     return 0;
 }
+
+// Wavefront launches spin on flags written by sibling CTAs, so every CTA of such a grid must become resident.  Two of them
+// enqueued on different streams could each grab half of the SMs and wait for the other half for ever; they are therefore
+// serialised per device with an event (each one fills the GPU anyway).  The mutex covers "wait, launch, record".
+std::mutex g_wave_mutex;
+cudaEvent_t g_wave_event[64] = {};
 
 // Brackets one kernel launch with CUDA events on its own stream when profiling is on.
 struct SpanGuard {
@@ -262,6 +282,8 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
     if (h->ev_fwd_done == nullptr) HRN_CUDA_OK(cudaEventCreateWithFlags(&h->ev_fwd_done, cudaEventDisableTiming));
     if (h->have_last && h->last_stream != s) HRN_CUDA_OK(cudaStreamWaitEvent(s, h->ev_fwd_done, 0));
     SpanGuard whole(h, s, HRN_PROF_FORWARD, 0.0);
+    if (h->wave_flags != nullptr && dump == nullptr && h->fuse_wave && W <= 128)     // hand-over counters of the wavefront levels
+        HRN_CUDA_OK(cudaMemsetAsync(h->wave_flags, 0, static_cast<size_t>(hrn::live_levels(L)) * hrn::fuse_wave_flag_bytes(h->sm_count), s));
 
     // ---- live-work lists: views / pairs that cannot reach the output (alpha = 0 padding) are not computed at all.
     // The stage-dump hook asks for dense lists so that every intermediate tensor is defined.  Must stay the first
@@ -272,7 +294,7 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
                                    h->live_scratch, h->lists, s))
             return -1;
     }
-    const int* enc_list = h->lists + 16;
+    const int* enc_list = h->lists + hrn::LIVE_HDR;
     const int* enc_count = h->lists;
 
     // ---- anchor + first conv (HRNet.py:200-204, 51-53)
@@ -359,7 +381,60 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
     // (alpha_bob = 0) therefore needs no work at all: alice is already where the next level expects it.
     int n = L, level = 0;
     __nv_bfloat16 *stack = h->act[cur], *t1 = h->act[3], *t2 = h->act[4];
-    const int* pair_list = h->lists + 16 + n_img;
+    const int* pair_list = h->lists + hrn::LIVE_HDR + n_img;
+    // Wavefront schedule (fuse_wave_umma.cu): one launch per level, the 128-channel intermediates stay in L2-resident rings,
+    // the level writes into a second view stack (act[3]); images wider than one column tile and the stage-dump hook take
+    // the three-launch schedule below.
+    const bool wave = h->fuse_wave && dump == nullptr && W <= 128 && h->wave_flags != nullptr && h->fuse[0].has_prelu &&
+                      h->fuse[1].has_prelu && h->fuse[2].has_prelu && hrn::live_levels(L) <= 16;
+    if (wave && n / 2 > 0) {
+        std::lock_guard<std::mutex> lock(g_wave_mutex);
+        cudaEvent_t& ev = g_wave_event[h->device];
+        if (ev == nullptr) HRN_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        else HRN_CUDA_OK(cudaStreamWaitEvent(s, ev, 0));
+        const size_t flag_ints = hrn::fuse_wave_flag_bytes(h->sm_count) / sizeof(uint32_t);
+        __nv_bfloat16* other = h->act[3];
+        while (n / 2 > 0) {
+            const int half = n / 2, top = n - (n % 2);
+            hrn::FuseWaveArgs fw{};
+            fw.H = H;
+            fw.W = W;
+            fw.half = half;
+            fw.src_views = L;
+            fw.top = top;
+            fw.live_list = pair_list;
+            fw.live_count = h->lists + 1 + level;
+            fw.carry_list = pair_list + n_img;               // the carry lists mirror the pair lists, B*L ints further on
+            fw.carry_count = h->lists + 16 + level;
+            fw.stack_in = stack;
+            fw.stack_images = B * L;
+            fw.stack_out = other;
+            fw.ring1 = h->wave_ring[0];
+            fw.ring2 = h->wave_ring[1];
+            fw.ring_rows = h->wave_ring_rows;
+            fw.flags = h->wave_flags + static_cast<size_t>(level) * flag_ints;
+            fw.alphas = alphas;
+            fw.alpha_stride = L;
+            fw.alpha_residual = h->cfg.rec_alpha_residual ? 1 : 0;
+            fw.debug_flags = h->debug_flags;
+            fw.streams = h->wave_streams;
+            for (int i = 0; i < 3; ++i) {
+                fw.w_img[i] = h->fuse[i].w_img;
+                fw.bias[i] = h->fuse[i].bias;
+                fw.prelu[i] = h->fuse[i].prelu;
+                fw.has_prelu[i] = 1;
+            }
+            {
+                SpanGuard guard(h, s, HRN_PROF_FUSE_WAVE, 2.0 * 9.0 * (128.0 * 128 * 2 + 128.0 * 64) * B * half * static_cast<double>(hw));
+                if (hrn::fuse_wave_launch(fw, h->sm_count, s)) return -1;
+            }
+            std::swap(stack, other);
+            pair_list += B * half;
+            n = half;
+            ++level;
+        }
+        HRN_CUDA_OK(cudaEventRecord(ev, s));
+    }
     while (n / 2 > 0) {
         const int half = n / 2, top = n - (n % 2);
         hrn::ConvArgs a{};
@@ -504,6 +579,9 @@ void hrn_destroy(hrn_handle* h) {
     rel(h->anchor);
     rel(h->lists);
     rel(h->live_scratch);
+    rel(h->wave_ring[0]);
+    rel(h->wave_ring[1]);
+    rel(h->wave_flags);
     for (auto* p : h->io) rel(p);
     rel(h->io_u16);
     if (h->ev_fwd_done != nullptr) cudaEventDestroy(h->ev_fwd_done);
@@ -894,7 +972,7 @@ int32_t hrn_scoring_debug_set(const char* knob, int32_t value) {
         return 0;
     }
     if (knob != nullptr && strcmp(knob, "cpsnr_window_v1") == 0) {
-        hrn::g_cpsnr_window_v1 = value != 0;
+        hrn::g_cpsnr_window_v1 = value != 0;      // 1 = scalar window kernel (default), 0 = packed fp32x2 kernel
         return 0;
     }
     if (knob != nullptr && strcmp(knob, "cpsnr_chunk") == 0) {
@@ -972,6 +1050,16 @@ int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value) {
     else if (strcmp(knob, "skip_dead_views") == 0) h->skip_dead = value != 0;
     else if (strcmp(knob, "strip_split") == 0) h->strip_split = value;
     else if (strcmp(knob, "fuse_resblock") == 0) h->fuse_resblock = value != 0;
+    else if (strcmp(knob, "fuse_wave") == 0) h->fuse_wave = value != 0;
+    else if (strcmp(knob, "wave_streams") == 0) h->wave_streams = value;
+    else if (strcmp(knob, "wave_ring_rows") == 0) {
+        if (value < 8 || value > 128) {
+            set_error("hrn_debug_set: wave_ring_rows must be in [8, 128]");
+            return -1;
+        }
+        if (value > h->wave_ring_rows) h->wave_ring_cap[0] = h->wave_ring_cap[1] = 0;   // regrown by the next forward
+        h->wave_ring_rows = value;
+    }
     else if (strcmp(knob, "mcast") == 0) h->mcast = value;        // 0 = plain, 1 = cluster pairs if they fit, 2 = required
     else {
         set_error("hrn_debug_set: unknown knob '%s'", knob);

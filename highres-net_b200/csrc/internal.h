@@ -90,6 +90,35 @@ int conv3x3_launch(const ConvArgs& a, int sm_count, cudaStream_t stream);
 int resblock64_launch(const ConvArgs& a1, const float* bias1_host, const uint8_t* w2_img, const float* bias2_host,
                       float prelu2, int sm_count, cudaStream_t stream);
 
+// fuse_wave_umma.cu: one fusion level (conv A, conv B + skip, conv C + PReLU + alpha merge) as a single wavefront launch.
+struct FuseWaveArgs {
+    int H, W;
+    int half, src_views, top;          // as in ConvArgs: pair (b, i) = views i and top - 1 - i; src_views = view stack stride
+    const int* live_list;              // live pairs of this level and their count (device)
+    const int* live_count;
+    const int* carry_list;             // dead pairs whose alice the next level needs (device)
+    const int* carry_count;
+    const __nv_bfloat16* stack_in;     // (stack_images, H, W, 64) bf16
+    int stack_images;
+    __nv_bfloat16* stack_out;          // same shape; merged pairs and carried views are written to their alice slot
+    __nv_bfloat16* ring1;              // fuse_wave_ring_bytes() each
+    __nv_bfloat16* ring2;
+    int ring_rows;
+    uint32_t* flags;                   // fuse_wave_flag_bytes(), all zero when the launch starts
+    const float* alphas;
+    int alpha_stride, alpha_residual;
+    const uint8_t* w_img[3];           // conv A, B, C: conv3x3_pack_weights images
+    const float* bias[3];
+    float prelu[3];
+    int has_prelu[3];
+    int debug_flags;
+    int streams;                       // 0 = as many as the SMs allow (sm_count / 5); tests force odd partitions with fewer
+};
+int fuse_wave_streams(int sm_count);
+size_t fuse_wave_ring_bytes(int sm_count, int ring_rows, int W);
+size_t fuse_wave_flag_bytes(int sm_count);
+int fuse_wave_launch(const FuseWaveArgs& a, int sm_count, cudaStream_t stream);
+
 // ------------------------------------------------------------------ pointwise / CUDA-core kernels
 int median_anchor_launch(const float* lrs, int B, int L, int H, int W, float* anchor, cudaStream_t s);
 // conv_init_umma.cu: conv 2->64 + PReLU on (view, anchor) pairs on the tensor cores (A operand built in smem with a
@@ -112,7 +141,10 @@ int u16_to_unit_float_launch(const uint16_t* in, size_t n, float* out, cudaStrea
 int unit_float_to_u16_launch(const float* in, size_t n, uint16_t* out, int* bad, cudaStream_t s);
 int collate_launch(const void* packed, int is_u16, const int* offsets, int B, int min_L, int H, int W, float* lrs,
                    float* alphas, cudaStream_t s);
-// live-work lists (see pointwise.cu)
+// live-work lists (see pointwise.cu).  Layout of `lists`: [0] = live encoder views, [1 + l] = live pairs of level l,
+// [16 + l] = carried pairs of level l (dead pairs whose alice the next level needs); [LIVE_HDR, LIVE_HDR + B*L) encoder
+// list, then the pair lists level by level; the carry lists start at LIVE_HDR + 2*B*L, level by level.
+constexpr int LIVE_HDR = 32;
 int live_levels(int L);
 size_t live_scratch_bytes(int B, int L);
 size_t live_lists_ints(int B, int L);

@@ -117,9 +117,11 @@ collate_kernel(const T* __restrict__ packed, const int* __restrict__ offsets, in
 //     need[l + 1][i]                        =>  need[l][i]                       (alice always survives)
 //     need[l + 1][i] and alpha[top-1-i] != 0 =>  pair (l, i) is live, need[l][top-1-i]
 // then the block compacts the flags into index lists (ascending, deterministic).  Layout of `lists`:
-//     [0, 16)                     counts: [0] = live encoder views, [1 + l] = live pairs of level l
-//     [16, 16 + B*L)              encoder list (image index b*L + v)
+//     [0, LIVE_HDR)               counts: [0] = live encoder views, [1 + l] = live pairs of level l, [16 + l] = carried pairs
+//     [LIVE_HDR, LIVE_HDR + B*L)  encoder list (image index b*L + v)
 //     then per level l            pair list (pair index b*half_l + i), B*half_l entries
+//     from LIVE_HDR + 2*B*L       per level l: carry list -- dead pairs whose alice the next level needs (the out-of-place
+//                                 wavefront schedule copies those; the in-place three-launch schedule needs nothing)
 // With skip == 0 every flag is set (dense lists; used by the stage-dump hook).
 constexpr int LIVE_THREADS = 1024;
 
@@ -159,6 +161,7 @@ live_lists_kernel(const float* __restrict__ alphas, int B, int L, int levels, in
     uint8_t* scratch = use_smem ? scratch_smem : scratch_global;
     const size_t BL = static_cast<size_t>(B) * L;
     uint8_t* pair_flags = scratch + (levels + 1) * BL;
+    uint8_t* carry_flags = pair_flags + levels * BL;     // dead pair whose alice is needed one level up (copied, not computed)
     for (int b = threadIdx.x; b < B; b += LIVE_THREADS) {
         int n_of[17];
         n_of[0] = L;
@@ -174,17 +177,19 @@ live_lists_kernel(const float* __restrict__ alphas, int B, int L, int levels, in
                 const bool wanted = !skip || need_up[i] != 0;
                 const bool live = wanted && (!skip || !alpha_residual || alphas[static_cast<size_t>(b) * L + top - 1 - i] != 0.0f);
                 pf[i] = live ? 1 : 0;
+                carry_flags[l * BL + static_cast<size_t>(b) * half + i] = (wanted && !live) ? 1 : 0;
                 if (wanted) need[i] = 1;
                 if (live) need[top - 1 - i] = 1;
             }
         }
     }
     __syncthreads();
-    block_compact(scratch, static_cast<int>(BL), lists + 16, lists);
-    int off = 16 + static_cast<int>(BL), n = L;
+    block_compact(scratch, static_cast<int>(BL), lists + LIVE_HDR, lists);
+    int off = LIVE_HDR + static_cast<int>(BL), n = L;
     for (int l = 0; l < levels; ++l) {
         const int half = n / 2;
         block_compact(pair_flags + l * BL, B * half, lists + off, lists + 1 + l);
+        block_compact(carry_flags + l * BL, B * half, lists + off + static_cast<int>(BL), lists + 16 + l);
         off += B * half;
         n = half;
     }
@@ -255,14 +260,14 @@ int live_levels(int L) {
     return levels;
 }
 
-size_t live_scratch_bytes(int B, int L) { return (2 * static_cast<size_t>(live_levels(L)) + 1) * B * L; }
-size_t live_lists_ints(int B, int L) { return 16 + 2 * static_cast<size_t>(B) * L; }
+size_t live_scratch_bytes(int B, int L) { return (3 * static_cast<size_t>(live_levels(L)) + 1) * B * L; }
+size_t live_lists_ints(int B, int L) { return LIVE_HDR + 3 * static_cast<size_t>(B) * L; }
 
 int live_lists_launch(const float* alphas, int B, int L, int skip, int alpha_residual, uint8_t* scratch, int* lists,
                       cudaStream_t s) {
     const int levels = live_levels(L);
-    if (levels > 15) {
-        set_error("hrn_forward: L=%d views need more than 15 fusion levels", L);
+    if (levels > 14) {
+        set_error("hrn_forward: L=%d views need more than 14 fusion levels", L);
         return -1;
     }
     // A plain launch on purpose (no programmatic dependent launch): every later kernel of the forward pass reads the

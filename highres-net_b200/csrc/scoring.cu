@@ -1078,9 +1078,13 @@ int lanczos_taps_launch(const float* d, int n, int a, int ntaps, float* out, cud
 }
 
 int g_cpsnr_generic = 0;
-int g_cpsnr_window_v1 = 0;     // test knob: 1 = second-generation window kernel (scalar fp32, all 49 sites per warp)
-int g_cpsnr_chunk = 0;         // test knob: imagesets per pass-1 / pass-2 round trip (0 = automatic, by L2 size)
-constexpr size_t CP_L2_BUDGET = 56ull << 20;   // bytes of sr + hr + map per chunk that pass 2 should still find in the 126 MB L2
+// Measured on a B200 (profiles/r02_cpsnr_ab.log, 512 x 384^2): scalar window kernel 1.86 ms, packed / split kernel 2.25 ms;
+// with the batch cut into L2-sized chunks 2.13-3.85 ms (chunk 64 ... 12).  The search is bound by the fp32 pipe (three-register
+// FFMA / FADD issue at one warp instruction per two cycles per scheduler, and an FFMA2 costs two of those), not by issue
+// slots or DRAM, so neither packing nor L2 residency of pass 2 pays; both stay behind knobs as measured alternatives.
+int g_cpsnr_window_v1 = 1;     // 1 (default) = scalar 49-sites-per-warp window kernel; 0 = packed fp32x2 kernel, x split over two warps
+int g_cpsnr_chunk = 0;         // imagesets per pass-1 / pass-2 round trip: 0 (default) = whole batch; -1 = by L2 budget; n > 0 = n
+constexpr size_t CP_L2_BUDGET = 56ull << 20;   // chunk = -1: bytes of sr + hr + map per chunk that pass 2 should still find in L2
 constexpr int CW2_TARGET_WARPS = 148 * 14;
 
 int shift_cpsnr_launch(const float* sr, const float* hr, const float* hm, int B, int H, int W, int border,
@@ -1133,13 +1137,13 @@ int shift_cpsnr_launch(const float* sr, const float* hr, const float* hm, int B,
     // border_w = 3 on 16-byte aligned rows (every case the reference produces) takes the 49-site window kernel
     const bool window = g.S == CW_S && g.vec_ok && g_cpsnr_generic == 0;
     const bool window2 = window && g_cpsnr_window_v1 == 0;
-    // Both passes read sr, hr and the map.  A batch that does not fit in L2 is therefore processed in chunks of imagesets:
-    // pass 1 -> bias -> pass 2 of one chunk run back to back, so that pass 2 finds the chunk's 3 planes per imageset in
-    // L2 and every byte comes from HBM once (512 imagesets in one go read everything twice: ncu, profiles/).
+    // Both passes read sr, hr and the map.  Optionally (knob cpsnr_chunk) a batch that does not fit in L2 is processed in
+    // chunks of imagesets -- pass 1 -> bias -> pass 2 of one chunk back to back, so that pass 2 finds the chunk in L2 and
+    // every byte comes from HBM once.  Off by default: the kernels are fp32-bound and the extra launches cost more.
     const size_t set_bytes = 3 * static_cast<size_t>(H) * W * sizeof(float);
     int chunk = B;
     if (g_cpsnr_chunk > 0) chunk = g_cpsnr_chunk;
-    else if (window && set_bytes * B > CP_L2_BUDGET) chunk = static_cast<int>(CP_L2_BUDGET / set_bytes);
+    else if (g_cpsnr_chunk < 0 && window && set_bytes * B > CP_L2_BUDGET) chunk = static_cast<int>(CP_L2_BUDGET / set_bytes);
     chunk = chunk < 1 ? 1 : (chunk > B ? B : chunk);
     const int per_pass = chunk < B ? chunk : B;            // imagesets per launch: sizes the row bands
     if (window) {

@@ -656,12 +656,13 @@ def test_shift_cpsnr_window_kernel_vs_generic_and_oracle(hb, dev, b, s, kind):
         best_g, xy_g, tab_g = hb.shift_cPSNR_argmax(*args)
     finally:
         hb.scoring_debug_set("cpsnr_generic", 0)
-    # the second-generation window kernel (scalar fp32, 49 sites per warp) and the chunked pass-1 / pass-2 schedule
-    hb.scoring_debug_set("cpsnr_window_v1", 1)
+    # the packed fp32x2 window kernel (x split over two warps; the default is the scalar 49-sites-per-warp kernel) and
+    # the chunked pass-1 / pass-2 schedule
+    hb.scoring_debug_set("cpsnr_window_v1", 0)
     try:
         best_1, xy_1, tab_1 = hb.shift_cPSNR_argmax(*args)
     finally:
-        hb.scoring_debug_set("cpsnr_window_v1", 0)
+        hb.scoring_debug_set("cpsnr_window_v1", 1)
     hb.scoring_debug_set("cpsnr_chunk", 2)
     try:
         best_c, xy_c, tab_c = hb.shift_cPSNR_argmax(*args)
