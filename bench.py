@@ -271,6 +271,8 @@ class Bench:
         self.net = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval()
         self.net.load_state_dict(self.params)
         self.net = self.net.to(self.dev)
+        if args.no_wave:
+            self.net.debug_set(self.dev, "fuse_wave", 0)
         self.peaks = load_peaks()
         self.gather_stream = torch.cuda.Stream(self.dev) if world > 1 else None
 
@@ -595,6 +597,7 @@ def main():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lean", action="store_true", help="headline loops and roofline only (A/B runs, ncu captures)")
+    ap.add_argument("--no-wave", action="store_true", help="fusion levels as three launches each instead of one wavefront launch (A/B)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -692,6 +695,8 @@ def main():
                        "l2": f"inputs rotate over {bench.n_rot} distinct batches ({bench.n_rot * b * l * s * s * 4 / 1e6:.0f} MB "
                              f"> 126 MB L2); activations stream through HBM every step",
                        "sharding": "batch (independent imagesets per rank); no collective inside the model",
+                       "fusion_schedule": ("three launches per level (--no-wave)" if args.no_wave else
+                                           "one wavefront launch per fusion level (fuse_wave_umma.cu)"),
                        "collective": (f"every step: NCCL all_gather of the SR images ({sr_bytes} B per rank, {world * sr_bytes} B "
                                       f"gathered per rank) on a side stream, inside the timed region" if world > 1 else
                                       "none at N=1 (the SR/score gather runs when N > 1)"),

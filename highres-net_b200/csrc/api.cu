@@ -70,8 +70,11 @@ struct hrn_handle {
     int fuse_wave = 1;                 // fusion levels as one wavefront launch each (fuse_wave_umma.cu) when W <= 128
     int wave_ring_rows = 16;           // rows per stream ring of the wavefront schedule (test knob, >= 8)
     int wave_streams = 0;              // streams of the wavefront schedule (0 = sm_count / 5; test knob)
+    int wave_publish_rows = 1;         // rows per hand-over publication of the wavefront schedule
+    int wave_lag_rows = 0;             // triage: consumers stay this many rows behind their producer
     __nv_bfloat16* wave_ring[2] = {nullptr, nullptr};
     size_t wave_ring_cap[2] = {0, 0};
+    unsigned long long* wave_stats = nullptr;   // triage counters of the wavefront kernel (knob "wave_stats"), 8 per CTA
     uint32_t* wave_flags = nullptr;    // 16 levels x fuse_wave_flag_bytes()
     size_t wave_flags_cap = 0;
     int host_chunks = 0;               // hrn_forward_host pipeline depth (0 = automatic)
@@ -418,6 +421,9 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
             fw.alpha_residual = h->cfg.rec_alpha_residual ? 1 : 0;
             fw.debug_flags = h->debug_flags;
             fw.streams = h->wave_streams;
+            fw.stats = h->wave_stats;
+            fw.publish_rows = h->wave_publish_rows;
+            fw.lag_rows = h->wave_lag_rows;
             for (int i = 0; i < 3; ++i) {
                 fw.w_img[i] = h->fuse[i].w_img;
                 fw.bias[i] = h->fuse[i].bias;
@@ -582,6 +588,7 @@ void hrn_destroy(hrn_handle* h) {
     rel(h->wave_ring[0]);
     rel(h->wave_ring[1]);
     rel(h->wave_flags);
+    rel(h->wave_stats);
     for (auto* p : h->io) rel(p);
     rel(h->io_u16);
     if (h->ev_fwd_done != nullptr) cudaEventDestroy(h->ev_fwd_done);
@@ -1052,9 +1059,36 @@ int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value) {
     else if (strcmp(knob, "fuse_resblock") == 0) h->fuse_resblock = value != 0;
     else if (strcmp(knob, "fuse_wave") == 0) h->fuse_wave = value != 0;
     else if (strcmp(knob, "wave_streams") == 0) h->wave_streams = value;
+    else if (strcmp(knob, "wave_publish_rows") == 0) h->wave_publish_rows = value < 1 ? 1 : value;
+    else if (strcmp(knob, "wave_lag_rows") == 0) h->wave_lag_rows = value < 0 ? 0 : value;
+    else if (strcmp(knob, "wave_stats") == 0) {
+        // 1: start collecting per-CTA wait counters of the wavefront kernel; 0: print their per-role means to stderr and stop
+        hrn::DeviceGuard on_device(h->device);
+        const size_t n = static_cast<size_t>(h->sm_count) * 12;
+        if (value) {
+            if (h->wave_stats == nullptr) HRN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->wave_stats), n * sizeof(unsigned long long)));
+            HRN_CUDA_OK(cudaDeviceSynchronize());
+            HRN_CUDA_OK(cudaMemset(h->wave_stats, 0, n * sizeof(unsigned long long)));
+        } else if (h->wave_stats != nullptr) {
+            HRN_CUDA_OK(cudaDeviceSynchronize());
+            std::vector<unsigned long long> host(n);
+            HRN_CUDA_OK(cudaMemcpy(host.data(), h->wave_stats, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            const char* names[5] = {"A0", "A1", "B0", "B1", "C "};
+            const int streams = h->wave_streams > 0 ? h->wave_streams : h->sm_count / 5;
+            fprintf(stderr, "wavefront triage (mean cycles per CTA over %d streams): kernel | TMA wait rows | TMA wait smem slot | epi wait ring space | epi wait accumulator | publisher wait rows | publisher stores | MMA wait input row\n", streams);
+            for (int r = 0; r < 5; ++r) {
+                double m[12] = {};
+                for (int st = 0; st < streams; ++st)
+                    for (int k = 0; k < 12; ++k) m[k] += static_cast<double>(host[(static_cast<size_t>(st) * 5 + r) * 12 + k]) / streams;
+                fprintf(stderr, "  %s %12.0f %12.0f %12.0f %12.0f %12.0f %12.0f %12.0f %10.0f | TMA fences %10.0f TMA loop %10.0f\n", names[r], m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9]);
+            }
+            HRN_CUDA_OK(cudaFree(h->wave_stats));
+            h->wave_stats = nullptr;
+        }
+    }
     else if (strcmp(knob, "wave_ring_rows") == 0) {
-        if (value < 8 || value > 128) {
-            set_error("hrn_debug_set: wave_ring_rows must be in [8, 128]");
+        if (value < 8 || value > 4096) {
+            set_error("hrn_debug_set: wave_ring_rows must be in [8, 4096]");
             return -1;
         }
         if (value > h->wave_ring_rows) h->wave_ring_cap[0] = h->wave_ring_cap[1] = 0;   // regrown by the next forward

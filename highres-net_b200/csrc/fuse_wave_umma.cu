@@ -61,8 +61,9 @@ constexpr int SMEM_BYTES = BIAS_OFFSET + NT * 4 + 1024;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 static_assert(16 * RING + 16 * ACC_SLOTS + 8 * ROWDONE + 8 + 8 <= 512, "barrier block overflows into the bias array");
 constexpr int CTAS_PER_STREAM = 5;
-constexpr int FLAGS_PER_STREAM = 8;         // prod1[2], cons1[2], prod2[2], cons2, pad
-enum : int { F_PROD1 = 0, F_CONS1 = 2, F_PROD2 = 4, F_CONS2 = 6 };
+constexpr int FLAG_STRIDE = 32;             // uint32 per counter: every hand-over counter sits in its own 128-byte line
+constexpr int FLAGS_PER_STREAM = 8 * FLAG_STRIDE;   // prod1[2], cons1[2], prod2[2], cons2, pad
+enum : int { F_PROD1 = 0, F_CONS1 = 2 * FLAG_STRIDE, F_PROD2 = 4 * FLAG_STRIDE, F_CONS2 = 6 * FLAG_STRIDE };
 
 struct WaveConv {
     const uint8_t* w_img;   // pre-swizzled weights of the whole layer (conv3x3_pack_weights)
@@ -89,6 +90,9 @@ struct WaveArgs {
     int alpha_stride, alpha_residual;
     WaveConv conv[3];
     int debug_flags;
+    unsigned long long* stats;         // optional (triage): per CTA 8 counters of clock64 cycles, see fuse_wave_kernel
+    int publish_rows;                  // rows per "stored" publication (one device-scope release each), >= 1
+    int lag_rows;                      // a consumer loads row k only when the producer has stored row k + lag_rows (triage)
 };
 
 // The stream's range of the flattened (live pair, row) space, as per-image strips extended by `e` halo rows on both
@@ -126,14 +130,22 @@ __device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
 __device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // Spin until *p >= want.  Bounded like the mbarrier waits: a protocol bug must surface as a CUDA error, never as a hung GPU.
-static __device__ __noinline__ uint32_t flag_wait_slow(const uint32_t* p, uint32_t want, int tag) {
+static __device__ __noinline__ uint32_t flag_wait_slow(const uint32_t* p, uint32_t want, int tag, bool sleep) {
     const long long t0 = clock64();
     uint32_t v;
-    while ((v = ld_acquire(p)) < want) {
-        __nanosleep(64);
+    while ((v = ld_relaxed(p)) < want) {
+        if (sleep) __nanosleep(64);
         if (clock64() - t0 > HRN_WAIT_LIMIT_CYCLES) {
             printf("hrn_b200: wavefront flag wait timed out (block %d thread %d tag %d: have %u, want %u)\n",
                    (int)blockIdx.x, (int)threadIdx.x, tag, v, want);
@@ -142,10 +154,21 @@ static __device__ __noinline__ uint32_t flag_wait_slow(const uint32_t* p, uint32
     }
     return v;
 }
-__device__ __forceinline__ uint32_t flag_wait(const uint32_t* p, uint32_t want, int tag) {
-    const uint32_t v = ld_acquire(p);
-    return v >= want ? v : flag_wait_slow(p, want, tag);
+// Relaxed polling; the caller adds the acquire fence where data written by the flag's producer is read afterwards (the
+// ring-reuse wait needs none: it only orders this CTA's later stores after the consumer's completed reads).
+__device__ __forceinline__ uint32_t flag_wait(const uint32_t* p, uint32_t want, int tag, bool sleep = false) {
+    const uint32_t v = ld_relaxed(p);
+    return v >= want ? v : flag_wait_slow(p, want, tag, sleep);
 }
+__device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+// Triage counters (per CTA, cycles): 0 = whole kernel, 1 = TMA thread waiting for the producer's rows, 2 = TMA thread
+// waiting for a free shared-memory slot, 3 = epilogue warp 4 waiting for ring space, 4 = epilogue warp 4 waiting for a full
+// accumulator, 5 = publisher waiting for stored rows, 6 = publisher inside its stores (release fence), 7 = MMA thread waiting
+// for an input row in shared memory (interior rows).
+#define WAVE_STAT_BEGIN(var) const long long var = w.stats != nullptr ? clock64() : 0
+#define WAVE_STAT_END(var, idx) \
+    if (w.stats != nullptr) atomicAdd(w.stats + static_cast<size_t>(blockIdx.x) * 12 + (idx), static_cast<unsigned long long>(clock64() - var))
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_constant__ CUtensorMap map_r1,
@@ -162,8 +185,10 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
     const uint32_t bar_rowdone = bar_tempty + 8 * ACC_SLOTS;     // [ROWDONE]
     const uint32_t bar_w = bar_rowdone + 8 * ROWDONE;
     const uint32_t tmem_slot = bar_w + 8;
+    const uint32_t credit_slot = tmem_slot + 4;                  // ring rows the consumer(s) have finished reading (mirror)
     uint8_t* smem_gen = smem_raw + (base - ptx::smem_u32(smem_raw));
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - base));
+    volatile uint32_t* credit_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (credit_slot - base));
     float* bias_s = reinterpret_cast<float*>(smem_gen + BIAS_OFFSET);
 
     const int warp = threadIdx.x >> 5;
@@ -189,6 +214,7 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
         }
         for (int i = 0; i < ROWDONE; ++i) ptx::mbar_init(bar_rowdone + 8 * i, EPI_WARPS);
         ptx::mbar_init(bar_w, 1);
+        *credit_gen = 0;
         ptx::fence_barrier_init();
         ptx::prefetch_tensormap(in_map);
     }
@@ -199,6 +225,7 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
+    WAVE_STAT_BEGIN(t_kernel);
 
     if (warp == 0) {
         // ===================================================== TMA producer: one elected thread
@@ -210,9 +237,16 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
             Strip s;
             bool have = walk.next(s);
             ptx::pdl_wait();                 // weights and lists are constants; the view stack comes from the previous kernel
+            uint32_t total_in = 0;           // in-image input rows of this CTA = rows its producer will ever store
+            if (conv != 0 && w.lag_rows > 0) {
+                WaveWalker count(w, stream, halo, false);
+                Strip c;
+                for (bool more = count.next(c); more; more = count.next(c)) total_in += min(w.H, c.y0 + c.rows + 1) - max(0, c.y0 - 1);
+            }
             uint32_t it = 0, cum = 0;        // cum: in-image input rows requested so far = rows the producer must have stored
             uint32_t seen0 = 0, seen1 = 0;   // last values read from the producer's two "rows stored" counters
             const uint32_t* prod = flags + (conv == 1 ? F_PROD1 : F_PROD2);
+            WAVE_STAT_BEGIN(t9);
             for (; have; have = walk.next(s)) {
                 int img[2] = {0, 0};
                 if (conv == 0) {
@@ -228,9 +262,17 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
                             yc = static_cast<int>(cum % static_cast<uint32_t>(R));
                             ++cum;
                             if (!(w.debug_flags & 32)) {
-                                if (seen0 < cum) seen0 = flag_wait(prod, cum, 20);
-                                if (seen1 < cum) seen1 = flag_wait(prod + 1, cum, 21);
-                                fence_proxy_async_global();  // the rows were written through the generic proxy, TMA reads through the async one
+                                const uint32_t need = w.lag_rows > 0 ? min(cum + static_cast<uint32_t>(w.lag_rows), total_in) : cum;
+                                if (seen0 < need || seen1 < need) {
+                                    WAVE_STAT_BEGIN(t0);
+                                    if (seen0 < need) seen0 = flag_wait(prod, need, 20, w.debug_flags & 512);
+                                    if (seen1 < need) seen1 = flag_wait(prod + FLAG_STRIDE, need, 21, w.debug_flags & 512);
+                                    WAVE_STAT_END(t0, 1);
+                                    WAVE_STAT_BEGIN(t8);
+                                    if (!(w.debug_flags & 128)) fence_acquire_gpu();         // pairs with the publisher's st.release
+                                    if (!(w.debug_flags & 256)) fence_proxy_async_global();  // generic-proxy writes -> async-proxy (TMA) reads
+                                    WAVE_STAT_END(t8, 8);
+                                }
                             }
                         } else {
                             yc = -1;
@@ -239,7 +281,9 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
 #pragma unroll
                     for (int c = 0; c < CHUNKS; ++c, ++it) {
                         const uint32_t slot = it % RING, ph = (it / RING) & 1;
+                        WAVE_STAT_BEGIN(t1);
                         ptx::mbar_wait(bar_empty + 8 * slot, ph ^ 1, 1);
+                        WAVE_STAT_END(t1, 2);
                         ptx::mbar_expect_tx(bar_full + 8 * slot, CHUNK_TX);
                         if (conv == 0)
                             ptx::tma_load_4d(ring_s + slot * CHUNK_BYTES, in_map, 0, -1, yc, img[c], bar_full + 8 * slot);
@@ -248,6 +292,7 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
                     }
                 }
             }
+            WAVE_STAT_END(t9, 9);
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer: ONE elected thread (see conv3x3_umma.cu)
@@ -278,7 +323,11 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
 #pragma unroll
                         for (int c = 0; c < CHUNKS; ++c, ++it) {
                             const uint32_t slot = it % RING;
-                            if (!full_seen) ptx::mbar_wait(bar_full + 8 * slot, (it / RING) & 1, 3);
+                            if (!full_seen) {
+                                WAVE_STAT_BEGIN(t7);
+                                ptx::mbar_wait(bar_full + 8 * slot, (it / RING) & 1, 3);
+                                WAVE_STAT_END(t7, 7);
+                            }
                             full_seen = false;
                             ptx::tc_fence_after();
                             uint64_t ad = make_desc(a_lo0 + slot * (CHUNK_BYTES / 16));
@@ -287,7 +336,9 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
                             // early waits for the next item, issued after k-step 7 while the MMA queue is full
                             auto early = [&]() {
                                 const uint32_t itn = it + 1;
+                                WAVE_STAT_BEGIN(t7);
                                 ptx::mbar_wait(bar_full + 8 * (itn % RING), (itn / RING) & 1, 6);
+                                WAVE_STAT_END(t7, 7);
                                 full_seen = true;
                                 if (c + 1 == CHUNKS && nxt_opens) {
                                     const uint32_t tn = t_new + 1;
@@ -409,18 +460,74 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
                 have = have_next;
             }
         }
+    } else if (warp == 2) {
+        // ===================================================== credit poller (conv A, B): ONE thread per CTA watches the
+        // consumer's "rows read" counter(s) in global memory and mirrors the minimum into shared memory, where the eight
+        // epilogue warps look it up; without it every epilogue warp would spin on the same global line.
+        if (conv < 2 && !(w.debug_flags & 1024) && ptx::elect_one()) {
+            uint32_t total_rows = 0;
+            WaveWalker count(w, stream, halo, false);
+            Strip s;
+            for (bool have = count.next(s); have; have = count.next(s)) total_rows += s.rows;
+            const uint32_t* cons = flags + (conv == 0 ? F_CONS1 : F_CONS2);
+            const uint32_t last_needed = total_rows > static_cast<uint32_t>(R) ? total_rows - R : 0;   // the last store waits for this
+            uint32_t have_credit = 0;
+            const long long t0 = clock64();
+            while (have_credit < last_needed) {
+                uint32_t v = ld_relaxed(cons);
+                if (conv == 0) v = min(v, ld_relaxed(cons + FLAG_STRIDE));
+                if (v > have_credit) {
+                    have_credit = v;
+                    *credit_gen = v;
+                }
+                if (clock64() - t0 > 40 * HRN_WAIT_LIMIT_CYCLES) {
+                    printf("hrn_b200: wavefront credit poller timed out (block %d: have %u, want %u)\n", (int)blockIdx.x, have_credit, last_needed);
+                    __trap();
+                }
+            }
+        }
     } else if (warp == 3) {
-        // ===================================================== publisher (conv A, B): "row k is in the ring" for the consumer
-        if (conv < 2 && ptx::elect_one()) {
+        // ===================================================== publisher: hand-over counters for the neighbours in the stream.
+        // Off the epilogue warps on purpose: a device-scope release (MEMBAR.GPU) costs about a microsecond under load, and
+        // an epilogue warp that pays it every row holds back the accumulator ring and with it the whole CTA.
+        if (ptx::elect_one()) {
             WaveWalker walk(w, stream, halo, false);
             Strip s;
-            uint32_t k = 0;
-            uint32_t* prod = flags + (conv == 0 ? F_PROD1 : F_PROD2) + part;
-            for (bool have = walk.next(s); have; have = walk.next(s))
+            uint32_t k = 0, in_base = 0, next_pub = 1, total_rows = 0;
+            {
+                WaveWalker count(w, stream, halo, false);
+                for (bool have = count.next(s); have; have = count.next(s)) total_rows += s.rows;
+            }
+            uint32_t* prod = flags + (conv == 0 ? F_PROD1 : F_PROD2) + part * FLAG_STRIDE;
+            uint32_t* my_cons = flags + (conv == 1 ? F_CONS1 + part * FLAG_STRIDE : F_CONS2);
+            for (bool have = walk.next(s); have; have = walk.next(s)) {
+                const int in_lo = max(0, s.y0 - 1), in_hi = min(w.H, s.y0 + s.rows + 1);
                 for (int i = 0; i < s.rows; ++i, ++k) {
-                    ptx::mbar_wait(bar_rowdone + 8 * (k % ROWDONE), (k / ROWDONE) & 1, 8);   // all eight epilogue warps stored row k
-                    st_release(prod, k + 1);
+                    WAVE_STAT_BEGIN(t5);
+                    ptx::mbar_wait(bar_rowdone + 8 * (k % ROWDONE), (k / ROWDONE) & 1, 8);   // all eight epilogue warps are done with row k
+                    WAVE_STAT_END(t5, 5);
+                    WAVE_STAT_BEGIN(t6);
+                    // rows of this strip that have been completed in the meantime are published with the same release: one
+                    // device-scope fence per batch keeps the publisher from becoming the pace setter of the stream
+                    while (i + 1 < s.rows && ptx::mbar_test_wait(bar_rowdone + 8 * ((k + 1) % ROWDONE), ((k + 1) / ROWDONE) & 1)) {
+                        ++i;
+                        ++k;
+                    }
+                    // conv B, C: the tensor pipe has finished every input row up to y + 1 of this strip (its accumulator was
+                    // complete before the epilogue ran), so those ring rows may be overwritten.  Needs no fence, and goes out
+                    // before the release below so that the credit does not wait for it.
+                    if (conv > 0) st_relaxed(my_cons, in_base + static_cast<uint32_t>(min(s.y0 + i + 2, in_hi) - in_lo));
+                    // conv A, B: rows 0 .. k are in the ring.  One device-scope release per `publish_rows` rows (and at the end
+                    // of the stream): the fence drains the SM's store path, which every epilogue warp shares.
+                    if (conv < 2 && (k + 1 >= next_pub || k + 1 == total_rows)) {
+                        if (w.debug_flags & 64) st_relaxed(prod, k + 1);
+                        else st_release(prod, k + 1);
+                        next_pub = k + 1 + w.publish_rows;
+                    }
+                    WAVE_STAT_END(t6, 6);
                 }
+                in_base += static_cast<uint32_t>(in_hi - in_lo);
+            }
         }
     } else if (warp >= 4) {
         // ===================================================== epilogue: 8 warps, (lane quadrant) x (column half)
@@ -435,15 +542,12 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
         const int out_c = conv < 2 ? 128 : 64;
         __nv_bfloat16* ring_out = conv == 0 ? w.ring1 : w.ring2;
         const uint32_t* cons = flags + (conv == 0 ? F_CONS1 : F_CONS2);      // the consumer's "input rows read" counter(s)
-        uint32_t* my_cons = flags + (conv == 1 ? F_CONS1 + part : F_CONS2);  // this CTA's own counter (conv B, C)
-        const bool cons_writer = conv > 0 && warp == 4 && lane == 0;
         uint32_t seen_c0 = 0, seen_c1 = 0;
         WaveWalker walk(w, stream, halo);
         Strip s;
         bool have = walk.next(s);
         ptx::pdl_wait();                         // residual reads and output writes touch the previous kernel's tensors
         uint32_t tile = 0;                       // rows produced so far = ring row counter of a producer
-        uint32_t in_base = 0;                    // in-image input rows of the earlier strips (consumers)
         const int x = wq * 32 + lane;
         const bool valid = x < w.W;
         for (; have; have = walk.next(s)) {
@@ -464,7 +568,6 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
             const size_t r_step = static_cast<size_t>(w.W) * 64;
             __nv_bfloat16* op = nullptr;
             if (conv == 2) op = w.stack_out + (static_cast<size_t>(b * w.src_views + ip) * w.H * w.W + pix0) * 64 + co0;
-            const int in_lo = max(0, s.y0 - 1), in_hi = min(w.H, s.y0 + s.rows + 1);
             for (int i = 0; i < s.rows; ++i, ++tile, rp += r_step) {
                 const uint32_t acc = tile % ACC_SLOTS, aph = (tile / ACC_SLOTS) & 1;
                 uint32_t rv[2][8];
@@ -472,10 +575,12 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
                     ptx::ldg_nc_v8(rp, rv[0]);
                     ptx::ldg_nc_v8(rp + 16, rv[1]);
                 }
-                ptx::mbar_wait(bar_tfull + 8 * acc, aph, 5);
+                {
+                    WAVE_STAT_BEGIN(t4);
+                    ptx::mbar_wait(bar_tfull + 8 * acc, aph, 5);
+                    if (warp == 4 && lane == 0) WAVE_STAT_END(t4, 4);
+                }
                 ptx::tc_fence_after();
-                if (cons_writer)                 // the tensor pipe has finished every input row up to y + 1 of this strip
-                    st_release(my_cons, in_base + static_cast<uint32_t>(min(s.y0 + i + 2, in_hi) - in_lo));
                 uint32_t v[32];
                 ptx::tmem_ld_x32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * NT + hf * 32, v);
                 ptx::tmem_ld_wait();
@@ -499,10 +604,25 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
                     // ring slot of produced row `tile`; it may be overwritten once the consumer(s) have read row tile - R
                     if (tile >= static_cast<uint32_t>(R) && !(w.debug_flags & 32)) {
                         const uint32_t want = tile - R + 1;
-                        if (seen_c0 < want || (conv == 0 && seen_c1 < want)) {
+                        if (!(w.debug_flags & 1024)) {
+                            if (seen_c0 < want) {            // shared-memory mirror kept by the credit poller (warp 2)
+                                WAVE_STAT_BEGIN(t3);
+                                const long long t0 = clock64();
+                                while ((seen_c0 = *credit_gen) < want) {
+                                    if (clock64() - t0 > HRN_WAIT_LIMIT_CYCLES) {
+                                        printf("hrn_b200: wavefront ring-space wait timed out (block %d warp %d: have %u, want %u)\n",
+                                               (int)blockIdx.x, warp, seen_c0, want);
+                                        __trap();
+                                    }
+                                }
+                                if (warp == 4 && lane == 0) WAVE_STAT_END(t3, 3);
+                            }
+                        } else if (seen_c0 < want || (conv == 0 && seen_c1 < want)) {
                             if (lane == 0) {
-                                if (seen_c0 < want) seen_c0 = flag_wait(cons, want, 30);
-                                if (conv == 0 && seen_c1 < want) seen_c1 = flag_wait(cons + 1, want, 31);
+                                WAVE_STAT_BEGIN(t3);
+                                if (seen_c0 < want) seen_c0 = flag_wait(cons, want, 30, w.debug_flags & 512);
+                                if (conv == 0 && seen_c1 < want) seen_c1 = flag_wait(cons + FLAG_STRIDE, want, 31, w.debug_flags & 512);
+                                if (warp == 4) WAVE_STAT_END(t3, 3);
                             }
                             seen_c0 = __shfl_sync(0xffffffffu, seen_c0, 0);
                             seen_c1 = __shfl_sync(0xffffffffu, seen_c1, 0);
@@ -513,8 +633,6 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
                         ptx::stg_v8(dst, o[0]);
                         ptx::stg_v8(dst + 16, o[1]);
                     }
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(bar_rowdone + 8 * (tile % ROWDONE));
                 } else {
                     if (valid) {
                         ptx::stg_v8(op, o[0]);
@@ -522,8 +640,9 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
                     }
                     op += static_cast<size_t>(w.W) * 64;
                 }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(bar_rowdone + 8 * (tile % ROWDONE));      // -> publisher (warp 3)
             }
-            in_base += static_cast<uint32_t>(in_hi - in_lo);
         }
         // ---- carried views: alice of a pair whose bob has alpha = 0 goes to the next level unchanged (conv C CTAs only)
         if (conv == 2 && w.carry_count != nullptr) {
@@ -543,6 +662,7 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
+    if (threadIdx.x == 0) WAVE_STAT_END(t_kernel, 0);
     if (warp == 2) ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
@@ -586,6 +706,17 @@ int fuse_wave_launch(const FuseWaveArgs& a, int sm_count, cudaStream_t stream) {
     w.alpha_stride = a.alpha_stride;
     w.alpha_residual = a.alpha_residual;
     w.debug_flags = a.debug_flags;
+    w.stats = a.stats;
+    w.publish_rows = a.publish_rows > 0 ? a.publish_rows : 1;
+    w.lag_rows = a.lag_rows > 0 ? a.lag_rows : 0;
+    if (a.ring_rows < w.publish_rows + w.lag_rows + 4) {
+        set_error("fuse_wave: ring_rows must be at least publish_rows + lag_rows + 4");
+        return -1;
+    }
+    if (a.ring_rows < w.publish_rows + 4) {
+        set_error("fuse_wave: ring_rows must be at least publish_rows + 4");
+        return -1;
+    }
     for (int i = 0; i < 3; ++i) {
         w.conv[i].w_img = a.w_img[i];
         w.conv[i].bias = a.bias[i];

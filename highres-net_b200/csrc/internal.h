@@ -113,6 +113,9 @@ struct FuseWaveArgs {
     int has_prelu[3];
     int debug_flags;
     int streams;                       // 0 = as many as the SMs allow (sm_count / 5); tests force odd partitions with fewer
+    unsigned long long* stats;         // optional triage counters: 8 per CTA (see fuse_wave_umma.cu), accumulated over launches
+    int publish_rows;                  // rows per hand-over publication (one device-scope release each); 0 = 1
+    int lag_rows;                      // triage: consumers stay this many rows behind their producer
 };
 int fuse_wave_streams(int sm_count);
 size_t fuse_wave_ring_bytes(int sm_count, int ring_rows, int W);

@@ -194,15 +194,18 @@ def test_dead_view_skipping_is_exact(hb, dev, l, pattern):
     lrs = rng.rand(len(pattern), l, 24, 24).astype(np.float32)
     alphas = np.array(pattern, dtype=np.float32)
     tl, ta = torch.from_numpy(lrs).to(dev), torch.from_numpy(alphas).to(dev)
-    # poison the workspace first, so that a skipped view that is read anyway shows up
-    model(torch.full_like(tl, 1e4), torch.ones_like(ta))
-    sr = model(tl, ta).cpu().numpy()
     ref = hrnet_oracle.hrnet_forward(params, lrs, alphas).numpy()
-    assert np.isfinite(sr).all()
-    assert np.abs(sr - ref).max() <= SR_REGRESSION_GATE
-    model.debug_set(dev, "skip_dead_views", 0)
-    dense = model(tl, ta).cpu().numpy()
-    assert np.array_equal(sr, dense)
+    for wave in (1, 0):                     # wavefront schedule (out of place: carried views) and three launches (in place)
+        model.debug_set(dev, "fuse_wave", wave)
+        model.debug_set(dev, "skip_dead_views", 1)
+        # poison the workspace first, so that a skipped view that is read anyway shows up
+        model(torch.full_like(tl, 1e4), torch.ones_like(ta))
+        sr = model(tl, ta).cpu().numpy()
+        assert np.isfinite(sr).all()
+        assert np.abs(sr - ref).max() <= SR_REGRESSION_GATE
+        model.debug_set(dev, "skip_dead_views", 0)
+        dense = model(tl, ta).cpu().numpy()
+        assert np.array_equal(sr, dense)
 
 
 def test_dead_view_lists_large_batch(net, dev):
@@ -281,11 +284,13 @@ def test_row_partition_does_not_change_results(hb, dev):
     tl, ta = torch.from_numpy(lrs).to(dev), torch.from_numpy(alphas).to(dev)
     outs = []
     for ctas in (0, 1, 2, 7, 37, 146):
-        model = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval()
-        model.load_state_dict(hrnet_oracle.make_params(cases.WEIGHT_SEED))
-        model = model.to(dev)
-        model.debug_set(dev, "max_ctas", ctas)
-        outs.append(model(tl, ta))
+        for wave in (0, 1):                     # encoder convs always; the fusion convs in the three-launch schedule
+            model = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval()
+            model.load_state_dict(hrnet_oracle.make_params(cases.WEIGHT_SEED))
+            model = model.to(dev)
+            model.debug_set(dev, "max_ctas", ctas)
+            model.debug_set(dev, "fuse_wave", wave)
+            outs.append(model(tl, ta))
     for split in (3, 16, 1000):             # several short ranges per CTA, dealt round-robin (1000: mostly empty ranges)
         model.debug_set(dev, "max_ctas", 5)
         model.debug_set(dev, "strip_split", split)
@@ -321,6 +326,86 @@ def test_fused_resblock_is_bit_identical_to_two_launches(hb, dev, b, l, s):
     assert np.abs(outs[0].cpu().numpy() - ref).max() <= SR_GATE
 
 
+def _net_with(hb, dev, **knobs):
+    model = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval()
+    model.load_state_dict(hrnet_oracle.make_params(cases.WEIGHT_SEED))
+    model = model.to(dev)
+    for knob, value in knobs.items():
+        model.debug_set(dev, knob, value)
+    return model
+
+
+@pytest.mark.parametrize("b,l,s", [(1, 2, 8), (1, 2, 16), (2, 3, 33), (2, 4, 128), (1, 5, 100), (3, 2, 1), (2, 2, 2), (1, 16, 64),
+                                   (4, 8, 128), (3, 9, 40), (2, 32, 32)])
+def test_wavefront_fusion_is_bit_identical_to_three_launches(hb, dev, b, l, s):
+    """fuse_wave_umma (one launch per fusion level: conv A / B / C as five-CTA streams that hand rows over through
+    L2-resident rings, HRNet.py:93-97, 113-128) against the three-launch schedule: every output element sees the same
+    products in the same order and the same rounding points, so the SR image must be bit-identical -- with full view
+    sets, padded / holed alpha patterns (carried views), and whatever the stream partition and ring depth."""
+    g = torch.Generator().manual_seed(b * 1000 + l * 10 + s)
+    lrs = torch.rand(b, l, s, s, generator=g).to(dev)
+    alphas = torch.ones(b, l, device=dev)
+    ref_net = _net_with(hb, dev, fuse_wave=0)
+    before = hb.kernel_launch_count()
+    ref = ref_net(lrs, alphas)
+    launches_ref = hb.kernel_launch_count() - before
+    wave_net = _net_with(hb, dev, fuse_wave=1)
+    before = hb.kernel_launch_count()
+    out = wave_net(lrs, alphas)
+    launches_wave = hb.kernel_launch_count() - before
+    levels = int(np.floor(np.log2(l)))
+    assert launches_ref - launches_wave == 2 * levels            # one launch per level instead of three
+    assert torch.equal(out, ref)
+    patterns = [alphas.clone() for _ in range(3)]
+    if l > 2:
+        patterns[0][:, l - 1:] = 0                                # trailing padding (utils.py:92-95)
+        patterns[1][0, 1] = 0                                     # a hole: some pair loses its bob at level 0
+        patterns[1][-1, l // 2:] = 0
+        patterns[2][:, 1:] = 0                                    # only view 0 left: every level just carries alice
+        for al in patterns:
+            assert torch.equal(wave_net(lrs * al[:, :, None, None], al), ref_net(lrs * al[:, :, None, None], al))
+    for knobs in ({"wave_streams": 1}, {"wave_streams": 3, "wave_ring_rows": 8}, {"wave_streams": 7, "wave_publish_rows": 3, "wave_ring_rows": 12},
+                  {"wave_ring_rows": 64}):
+        other = _net_with(hb, dev, fuse_wave=1, **knobs)
+        assert torch.equal(other(lrs, alphas), ref), knobs
+        if l > 2:
+            assert torch.equal(other(lrs * patterns[1][:, :, None, None], patterns[1]), ref_net(lrs * patterns[1][:, :, None, None], patterns[1])), knobs
+
+
+def test_wavefront_fusion_soak_c2(hb, dev):
+    """Hand-over protocol under load: 40 back-to-back forwards at BASELINE configs[1] size on two alternating inputs must
+    reproduce the three-launch results every time (a missed release / stale ring row would show up as a changed bit)."""
+    g = torch.Generator().manual_seed(99)
+    xs = [torch.rand(32, 16, 128, 128, generator=g).to(dev) for _ in range(2)]
+    alphas = torch.ones(32, 16, device=dev)
+    ref_net, wave_net = _net_with(hb, dev, fuse_wave=0), _net_with(hb, dev, fuse_wave=1)
+    refs = [ref_net(x, alphas) for x in xs]
+    outs = [wave_net(xs[i % 2], alphas) for i in range(40)]
+    torch.cuda.synchronize()
+    for i, o in enumerate(outs):
+        assert torch.equal(o, refs[i % 2]), i
+
+
+def test_wavefront_fusion_two_handles_two_streams(hb, dev):
+    """Wavefront launches spin on flags of sibling CTAs, so two of them must never share the GPU half and half: the
+    library serialises them per device.  Two models on two streams, interleaved, must both finish and agree."""
+    g = torch.Generator().manual_seed(5)
+    x1, x2 = torch.rand(8, 8, 128, 128, generator=g).to(dev), torch.rand(8, 8, 128, 128, generator=g).to(dev)
+    alphas = torch.ones(8, 8, device=dev)
+    m1, m2 = _net_with(hb, dev), _net_with(hb, dev)
+    r1, r2 = m1(x1, alphas), m2(x2, alphas)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    outs = []
+    for _ in range(10):
+        with torch.cuda.stream(s1):
+            outs.append((m1(x1, alphas), r1))
+        with torch.cuda.stream(s2):
+            outs.append((m2(x2, alphas), r2))
+    torch.cuda.synchronize()
+    assert all(torch.equal(o, r) for o, r in outs)
+
+
 @pytest.mark.parametrize("b,l,s", [(1, 2, 8), (2, 3, 33), (2, 4, 128), (1, 5, 100), (3, 2, 1), (1, 16, 64), (2, 8, 256)])
 def test_multicast_cluster_pairs_are_bit_identical(hb, dev, b, l, s):
     """The 128 -> 128 convs of the fusion stage run as clusters of two CTAs (the two 64-channel output halves of the same
@@ -329,6 +414,7 @@ def test_multicast_cluster_pairs_are_bit_identical(hb, dev, b, l, s):
     model = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval()
     model.load_state_dict(hrnet_oracle.make_params(cases.WEIGHT_SEED))
     model = model.to(dev)
+    model.debug_set(dev, "fuse_wave", 0)        # the three-launch schedule is what uses these convolutions when W <= 128
     g = torch.Generator().manual_seed(2000 + 10 * s + l)
     lrs = torch.rand(b, l, s, s, generator=g).to(dev)
     al = (torch.rand(b, l, generator=g) > 0.25).float()
