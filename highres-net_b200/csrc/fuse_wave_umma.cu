@@ -141,11 +141,10 @@ __device__ __forceinline__ void st_relaxed(uint32_t* p, uint32_t v) {
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // Spin until *p >= want.  Bounded like the mbarrier waits: a protocol bug must surface as a CUDA error, never as a hung GPU.
-static __device__ __noinline__ uint32_t flag_wait_slow(const uint32_t* p, uint32_t want, int tag, bool sleep) {
+static __device__ __noinline__ uint32_t flag_wait_slow(const uint32_t* p, uint32_t want, int tag) {
     const long long t0 = clock64();
     uint32_t v;
     while ((v = ld_relaxed(p)) < want) {
-        if (sleep) __nanosleep(64);
         if (clock64() - t0 > HRN_WAIT_LIMIT_CYCLES) {
             printf("hrn_b200: wavefront flag wait timed out (block %d thread %d tag %d: have %u, want %u)\n",
                    (int)blockIdx.x, (int)threadIdx.x, tag, v, want);
@@ -156,11 +155,30 @@ static __device__ __noinline__ uint32_t flag_wait_slow(const uint32_t* p, uint32
 }
 // Relaxed polling; the caller adds the acquire fence where data written by the flag's producer is read afterwards (the
 // ring-reuse wait needs none: it only orders this CTA's later stores after the consumer's completed reads).
-__device__ __forceinline__ uint32_t flag_wait(const uint32_t* p, uint32_t want, int tag, bool sleep = false) {
+__device__ __forceinline__ uint32_t flag_wait(const uint32_t* p, uint32_t want, int tag) {
     const uint32_t v = ld_relaxed(p);
-    return v >= want ? v : flag_wait_slow(p, want, tag, sleep);
+    return v >= want ? v : flag_wait_slow(p, want, tag);
 }
 __device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// Consumer side: the poll that succeeds must be an acquire (it pairs with the publisher's st.release).  ld.acquire.gpu is a
+// strong load plus an L1 invalidate; a relaxed load followed by fence.acq_rel.gpu costs a full MEMBAR.GPU on the TMA thread
+// for every batch of rows (4 % of the fusion stage, tools/wave_time.py).
+static __device__ __noinline__ uint32_t flag_acquire_slow(const uint32_t* p, uint32_t want, int tag) {
+    const long long t0 = clock64();
+    uint32_t v;
+    while ((v = ld_acquire(p)) < want) {
+        if (clock64() - t0 > HRN_WAIT_LIMIT_CYCLES) {
+            printf("hrn_b200: wavefront row wait timed out (block %d thread %d tag %d: have %u, want %u)\n",
+                   (int)blockIdx.x, (int)threadIdx.x, tag, v, want);
+            __trap();
+        }
+    }
+    return v;
+}
+__device__ __forceinline__ uint32_t flag_acquire(const uint32_t* p, uint32_t want, int tag) {
+    const uint32_t v = ld_acquire(p);
+    return v >= want ? v : flag_acquire_slow(p, want, tag);
+}
 
 // Triage counters (per CTA, cycles): 0 = whole kernel, 1 = TMA thread waiting for the producer's rows, 2 = TMA thread
 // waiting for a free shared-memory slot, 3 = epilogue warp 4 waiting for ring space, 4 = epilogue warp 4 waiting for a full
@@ -265,11 +283,16 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
                                 const uint32_t need = w.lag_rows > 0 ? min(cum + static_cast<uint32_t>(w.lag_rows), total_in) : cum;
                                 if (seen0 < need || seen1 < need) {
                                     WAVE_STAT_BEGIN(t0);
-                                    if (seen0 < need) seen0 = flag_wait(prod, need, 20, w.debug_flags & 512);
-                                    if (seen1 < need) seen1 = flag_wait(prod + FLAG_STRIDE, need, 21, w.debug_flags & 512);
+                                    if (w.debug_flags & 128) {               // A/B: relaxed polls + one device-scope fence
+                                        if (seen0 < need) seen0 = flag_wait(prod, need, 20);
+                                        if (seen1 < need) seen1 = flag_wait(prod + FLAG_STRIDE, need, 21);
+                                        fence_acquire_gpu();
+                                    } else {                                 // acquire polls: pair with the publisher's st.release
+                                        if (seen0 < need) seen0 = flag_acquire(prod, need, 20);
+                                        if (seen1 < need) seen1 = flag_acquire(prod + FLAG_STRIDE, need, 21);
+                                    }
                                     WAVE_STAT_END(t0, 1);
                                     WAVE_STAT_BEGIN(t8);
-                                    if (!(w.debug_flags & 128)) fence_acquire_gpu();         // pairs with the publisher's st.release
                                     if (!(w.debug_flags & 256)) fence_proxy_async_global();  // generic-proxy writes -> async-proxy (TMA) reads
                                     WAVE_STAT_END(t8, 8);
                                 }
@@ -561,19 +584,26 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
                 res_img = w.stack_in + (static_cast<size_t>(b * w.src_views + ip) * w.H * w.W) * 64 + hf * 32;
                 scale = w.alphas[b * w.alpha_stride + (w.top - 1 - ip)];
             }
-            const bool use_res = res_img != nullptr && valid;
+            const bool use_res = res_img != nullptr && valid && !(w.debug_flags & 8);
             const __nv_bfloat162 scale2 = __floats2bfloat162_rn(scale, scale);
             const size_t pix0 = static_cast<size_t>(s.y0) * w.W + x;
             const __nv_bfloat16* rp = res_img + pix0 * 64;
             const size_t r_step = static_cast<size_t>(w.W) * 64;
             __nv_bfloat16* op = nullptr;
             if (conv == 2) op = w.stack_out + (static_cast<size_t>(b * w.src_views + ip) * w.H * w.W + pix0) * 64 + co0;
-            for (int i = 0; i < s.rows; ++i, ++tile, rp += r_step) {
+            // The residual row (skip connection / alice) is fetched one whole row ahead into the other register buffer:
+            // at the L2 latency under load (~2000 cycles) a load issued at the top of its own row made the epilogue as slow
+            // as the tensor pipe (2400 vs 2300 cycles per row) and cost the stream 12 %.
+            uint32_t rv_a[2][8], rv_b[2][8];
+            if (use_res) {
+                ptx::ldg_nc_v8(rp, rv_a[0]);
+                ptx::ldg_nc_v8(rp + 16, rv_a[1]);
+            }
+            auto do_row = [&](int i, uint32_t (&rv)[2][8], uint32_t (&rv_next)[2][8]) {
                 const uint32_t acc = tile % ACC_SLOTS, aph = (tile / ACC_SLOTS) & 1;
-                uint32_t rv[2][8];
-                if (use_res) {
-                    ptx::ldg_nc_v8(rp, rv[0]);
-                    ptx::ldg_nc_v8(rp + 16, rv[1]);
+                if (use_res && i + 1 < s.rows) {
+                    ptx::ldg_nc_v8(rp + r_step, rv_next[0]);
+                    ptx::ldg_nc_v8(rp + r_step + 16, rv_next[1]);
                 }
                 {
                     WAVE_STAT_BEGIN(t4);
@@ -620,8 +650,8 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
                         } else if (seen_c0 < want || (conv == 0 && seen_c1 < want)) {
                             if (lane == 0) {
                                 WAVE_STAT_BEGIN(t3);
-                                if (seen_c0 < want) seen_c0 = flag_wait(cons, want, 30, w.debug_flags & 512);
-                                if (conv == 0 && seen_c1 < want) seen_c1 = flag_wait(cons + FLAG_STRIDE, want, 31, w.debug_flags & 512);
+                                if (seen_c0 < want) seen_c0 = flag_wait(cons, want, 30);
+                                if (conv == 0 && seen_c1 < want) seen_c1 = flag_wait(cons + FLAG_STRIDE, want, 31);
                                 if (warp == 4) WAVE_STAT_END(t3, 3);
                             }
                             seen_c0 = __shfl_sync(0xffffffffu, seen_c0, 0);
@@ -642,6 +672,12 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
                 }
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(bar_rowdone + 8 * (tile % ROWDONE));      // -> publisher (warp 3)
+                ++tile;
+                rp += r_step;
+            };
+            for (int i = 0; i < s.rows; i += 2) {
+                do_row(i, rv_a, rv_b);
+                if (i + 1 < s.rows) do_row(i + 1, rv_b, rv_a);
             }
         }
         // ---- carried views: alice of a pair whose bob has alpha = 0 goes to the next level unchanged (conv C CTAs only)

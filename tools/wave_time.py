@@ -20,14 +20,11 @@ def timed(m, n=60):
     for _ in range(n): m(lrs, al)
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
-configs = [("three launches", dict(wave=0)), ("wave (smem credit, padded flags)", dict(wave=1)),
-           ("wave global polls, padded flags", dict(wave=1, debug_flags=1024)),
-           ("wave ring 32", dict(wave=1, wave_ring_rows=32)), ("wave ring 32 publish 4", dict(wave=1, wave_ring_rows=32, wave_publish_rows=4)),
-           ("wave ring 24 publish 2", dict(wave=1, wave_ring_rows=24, wave_publish_rows=2)),
-           ("wave ring 16 publish 4", dict(wave=1, wave_publish_rows=4)),
-           ("three launches", dict(wave=0))]
+configs = [("three launches", dict(wave=0)), ("wave (acquire polls)", dict(wave=1)), ("wave relaxed polls + fence", dict(wave=1, debug_flags=128)),
+           ("wave no proxy fence", dict(wave=1, debug_flags=256)),
+           ("three launches", dict(wave=0)), ("wave (acquire polls)", dict(wave=1))]
 ref = make(0)(lrs, al)
-for name, kw in (("wave", dict(wave=1)), ("wave global polls", dict(wave=1, debug_flags=1024)), ("wave no flag waits", dict(wave=1, debug_flags=32))):
+for name, kw in (("wave", dict(wave=1)), ("wave no proxy fence", dict(wave=1, debug_flags=256)), ("wave no flag waits", dict(wave=1, debug_flags=32))):
     kw = dict(kw); wave = kw.pop("wave")
     net = make(wave, **kw)
     for _ in range(10): net(lrs, al)
