@@ -273,6 +273,9 @@ class Bench:
         self.net = self.net.to(self.dev)
         if args.no_wave:
             self.net.debug_set(self.dev, "fuse_wave", 0)
+        for kv in args.knob:
+            name, value = kv.split("=")
+            self.net.debug_set(self.dev, name, int(value))
         self.peaks = load_peaks()
         self.gather_stream = torch.cuda.Stream(self.dev) if world > 1 else None
 
@@ -598,6 +601,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lean", action="store_true", help="headline loops and roofline only (A/B runs, ncu captures)")
     ap.add_argument("--no-wave", action="store_true", help="fusion levels as three launches each instead of one wavefront launch (A/B)")
+    ap.add_argument("--knob", action="append", default=[], metavar="NAME=VALUE", help="hrn_debug_set knob for A/B runs (repeatable)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -697,6 +701,7 @@ def main():
                        "sharding": "batch (independent imagesets per rank); no collective inside the model",
                        "fusion_schedule": ("three launches per level (--no-wave)" if args.no_wave else
                                            "one wavefront launch per fusion level (fuse_wave_umma.cu)"),
+                       "knobs": args.knob,
                        "collective": (f"every step: NCCL all_gather of the SR images ({sr_bytes} B per rank, {world * sr_bytes} B "
                                       f"gathered per rank) on a side stream, inside the timed region" if world > 1 else
                                       "none at N=1 (the SR/score gather runs when N > 1)"),

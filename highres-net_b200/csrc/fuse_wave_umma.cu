@@ -52,14 +52,16 @@ constexpr int EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;
 constexpr int BTILE_BYTES = 3 * NT * 128;   // one (kx, chunk) B tile: 192 rows x 64 bf16
 constexpr int CHUNKS = 2;                   // 128 input channels
-constexpr int RING = 4;                     // resident (input row, chunk) buffers
+constexpr int RING = 4;                     // resident (input row, chunk) buffers = 2 rows.  A fifth slot (16,640-byte slots) fits
+                                            // and is bit-identical, but measured no faster: the loads are not what the streams wait for
 constexpr int W_BYTES = 3 * CHUNKS * BTILE_BYTES;   // 147,456
 constexpr int ROWDONE = 16;                 // "row stored by all epilogue warps" barriers (skew between warps < 16 rows)
 constexpr int BAR_OFFSET = W_BYTES + RING * CHUNK_BYTES;
 constexpr int BIAS_OFFSET = BAR_OFFSET + 512;
 constexpr int SMEM_BYTES = BIAS_OFFSET + NT * 4 + 1024;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-static_assert(16 * RING + 16 * ACC_SLOTS + 8 * ROWDONE + 8 + 8 <= 512, "barrier block overflows into the bias array");
+static_assert(16 * RING + 16 * ACC_SLOTS + 8 * ROWDONE + 8 + 8 + 4 <= 512, "barrier block overflows into the bias array");
+static_assert((W_BYTES + RING * CHUNK_BYTES) % 128 == 0, "barrier block alignment");
 constexpr int CTAS_PER_STREAM = 5;
 constexpr int FLAG_STRIDE = 32;             // uint32 per counter: every hand-over counter sits in its own 128-byte line
 constexpr int FLAGS_PER_STREAM = 8 * FLAG_STRIDE;   // prod1[2], cons1[2], prod2[2], cons2, pad
@@ -175,10 +177,6 @@ static __device__ __noinline__ uint32_t flag_acquire_slow(const uint32_t* p, uin
     }
     return v;
 }
-__device__ __forceinline__ uint32_t flag_acquire(const uint32_t* p, uint32_t want, int tag) {
-    const uint32_t v = ld_acquire(p);
-    return v >= want ? v : flag_acquire_slow(p, want, tag);
-}
 
 // Triage counters (per CTA, cycles): 0 = whole kernel, 1 = TMA thread waiting for the producer's rows, 2 = TMA thread
 // waiting for a free shared-memory slot, 3 = epilogue warp 4 waiting for ring space, 4 = epilogue warp 4 waiting for a full
@@ -288,8 +286,9 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
                                         if (seen1 < need) seen1 = flag_wait(prod + FLAG_STRIDE, need, 21);
                                         fence_acquire_gpu();
                                     } else {                                 // acquire polls: pair with the publisher's st.release
-                                        if (seen0 < need) seen0 = flag_acquire(prod, need, 20);
-                                        if (seen1 < need) seen1 = flag_acquire(prod + FLAG_STRIDE, need, 21);
+                                        const uint32_t v0 = ld_acquire(prod), v1 = ld_acquire(prod + FLAG_STRIDE);   // both in flight
+                                        seen0 = v0 >= need ? v0 : flag_acquire_slow(prod, need, 20);
+                                        seen1 = v1 >= need ? v1 : flag_acquire_slow(prod + FLAG_STRIDE, need, 21);
                                     }
                                     WAVE_STAT_END(t0, 1);
                                     WAVE_STAT_BEGIN(t8);

@@ -20,11 +20,10 @@ def timed(m, n=60):
     for _ in range(n): m(lrs, al)
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
-configs = [("three launches", dict(wave=0)), ("wave (acquire polls)", dict(wave=1)), ("wave relaxed polls + fence", dict(wave=1, debug_flags=128)),
-           ("wave no proxy fence", dict(wave=1, debug_flags=256)),
-           ("three launches", dict(wave=0)), ("wave (acquire polls)", dict(wave=1))]
+configs = [("three launches", dict(wave=0)), ("wave (MMA in warp 9)", dict(wave=1)), ("wave (MMA in warp 1)", dict(wave=1, debug_flags=2048)),
+           ("three launches", dict(wave=0)), ("wave (MMA in warp 9)", dict(wave=1)), ("wave (MMA in warp 1)", dict(wave=1, debug_flags=2048))]
 ref = make(0)(lrs, al)
-for name, kw in (("wave", dict(wave=1)), ("wave no proxy fence", dict(wave=1, debug_flags=256)), ("wave no flag waits", dict(wave=1, debug_flags=32))):
+for name, kw in (("wave", dict(wave=1)), ("wave MMA in warp 1", dict(wave=1, debug_flags=2048)), ("wave no flag waits", dict(wave=1, debug_flags=32))):
     kw = dict(kw); wave = kw.pop("wave")
     net = make(wave, **kw)
     for _ in range(10): net(lrs, al)
