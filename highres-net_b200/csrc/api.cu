@@ -192,7 +192,7 @@ int ensure_workspace(hrn_handle* h, int B, int L, int H, int W) {
     if (grow(reinterpret_cast<void**>(&h->anchor), &h->anchor_cap, static_cast<size_t>(B) * hw * sizeof(float))) return -1;
     if (grow(reinterpret_cast<void**>(&h->lists), &h->lists_cap, hrn::live_lists_ints(B, L) * sizeof(int))) return -1;
     if (grow(reinterpret_cast<void**>(&h->live_scratch), &h->live_scratch_cap, hrn::live_scratch_bytes(B, L))) return -1;
-    if (h->fuse_wave && W <= 128 && hrn::fuse_wave_streams(h->sm_count) >= 1) {
+    if (h->fuse_wave && W <= 128 && hrn::fuse_wave_streams(h->sm_count) >= 1 && hrn::fuse_wave_fits(h->sm_count)) {
         const size_t ring = hrn::fuse_wave_ring_bytes(h->sm_count, h->wave_ring_rows, W);
         for (int i = 0; i < 2; ++i)
             if (grow(reinterpret_cast<void**>(&h->wave_ring[i]), &h->wave_ring_cap[i], ring)) return -1;

@@ -704,6 +704,27 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
 }  // namespace
 
 int fuse_wave_streams(int sm_count) { return sm_count / CTAS_PER_STREAM; }
+
+// The CTAs of a wavefront grid wait for one another, so the whole grid has to be resident at once.  Asked once per device:
+// how many CTAs of this kernel fit (one per SM with 214 KB of shared memory, fewer when the context is limited to a share of
+// the SMs); the caller falls back to the three-launch schedule when the answer is smaller than the grid.
+bool fuse_wave_fits(int sm_count) {
+    static int max_ctas[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    static bool attr_set[64] = {};
+    if (allow_dynamic_smem(fuse_wave_kernel, SMEM_BYTES, attr_set)) return false;
+    std::lock_guard<std::mutex> lock(lazy_init_mutex());
+    if (max_ctas[dev] == 0) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fuse_wave_kernel, NUM_THREADS, SMEM_BYTES) != cudaSuccess) {
+            cudaGetLastError();
+            per_sm = 0;
+        }
+        max_ctas[dev] = per_sm > 0 ? per_sm * sm_count : -1;
+    }
+    return max_ctas[dev] >= fuse_wave_streams(sm_count) * CTAS_PER_STREAM;
+}
 size_t fuse_wave_ring_bytes(int sm_count, int ring_rows, int W) {
     return static_cast<size_t>(fuse_wave_streams(sm_count)) * ring_rows * W * 128 * sizeof(__nv_bfloat16);
 }

@@ -118,6 +118,7 @@ struct FuseWaveArgs {
     int lag_rows;                      // triage: consumers stay this many rows behind their producer
 };
 int fuse_wave_streams(int sm_count);
+bool fuse_wave_fits(int sm_count);        // every CTA of a wavefront grid can be resident at once on the current device
 size_t fuse_wave_ring_bytes(int sm_count, int ring_rows, int W);
 size_t fuse_wave_flag_bytes(int sm_count);
 int fuse_wave_launch(const FuseWaveArgs& a, int sm_count, cudaStream_t stream);

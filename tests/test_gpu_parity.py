@@ -1081,7 +1081,8 @@ def test_forward_host_accepts_raw_u16_views(net, dev):
 
 # ---------------------------------------------------------------------------- ShiftNet
 # bf16 activations / weights with fp32 accumulation through 8 conv layers and a K = 32768 GEMM, against the fp32 reference
-SHIFTNET_GATE = 2e-2      # absolute, on thetas of magnitude ~0.2-0.7 (measured: see DESIGN.md)
+SHIFTNET_GATE = 1e-2      # absolute, on thetas of magnitude ~0.2-0.7: bf16 activations and weights through 8 conv layers and a K = 32768
+                          # contraction; measured 4.6e-3, so the gate keeps 2x of headroom instead of 4x
 
 
 @pytest.fixture(scope="module")
