@@ -73,7 +73,7 @@ def _ncu_rows():
 
 def _ncu_tag(kernel_class):
     return (kernel_class.replace("conv3x3_umma", "conv3x3_umma_kernel").replace("resblock64_umma", "resblock64_umma_kernel")
-            .replace("fuse_wave", "fuse_wave_kernel").rstrip(">"))
+            .replace("fuse_wave", "fuse_wave_kernel").replace("enc_wave", "enc_wave_kernel").rstrip(">"))
 
 
 def ncu_class_stats(kernel_class):
@@ -640,7 +640,7 @@ def main():
         ms_step = ms_total / args.steps
         value = total_sets / ms_total * 1e3
         e2e_value = total_sets / ms_e2e * 1e3
-        tensor_classes = ("conv3x3_umma<64>", "conv3x3_umma<128>", "resblock64_umma", "fuse_wave")
+        tensor_classes = ("conv3x3_umma<64>", "conv3x3_umma<128>", "resblock64_umma", "fuse_wave", "enc_wave")
         dom = max(tensor_classes, key=lambda k: prof[k]["ms"])
         ach = prof[dom]["flops"] / max(prof[dom]["ms"], 1e-9) / 1e9       # TFLOP/s
         ncu = ncu_class_stats(dom) or {}

@@ -68,6 +68,10 @@ struct hrn_handle {
     int mcast = 1;                     // 128 -> 128 convs as cluster pairs with multicast A rows (0: plain launch, test knob)
     int fuse_resblock = 1;             // encoder ResidualBlocks as one launch each (resblock64_umma.cu) when W <= 128
     int fuse_wave = 1;                 // fusion levels as one wavefront launch each (fuse_wave_umma.cu) when W <= 128
+    int enc_wave = 1;                  // encoder ResidualBlocks + final conv as one wavefront launch (enc_wave_umma.cu) when W <= 128
+    int enc_ring_rows = 24;            // rows per stream ring of the encoder wavefront (x1 has two readers, the second ~10 rows later)
+    __nv_bfloat16* enc_ring[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t enc_ring_cap[4] = {0, 0, 0, 0};
     int wave_ring_rows = 16;           // rows per stream ring of the wavefront schedule (test knob, >= 8)
     int wave_streams = 0;              // streams of the wavefront schedule (0 = sm_count / 5; test knob)
     int wave_publish_rows = 1;         // rows per hand-over publication of the wavefront schedule
@@ -192,11 +196,17 @@ int ensure_workspace(hrn_handle* h, int B, int L, int H, int W) {
     if (grow(reinterpret_cast<void**>(&h->anchor), &h->anchor_cap, static_cast<size_t>(B) * hw * sizeof(float))) return -1;
     if (grow(reinterpret_cast<void**>(&h->lists), &h->lists_cap, hrn::live_lists_ints(B, L) * sizeof(int))) return -1;
     if (grow(reinterpret_cast<void**>(&h->live_scratch), &h->live_scratch_cap, hrn::live_scratch_bytes(B, L))) return -1;
-    if (h->fuse_wave && W <= 128 && hrn::fuse_wave_streams(h->sm_count) >= 1 && hrn::fuse_wave_fits(h->sm_count)) {
+    if ((h->fuse_wave || h->enc_wave) && W <= 128 && hrn::fuse_wave_streams(h->sm_count) >= 1 && hrn::fuse_wave_fits(h->sm_count)) {
         const size_t ring = hrn::fuse_wave_ring_bytes(h->sm_count, h->wave_ring_rows, W);
         for (int i = 0; i < 2; ++i)
             if (grow(reinterpret_cast<void**>(&h->wave_ring[i]), &h->wave_ring_cap[i], ring)) return -1;
-        if (grow(reinterpret_cast<void**>(&h->wave_flags), &h->wave_flags_cap, 16 * hrn::fuse_wave_flag_bytes(h->sm_count))) return -1;
+        if (grow(reinterpret_cast<void**>(&h->wave_flags), &h->wave_flags_cap,
+                 16 * hrn::fuse_wave_flag_bytes(h->sm_count) + hrn::enc_wave_flag_bytes(h->sm_count))) return -1;
+        if (h->enc_wave && hrn::enc_wave_fits(h->sm_count)) {
+            const size_t ering = hrn::enc_wave_ring_bytes(h->sm_count, h->enc_ring_rows, W);
+            for (int i = 0; i < 4; ++i)
+                if (grow(reinterpret_cast<void**>(&h->enc_ring[i]), &h->enc_ring_cap[i], ering)) return -1;
+        }
     }
     return 0;
 }
@@ -285,8 +295,8 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
     if (h->ev_fwd_done == nullptr) HRN_CUDA_OK(cudaEventCreateWithFlags(&h->ev_fwd_done, cudaEventDisableTiming));
     if (h->have_last && h->last_stream != s) HRN_CUDA_OK(cudaStreamWaitEvent(s, h->ev_fwd_done, 0));
     SpanGuard whole(h, s, HRN_PROF_FORWARD, 0.0);
-    if (h->wave_flags != nullptr && dump == nullptr && h->fuse_wave && W <= 128)     // hand-over counters of the wavefront levels
-        HRN_CUDA_OK(cudaMemsetAsync(h->wave_flags, 0, static_cast<size_t>(hrn::live_levels(L)) * hrn::fuse_wave_flag_bytes(h->sm_count), s));
+    if (h->wave_flags != nullptr && dump == nullptr && (h->fuse_wave || h->enc_wave) && W <= 128)     // hand-over counters of the wavefront launches
+        HRN_CUDA_OK(cudaMemsetAsync(h->wave_flags, 0, h->wave_flags_cap, s));
 
     // ---- live-work lists: views / pairs that cannot reach the output (alpha = 0 padding) are not computed at all.
     // The stage-dump hook asks for dense lists so that every intermediate tensor is defined.  Must stay the first
@@ -327,6 +337,47 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
     base.live_list = enc_list;
     base.live_count = enc_count;
     int cur = 0;
+    // Wavefront schedules spin on flags written by sibling CTAs: they are serialised per device (see g_wave_mutex); the lock
+    // covers the enqueue of every wavefront launch of this forward.
+    const bool wave_ok = dump == nullptr && W <= 128 && h->wave_flags != nullptr;
+    bool enc_as_wave = wave_ok && h->enc_wave && h->cfg.enc_num_layers == 2 && h->enc_ring[0] != nullptr;
+    for (int i = 0; i < 4 && enc_as_wave; ++i) enc_as_wave = h->enc[i].has_prelu;
+    const bool fuse_as_wave = wave_ok && h->fuse_wave && L >= 2 && h->fuse[0].has_prelu && h->fuse[1].has_prelu && h->fuse[2].has_prelu;
+    std::unique_lock<std::mutex> wave_lock(g_wave_mutex, std::defer_lock);
+    if (enc_as_wave || fuse_as_wave) {
+        wave_lock.lock();
+        cudaEvent_t& ev = g_wave_event[h->device];
+        if (ev == nullptr) HRN_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        else HRN_CUDA_OK(cudaStreamWaitEvent(s, ev, 0));
+    }
+    if (enc_as_wave) {
+        // the two ResidualBlocks and the final conv in one launch (enc_wave_umma.cu): x0 = act[0] -> view stack = act[1]
+        hrn::EncWaveLaunch ew{};
+        ew.H = H;
+        ew.W = W;
+        ew.n_img = static_cast<int>(n_img);
+        ew.live_list = enc_list;
+        ew.live_count = enc_count;
+        ew.x0 = h->act[0];
+        ew.out = h->act[1];
+        for (int i = 0; i < 4; ++i) ew.ring[i] = h->enc_ring[i];
+        ew.ring_rows = h->enc_ring_rows;
+        ew.flags = h->wave_flags + 16 * (hrn::fuse_wave_flag_bytes(h->sm_count) / sizeof(uint32_t));
+        ew.debug_flags = h->debug_flags;
+        ew.streams = h->wave_streams;
+        for (int i = 0; i < 5; ++i) {
+            ew.w_img[i] = h->enc[i].w_img;
+            ew.bias[i] = h->enc[i].bias;
+            ew.prelu[i] = h->enc[i].prelu;
+            ew.has_prelu[i] = h->enc[i].has_prelu ? 1 : 0;
+        }
+        {
+            SpanGuard guard(h, s, HRN_PROF_ENC_WAVE, 5.0 * 2.0 * 9.0 * 64 * 64 * static_cast<double>(n_img) * hw);
+            if (hrn::enc_wave_launch(ew, h->sm_count, s)) return -1;
+        }
+        cur = 1;
+        stage += 5;
+    } else {
     for (int r = 0; r < h->cfg.enc_num_layers; ++r) {
         const int t1 = (cur + 1) % 3, t2 = (cur + 2) % 3;
         hrn::ConvArgs a = base;
@@ -379,6 +430,8 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
         if (maybe_dump(dump, HRN_STAGE_ENC(++stage), h->act[cur], base.n_img, H, W, 64, s)) return -1;
     }
 
+    }
+
     // ---- recursive fusion (HRNet.py:99-134), in place: the 64-channel view stack keeps its stride of L images per
     // imageset at every level and the merged pair (b, i) overwrites alice's slot b * L + i.  A pair that is not live
     // (alpha_bob = 0) therefore needs no work at all: alice is already where the next level expects it.
@@ -388,13 +441,7 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
     // Wavefront schedule (fuse_wave_umma.cu): one launch per level, the 128-channel intermediates stay in L2-resident rings,
     // the level writes into a second view stack (act[3]); images wider than one column tile and the stage-dump hook take
     // the three-launch schedule below.
-    const bool wave = h->fuse_wave && dump == nullptr && W <= 128 && h->wave_flags != nullptr && h->fuse[0].has_prelu &&
-                      h->fuse[1].has_prelu && h->fuse[2].has_prelu && hrn::live_levels(L) <= 16;
-    if (wave && n / 2 > 0) {
-        std::lock_guard<std::mutex> lock(g_wave_mutex);
-        cudaEvent_t& ev = g_wave_event[h->device];
-        if (ev == nullptr) HRN_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        else HRN_CUDA_OK(cudaStreamWaitEvent(s, ev, 0));
+    if (fuse_as_wave) {
         const size_t flag_ints = hrn::fuse_wave_flag_bytes(h->sm_count) / sizeof(uint32_t);
         __nv_bfloat16* other = h->act[3];
         while (n / 2 > 0) {
@@ -439,7 +486,10 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
             n = half;
             ++level;
         }
-        HRN_CUDA_OK(cudaEventRecord(ev, s));
+    }
+    if (wave_lock.owns_lock()) {
+        HRN_CUDA_OK(cudaEventRecord(g_wave_event[h->device], s));
+        wave_lock.unlock();
     }
     while (n / 2 > 0) {
         const int half = n / 2, top = n - (n % 2);
@@ -589,6 +639,7 @@ void hrn_destroy(hrn_handle* h) {
     rel(h->wave_ring[1]);
     rel(h->wave_flags);
     rel(h->wave_stats);
+    for (auto* p : h->enc_ring) rel(p);
     for (auto* p : h->io) rel(p);
     rel(h->io_u16);
     if (h->ev_fwd_done != nullptr) cudaEventDestroy(h->ev_fwd_done);
@@ -1058,6 +1109,15 @@ int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value) {
     else if (strcmp(knob, "strip_split") == 0) h->strip_split = value;
     else if (strcmp(knob, "fuse_resblock") == 0) h->fuse_resblock = value != 0;
     else if (strcmp(knob, "fuse_wave") == 0) h->fuse_wave = value != 0;
+    else if (strcmp(knob, "enc_wave") == 0) h->enc_wave = value != 0;
+    else if (strcmp(knob, "enc_ring_rows") == 0) {
+        if (value < 12 || value > 4096) {
+            set_error("hrn_debug_set: enc_ring_rows must be in [12, 4096]");
+            return -1;
+        }
+        if (value > h->enc_ring_rows) h->enc_ring_cap[0] = h->enc_ring_cap[1] = h->enc_ring_cap[2] = h->enc_ring_cap[3] = 0;
+        h->enc_ring_rows = value;
+    }
     else if (strcmp(knob, "wave_streams") == 0) h->wave_streams = value;
     else if (strcmp(knob, "wave_publish_rows") == 0) h->wave_publish_rows = value < 1 ? 1 : value;
     else if (strcmp(knob, "wave_lag_rows") == 0) h->wave_lag_rows = value < 0 ? 0 : value;

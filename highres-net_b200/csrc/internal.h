@@ -123,6 +123,30 @@ size_t fuse_wave_ring_bytes(int sm_count, int ring_rows, int W);
 size_t fuse_wave_flag_bytes(int sm_count);
 int fuse_wave_launch(const FuseWaveArgs& a, int sm_count, cudaStream_t stream);
 
+// enc_wave_umma.cu: the encoder's two ResidualBlocks and its final conv (five 64 -> 64 convolutions) as one wavefront launch.
+struct EncWaveLaunch {
+    int H, W;
+    int n_img;                         // images of x0 / out (B * L)
+    const int* live_list;              // live views and their count (device)
+    const int* live_count;
+    const __nv_bfloat16* x0;           // (n_img, H, W, 64) bf16: output of the first conv
+    __nv_bfloat16* out;                // (n_img, H, W, 64) bf16: the view stack
+    __nv_bfloat16* ring[4];            // enc_wave_ring_bytes() each
+    int ring_rows;
+    uint32_t* flags;                   // enc_wave_flag_bytes(), all zero when the launch starts
+    const uint8_t* w_img[5];           // R0a, R0b, R1a, R1b, FIN: conv3x3_pack_weights images
+    const float* bias[5];
+    float prelu[5];
+    int has_prelu[5];
+    int debug_flags;
+    int streams;                       // 0 = sm_count / 5
+};
+int enc_wave_streams(int sm_count);
+bool enc_wave_fits(int sm_count);
+size_t enc_wave_ring_bytes(int sm_count, int ring_rows, int W);
+size_t enc_wave_flag_bytes(int sm_count);
+int enc_wave_launch(const EncWaveLaunch& a, int sm_count, cudaStream_t stream);
+
 // ------------------------------------------------------------------ pointwise / CUDA-core kernels
 int median_anchor_launch(const float* lrs, int B, int L, int H, int W, float* anchor, cudaStream_t s);
 // conv_init_umma.cu: conv 2->64 + PReLU on (view, anchor) pairs on the tensor cores (A operand built in smem with a

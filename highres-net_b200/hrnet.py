@@ -102,7 +102,7 @@ class HRNet(NativeHandleMixin, nn.Module):
         _lib.check(_lib.load().hrn_debug_set(handle, knob.encode(), int(value)), "hrn_debug_set")
 
     PROFILE_CLASSES = ("conv3x3_umma<64>", "conv3x3_umma<128>", "conv_init", "decoder", "median_anchor",
-                       "resblock64_umma", "live_lists", "forward_span", "fuse_wave")
+                       "resblock64_umma", "live_lists", "forward_span", "fuse_wave", "enc_wave")
 
     def profile_begin(self, device) -> None:
         """Arm per-launch CUDA-event timing of the following forward calls (hrn_profile_begin)."""

@@ -186,7 +186,8 @@ int32_t hrn_scoring_debug_set(const char* knob, int32_t value);
 #define HRN_PROF_LIVE_LISTS 6 /* live-work lists (first launch of every forward) */
 #define HRN_PROF_FORWARD 7    /* one span around the whole forward: FORWARD - sum(classes 0..6) = gaps between launches */
 #define HRN_PROF_FUSE_WAVE 8  /* fused fusion level (three convs of one level in one wavefront launch) */
-#define HRN_PROF_CLASSES 9
+#define HRN_PROF_ENC_WAVE 9   /* encoder ResidualBlocks + final conv (five 64 -> 64 convs in one wavefront launch) */
+#define HRN_PROF_CLASSES 10
 int32_t hrn_profile_begin(hrn_handle* h);
 int32_t hrn_profile_end(hrn_handle* h, double* ms, double* flops, int64_t* launches);
 

@@ -1,23 +1,22 @@
-"""First-light check of the wavefront fusion kernel: SR bit-identical to the three-launch schedule on growing shapes.
-Run under `timeout`: a protocol bug shows up as a trap after the bounded waits, never as a hang."""
+"""First-light check of the wavefront kernels (encoder chain, fusion levels): SR bit-identical to the per-layer launches on
+growing shapes.  Run under `timeout`: a protocol bug shows up as a trap after the bounded waits, never as a hang."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import highres_net_b200 as hb
 from oracle import hrnet_oracle
 dev = torch.device("cuda:0")
-def make(wave, **knobs):
+def make(**knobs):
     net = hb.HRNet(hrnet_oracle.DEFAULT_NETWORK_CONFIG).eval(); net.load_state_dict(hrnet_oracle.make_params(0)); net = net.to(dev)
-    net.debug_set(dev, "fuse_wave", wave)
     for k, v in knobs.items(): net.debug_set(dev, k, v)
     return net
-ref_net = make(0)
+ref_net = make(fuse_wave=0, enc_wave=0)
 shapes = [(1, 2, 8), (1, 2, 16), (2, 3, 33), (1, 4, 64), (2, 4, 128), (1, 5, 100), (3, 2, 1), (1, 16, 64), (4, 8, 128), (32, 16, 128)]
 if len(sys.argv) > 1: shapes = shapes[:int(sys.argv[1])]
-for knobs in ({}, {"wave_streams": 1}, {"wave_streams": 3}, {"wave_streams": 7, "wave_ring_rows": 8}):
-    net = make(1, **knobs)
+for knobs in ({"fuse_wave": 0, "enc_wave": 1}, {}, {"wave_streams": 1}, {"wave_streams": 3, "enc_ring_rows": 12}, {"wave_streams": 7, "wave_ring_rows": 8}):
+    net = make(**knobs)
     for (b, l, s) in shapes:
-        if knobs and b * l * s * s > 4 * 8 * 128 * 128: continue
+        if "wave_streams" in knobs and b * l * s * s > 4 * 8 * 128 * 128: continue
         g = torch.Generator().manual_seed(b * 1000 + l * 10 + s)
         lrs = torch.rand(b, l, s, s, generator=g).to(dev); al = torch.ones(b, l, device=dev)
         if b > 1 and l > 2:
@@ -32,13 +31,18 @@ for knobs in ({}, {"wave_streams": 1}, {"wave_streams": 3}, {"wave_streams": 7, 
             bad = d.amax(dim=(1, 2)); rows = d.amax(dim=2)
             print("  per-imageset max:", bad.cpu().numpy().round(5).tolist()[:8])
             r = rows[int(bad.argmax())].cpu().numpy(); print("  bad SR rows (of %d):" % r.shape[0], np.nonzero(r > 0)[0][:40].tolist())
-# timing A/B at C2
-net = make(1); lrs = torch.rand(32, 16, 128, 128, device=dev); al = torch.ones(32, 16, device=dev)
-for name, m in (("three launches", ref_net), ("wavefront", net), ("three launches", ref_net), ("wavefront", net)):
+lrs = torch.rand(32, 16, 128, 128, device=dev); al = torch.ones(32, 16, device=dev)
+nets = [("per-layer launches", ref_net), ("fusion wavefront only", make(enc_wave=0)), ("encoder + fusion wavefronts", make()),
+        ("enc ring 16", make(enc_ring_rows=16)), ("enc ring 48", make(enc_ring_rows=48))]
+for name, m in nets + nets[:3]:
     for _ in range(20): m(lrs, al)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(100): m(lrs, al)
     e1.record(); torch.cuda.synchronize()
-    print(name, f"{e0.elapsed_time(e1) / 100:.3f} ms per C2 step", flush=True)
+    m.profile_begin(dev)
+    for _ in range(5): m(lrs, al)
+    pr = m.profile_end(dev)
+    enc = (pr["enc_wave"]["ms"] + pr["resblock64_umma"]["ms"] + pr["conv3x3_umma<64>"]["ms"]) / 5
+    print(f"{name:30s} {e0.elapsed_time(e1) / 100:.3f} ms per C2 step   encoder convs {enc:.3f} ms", flush=True)
