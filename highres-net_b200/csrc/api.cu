@@ -68,7 +68,9 @@ struct hrn_handle {
     int mcast = 1;                     // 128 -> 128 convs as cluster pairs with multicast A rows (0: plain launch, test knob)
     int fuse_resblock = 1;             // encoder ResidualBlocks as one launch each (resblock64_umma.cu) when W <= 128
     int fuse_wave = 1;                 // fusion levels as one wavefront launch each (fuse_wave_umma.cu) when W <= 128
-    int enc_wave = 1;                  // encoder ResidualBlocks + final conv as one wavefront launch (enc_wave_umma.cu) when W <= 128
+    int enc_wave = 0;                  // 1: encoder ResidualBlocks + final conv as one wavefront launch (enc_wave_umma.cu, W <= 128).
+                                       // Off by default: bit-identical and 4.5 GB less DRAM traffic, but 3.4 ms against 2.3-2.6 ms
+                                       // (the two skip stages are bound by the load/store unit; profiles/r02_enc_wave_triage.log)
     int enc_ring_rows = 24;            // rows per stream ring of the encoder wavefront (x1 has two readers, the second ~10 rows later)
     __nv_bfloat16* enc_ring[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t enc_ring_cap[4] = {0, 0, 0, 0};
@@ -78,7 +80,8 @@ struct hrn_handle {
     int wave_lag_rows = 0;             // triage: consumers stay this many rows behind their producer
     __nv_bfloat16* wave_ring[2] = {nullptr, nullptr};
     size_t wave_ring_cap[2] = {0, 0};
-    unsigned long long* wave_stats = nullptr;   // triage counters of the wavefront kernel (knob "wave_stats"), 8 per CTA
+    unsigned long long* wave_stats = nullptr;   // triage counters of the fusion wavefront kernel (knob "wave_stats"), 12 per CTA
+    unsigned long long* enc_stats = nullptr;    // the same for the encoder wavefront (knob "enc_stats")
     uint32_t* wave_flags = nullptr;    // 16 levels x fuse_wave_flag_bytes()
     size_t wave_flags_cap = 0;
     int host_chunks = 0;               // hrn_forward_host pipeline depth (0 = automatic)
@@ -365,6 +368,7 @@ int forward_impl(hrn_handle* h, const float* lrs, const float* alphas, int B, in
         ew.flags = h->wave_flags + 16 * (hrn::fuse_wave_flag_bytes(h->sm_count) / sizeof(uint32_t));
         ew.debug_flags = h->debug_flags;
         ew.streams = h->wave_streams;
+        ew.stats = h->enc_stats;
         for (int i = 0; i < 5; ++i) {
             ew.w_img[i] = h->enc[i].w_img;
             ew.bias[i] = h->enc[i].bias;
@@ -639,6 +643,7 @@ void hrn_destroy(hrn_handle* h) {
     rel(h->wave_ring[1]);
     rel(h->wave_flags);
     rel(h->wave_stats);
+    rel(h->enc_stats);
     for (auto* p : h->enc_ring) rel(p);
     for (auto* p : h->io) rel(p);
     rel(h->io_u16);
@@ -1144,6 +1149,40 @@ int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value) {
             }
             HRN_CUDA_OK(cudaFree(h->wave_stats));
             h->wave_stats = nullptr;
+        }
+    }
+    else if (strcmp(knob, "wave_ring_rows") == 0) {
+        if (value < 8 || value > 4096) {
+            set_error("hrn_debug_set: wave_ring_rows must be in [8, 4096]");
+            return -1;
+        }
+        if (value > h->wave_ring_rows) h->wave_ring_cap[0] = h->wave_ring_cap[1] = 0;   // regrown by the next forward
+        h->wave_ring_rows = value;
+    }
+    else if (strcmp(knob, "mcast") == 0) h->mcast = value;        // 0 = plain, 1 = cluster pairs if they fit, 2 = required
+    else if (strcmp(knob, "enc_stats") == 0) {
+        // 1: start collecting per-CTA wait counters of the wavefront kernel; 0: print their per-role means to stderr and stop
+        hrn::DeviceGuard on_device(h->device);
+        const size_t n = static_cast<size_t>(h->sm_count) * 12;
+        if (value) {
+            if (h->enc_stats == nullptr) HRN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&h->enc_stats), n * sizeof(unsigned long long)));
+            HRN_CUDA_OK(cudaDeviceSynchronize());
+            HRN_CUDA_OK(cudaMemset(h->enc_stats, 0, n * sizeof(unsigned long long)));
+        } else if (h->enc_stats != nullptr) {
+            HRN_CUDA_OK(cudaDeviceSynchronize());
+            std::vector<unsigned long long> host(n);
+            HRN_CUDA_OK(cudaMemcpy(host.data(), h->enc_stats, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            const char* names[5] = {"R0a", "R0b", "R1a", "R1b", "FIN"};
+            const int streams = h->wave_streams > 0 ? h->wave_streams : h->sm_count / 5;
+            fprintf(stderr, "encoder wavefront triage (mean cycles per CTA over %d streams): kernel | TMA wait rows | TMA wait smem slot | epi wait ring space | epi wait accumulator | publisher wait rows | publisher stores | MMA wait input row\n", streams);
+            for (int r = 0; r < 5; ++r) {
+                double m[12] = {};
+                for (int st = 0; st < streams; ++st)
+                    for (int k = 0; k < 12; ++k) m[k] += static_cast<double>(host[(static_cast<size_t>(st) * 5 + r) * 12 + k]) / streams;
+                fprintf(stderr, "  %s %12.0f %12.0f %12.0f %12.0f %12.0f %12.0f %12.0f %10.0f | TMA fences %10.0f TMA loop %10.0f\n", names[r], m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9]);
+            }
+            HRN_CUDA_OK(cudaFree(h->enc_stats));
+            h->enc_stats = nullptr;
         }
     }
     else if (strcmp(knob, "wave_ring_rows") == 0) {

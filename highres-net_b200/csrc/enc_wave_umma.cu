@@ -71,6 +71,7 @@ struct EncWaveArgs {
     uint32_t* flags;                   // (streams, FLAGS_PER_STREAM), zero before the launch
     EncStage stage[STAGES];
     int debug_flags;
+    unsigned long long* stats;         // optional triage counters, 12 per CTA
 };
 
 // The stream's range of the flattened (live view, row) space, as per-image strips extended by `e` halo rows on both sides
@@ -120,10 +121,9 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
 // 32 bytes from a ring row another SM wrote earlier in this launch: L2 only (the line may sit stale in this SM's L1 from the
 // ring's previous lap)
 __device__ __forceinline__ void ldg_cg_v8(const void* p, uint32_t (&r)[8]) {
-    asm volatile("ld.global.cg.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p));
-    asm volatile("ld.global.cg.v4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "l"(static_cast<const uint8_t*>(p) + 16));
+    asm volatile("ld.global.cg.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
 }
 
 // Bounded spin: a protocol bug must surface as a CUDA error, never as a hung GPU.
@@ -140,8 +140,10 @@ static __device__ __noinline__ uint32_t flag_acquire_slow(const uint32_t* p, uin
     return v;
 }
 
-#define WAVE_STAT_BEGIN(var) do { } while (0)
-#define WAVE_STAT_END(var, idx) do { } while (0)
+// Triage counters (per CTA, cycles), same layout as fuse_wave_umma.cu.
+#define WAVE_STAT_BEGIN(var) const long long var = w.stats != nullptr ? clock64() : 0
+#define WAVE_STAT_END(var, idx) \
+    if (w.stats != nullptr) atomicAdd(w.stats + static_cast<size_t>(blockIdx.x) * 12 + (idx), static_cast<unsigned long long>(clock64() - var))
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 enc_wave_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_r0,
@@ -208,6 +210,7 @@ enc_wave_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
             bool have = walk.next(s);
             ptx::pdl_wait();                 // weights and lists are constants; x0 comes from the previous kernel
             uint32_t it = 0, cum = 0, seen = 0;   // cum: in-image input rows requested so far = rows the producer must have stored
+            WAVE_STAT_BEGIN(t9);
             const uint32_t* prod = flags + F_PROD + (conv - 1) * FLAG_STRIDE;
             for (; have; have = walk.next(s)) {
                 for (int q = 0; q < s.rows + 2; ++q, ++it) {
@@ -218,20 +221,27 @@ enc_wave_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
                             yc = static_cast<int>(cum % static_cast<uint32_t>(R));
                             ++cum;
                             if (seen < cum && !(w.debug_flags & 32)) {
+                                WAVE_STAT_BEGIN(t0);
                                 const uint32_t v = ld_acquire(prod);                 // pairs with the publisher's st.release
                                 seen = v >= cum ? v : flag_acquire_slow(prod, cum, 20);
                                 fence_proxy_async_global();  // generic-proxy writes -> async-proxy (TMA) reads
+                                WAVE_STAT_END(t0, 1);
                             }
                         } else {
                             yc = -1;
                         }
                     }
                     const uint32_t slot = it % RING, ph = (it / RING) & 1;
-                    ptx::mbar_wait(bar_empty + 8 * slot, ph ^ 1, 1);
+                    {
+                        WAVE_STAT_BEGIN(t1);
+                        ptx::mbar_wait(bar_empty + 8 * slot, ph ^ 1, 1);
+                        WAVE_STAT_END(t1, 2);
+                    }
                     ptx::mbar_expect_tx(bar_full + 8 * slot, CHUNK_TX);
                     ptx::tma_load_4d(ring_s + slot * CHUNK_BYTES, in_map, 0, -1, yc, conv == 0 ? s.m : stream, bar_full + 8 * slot);
                 }
             }
+            WAVE_STAT_END(t9, 9);
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer: ONE elected thread (see conv3x3_umma.cu)
@@ -441,7 +451,12 @@ enc_wave_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
                 walk_skip.next(sk);
                 const int in_lo = max(0, s.y0 - 1), in_hi = min(w.H, s.y0 + s.rows + 1);
                 for (int i = 0; i < s.rows; ++i, ++k) {
-                    ptx::mbar_wait(bar_rowdone + 8 * (k % ROWDONE), (k / ROWDONE) & 1, 8);   // all eight epilogue warps are done with row k
+                    {
+                        WAVE_STAT_BEGIN(t5);
+                        ptx::mbar_wait(bar_rowdone + 8 * (k % ROWDONE), (k / ROWDONE) & 1, 8);   // all eight epilogue warps are done with row k
+                        WAVE_STAT_END(t5, 5);
+                    }
+                    WAVE_STAT_BEGIN(t6);
                     while (i + 1 < s.rows && ptx::mbar_test_wait(bar_rowdone + 8 * ((k + 1) % ROWDONE), ((k + 1) / ROWDONE) & 1)) {
                         ++i;
                         ++k;
@@ -455,6 +470,7 @@ enc_wave_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
                         st_release(prod, k + 1);
                         next_pub = k + 2;
                     }
+                    WAVE_STAT_END(t6, 6);
                 }
                 in_base += static_cast<uint32_t>(in_hi - in_lo);
                 skip_base += static_cast<uint32_t>(sk.rows);
@@ -485,41 +501,51 @@ enc_wave_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
             walk_skip.next(sk);
             // skip connection: R0b adds x0 (a tensor of the previous kernel), R1b adds x1 (ring 1, written by R0b in this launch)
             const bool res_x0 = conv == 1, res_ring = conv == SKIP_STAGE;
-            const bool use_res = (res_x0 || res_ring) && valid;
+            const bool use_res = (res_x0 || res_ring) && valid && !(w.debug_flags & 8);
             const __nv_bfloat16* rp = nullptr;
             if (res_x0) rp = w.x0 + ((static_cast<size_t>(s.m) * w.H + s.y0) * w.W + x) * 64 + co0;
-            uint32_t ring_row = skip_base + static_cast<uint32_t>(s.y0 - sk.y0);      // ring-1 row counter of image row s.y0
+            const uint32_t ring_row0 = skip_base + static_cast<uint32_t>(s.y0 - sk.y0);   // ring-1 row counter of image row s.y0
             auto res_ptr = [&](uint32_t rr) {
                 return w.ring[SKIP_RING] + ((static_cast<size_t>(stream) * R + rr % R) * w.W + x) * 64 + co0;
             };
             const size_t r_step = static_cast<size_t>(w.W) * 64;
             __nv_bfloat16* op = nullptr;
             if (conv == STAGES - 1) op = w.out + ((static_cast<size_t>(s.m) * w.H + s.y0) * w.W + x) * 64 + co0;
-            // The residual row is fetched a row ahead into the other register buffer (see fuse_wave_umma.cu).  x0 belongs to the
-            // previous kernel and may be read at any time; a row of x1 is known to be in ring 1 only once the accumulator of the
-            // row BEFORE it is complete (that needed R1a's rows up to y + 1, hence R0b's up to y + 2), so its load is issued
-            // behind that wait -- still a whole row ahead of its use, except for the first row of a strip.
-            uint32_t rv_a[2][8], rv_b[2][8];
-            if (use_res && res_x0) {
-                ptx::ldg_nc_v8(rp, rv_a[0]);
-                ptx::ldg_nc_v8(rp + 16, rv_a[1]);
-            }
-            auto do_row = [&](int i, uint32_t (&rv)[2][8], uint32_t (&rv_next)[2][8]) {
-                const uint32_t acc = tile % ACC_SLOTS, aph = (tile / ACC_SLOTS) & 1;
-                if (use_res && res_x0 && i + 1 < s.rows) {
-                    ptx::ldg_nc_v8(rp + r_step, rv_next[0]);
-                    ptx::ldg_nc_v8(rp + r_step + 16, rv_next[1]);
+            // The residual row is fetched TWO rows ahead, rotating three register buffers: a 64-channel row takes the tensor
+            // pipe 1150 cycles, less than an L2 round trip under load, and a load issued one row ahead stalled the epilogue
+            // (2100-3000 instead of 1500 cycles per row: the whole stream ran at the pace of the two skip stages).  x0 belongs
+            // to the previous kernel and may be read at any time; rows y + 1 and y + 2 of x1 are known to be in ring 1 once the
+            // accumulator of row y is complete (that needed R1a's rows up to y + 1, hence R0b's up to y + 2), so their loads
+            // are issued behind that wait.
+            uint32_t rv0[2][8], rv1[2][8], rv2[2][8];
+            auto load_res = [&](int i, uint32_t (&dst)[2][8]) {      // residual row i of this strip
+                if (res_x0) {
+                    ptx::ldg_nc_v8(rp + static_cast<size_t>(i) * r_step, dst[0]);
+                    ptx::ldg_nc_v8(rp + static_cast<size_t>(i) * r_step + 16, dst[1]);
+                } else {
+                    const __nv_bfloat16* q = res_ptr(ring_row0 + static_cast<uint32_t>(i));
+                    ldg_cg_v8(q, dst[0]);
+                    ldg_cg_v8(q + 16, dst[1]);
                 }
-                ptx::mbar_wait(bar_tfull + 8 * acc, aph, 5);
+            };
+            if (use_res && res_x0) {
+                load_res(0, rv0);
+                if (s.rows > 1) load_res(1, rv1);
+            }
+            auto do_row = [&](int i, uint32_t (&rv)[2][8], uint32_t (&rv_n1)[2][8], uint32_t (&rv_n2)[2][8]) {
+                const uint32_t acc = tile % ACC_SLOTS, aph = (tile / ACC_SLOTS) & 1;
+                if (use_res && res_x0 && i + 2 < s.rows) load_res(i + 2, rv_n2);
+                {
+                    WAVE_STAT_BEGIN(t4);
+                    ptx::mbar_wait(bar_tfull + 8 * acc, aph, 5);
+                    if (warp == 4 && lane == 0) WAVE_STAT_END(t4, 4);
+                }
                 if (use_res && res_ring) {
                     if (i == 0) {
-                        ldg_cg_v8(res_ptr(ring_row), rv[0]);
-                        ldg_cg_v8(res_ptr(ring_row) + 16, rv[1]);
+                        load_res(0, rv);
+                        if (s.rows > 1) load_res(1, rv_n1);
                     }
-                    if (i + 1 < s.rows) {
-                        ldg_cg_v8(res_ptr(ring_row + 1), rv_next[0]);
-                        ldg_cg_v8(res_ptr(ring_row + 1) + 16, rv_next[1]);
-                    }
+                    if (i + 2 < s.rows) load_res(i + 2, rv_n2);
                 }
                 ptx::tc_fence_after();
                 uint32_t v[32];
@@ -546,6 +572,7 @@ enc_wave_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
                     if (tile >= static_cast<uint32_t>(R) && !(w.debug_flags & 32)) {
                         const uint32_t want = tile - R + 1;
                         if (seen_c < want) {                 // shared-memory mirror kept by the credit poller (warp 2)
+                            WAVE_STAT_BEGIN(t3);
                             const long long t0 = clock64();
                             while ((seen_c = *credit_gen) < want) {
                                 if (clock64() - t0 > HRN_WAIT_LIMIT_CYCLES) {
@@ -554,9 +581,10 @@ enc_wave_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
                                     __trap();
                                 }
                             }
+                            if (warp == 4 && lane == 0) WAVE_STAT_END(t3, 3);
                         }
                     }
-                    if (valid) {
+                    if (valid && !(w.debug_flags & 2)) {
                         __nv_bfloat16* dst = ring_out + ((static_cast<size_t>(stream) * R + tile % R) * w.W + x) * 64 + co0;
                         ptx::stg_v8(dst, o[0]);
                         ptx::stg_v8(dst + 16, o[1]);
@@ -571,12 +599,11 @@ enc_wave_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(bar_rowdone + 8 * (tile % ROWDONE));      // -> publisher (warp 3)
                 ++tile;
-                ++ring_row;
-                if (res_x0) rp += r_step;
             };
-            for (int i = 0; i < s.rows; i += 2) {
-                do_row(i, rv_a, rv_b);
-                if (i + 1 < s.rows) do_row(i + 1, rv_b, rv_a);
+            for (int i = 0; i < s.rows; i += 3) {
+                do_row(i, rv0, rv1, rv2);
+                if (i + 1 < s.rows) do_row(i + 1, rv1, rv2, rv0);
+                if (i + 2 < s.rows) do_row(i + 2, rv2, rv0, rv1);
             }
             skip_base += static_cast<uint32_t>(sk.rows);
         }
@@ -638,6 +665,7 @@ int enc_wave_launch(const EncWaveLaunch& a, int sm_count, cudaStream_t stream) {
     w.streams = streams;
     w.flags = a.flags;
     w.debug_flags = a.debug_flags;
+    w.stats = a.stats;
     for (int i = 0; i < STAGES; ++i) {
         w.stage[i].w_img = a.w_img[i];
         w.stage[i].bias = a.bias[i];

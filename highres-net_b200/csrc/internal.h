@@ -140,6 +140,7 @@ struct EncWaveLaunch {
     int has_prelu[5];
     int debug_flags;
     int streams;                       // 0 = sm_count / 5
+    unsigned long long* stats;         // optional triage counters, 12 per CTA (knob "enc_stats")
 };
 int enc_wave_streams(int sm_count);
 bool enc_wave_fits(int sm_count);

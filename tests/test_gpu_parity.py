@@ -372,6 +372,28 @@ def test_wavefront_fusion_is_bit_identical_to_three_launches(hb, dev, b, l, s):
             assert torch.equal(other(lrs * patterns[1][:, :, None, None], patterns[1]), ref_net(lrs * patterns[1][:, :, None, None], patterns[1])), knobs
 
 
+@pytest.mark.parametrize("b,l,s", [(1, 2, 8), (2, 3, 33), (2, 4, 128), (1, 5, 100), (3, 2, 1), (1, 16, 64), (4, 8, 128)])
+def test_encoder_wavefront_is_bit_identical_to_per_layer_launches(hb, dev, b, l, s):
+    """enc_wave_umma (opt-in, knob "enc_wave"): the two ResidualBlocks and the final conv of the encoder (HRNet.py:55-60) as
+    five-CTA streams over L2 rings, with x1 read twice (conv input of ResidualBlock 1 and, rows later, its skip connection).
+    Same products, same order, same rounding points as resblock64_umma / conv3x3_umma<64>: bit-identical SR, with dead views
+    and whatever the stream partition and ring depth."""
+    g = torch.Generator().manual_seed(7 * b + 100 * l + s)
+    lrs = torch.rand(b, l, s, s, generator=g).to(dev)
+    alphas = torch.ones(b, l, device=dev)
+    if l > 2:
+        alphas[-1, l - 1:] = 0
+    ref = _net_with(hb, dev, fuse_wave=0, enc_wave=0)(lrs, alphas)
+    for knobs in ({"enc_wave": 1, "fuse_wave": 0}, {"enc_wave": 1}, {"enc_wave": 1, "wave_streams": 1, "enc_ring_rows": 12},
+                  {"enc_wave": 1, "wave_streams": 7, "enc_ring_rows": 40}):
+        model = _net_with(hb, dev, **knobs)
+        before = hb.kernel_launch_count()
+        out = model(lrs, alphas)
+        assert torch.equal(out, ref), knobs
+        assert torch.equal(model(lrs, alphas), ref), knobs          # second forward: counters were reset
+    assert hb.kernel_launch_count() > before
+
+
 def test_wavefront_fusion_soak_c2(hb, dev):
     """Hand-over protocol under load: 40 back-to-back forwards at BASELINE configs[1] size on two alternating inputs must
     reproduce the three-launch results every time (a missed release / stale ring row would show up as a changed bit)."""

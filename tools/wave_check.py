@@ -13,7 +13,7 @@ def make(**knobs):
 ref_net = make(fuse_wave=0, enc_wave=0)
 shapes = [(1, 2, 8), (1, 2, 16), (2, 3, 33), (1, 4, 64), (2, 4, 128), (1, 5, 100), (3, 2, 1), (1, 16, 64), (4, 8, 128), (32, 16, 128)]
 if len(sys.argv) > 1: shapes = shapes[:int(sys.argv[1])]
-for knobs in ({"fuse_wave": 0, "enc_wave": 1}, {}, {"wave_streams": 1}, {"wave_streams": 3, "enc_ring_rows": 12}, {"wave_streams": 7, "wave_ring_rows": 8}):
+for knobs in ({"fuse_wave": 0, "enc_wave": 1}, {"enc_wave": 1}, {"enc_wave": 1, "wave_streams": 1}, {"enc_wave": 1, "wave_streams": 3, "enc_ring_rows": 12}, {"wave_streams": 7, "wave_ring_rows": 8}):
     net = make(**knobs)
     for (b, l, s) in shapes:
         if "wave_streams" in knobs and b * l * s * s > 4 * 8 * 128 * 128: continue
@@ -32,8 +32,7 @@ for knobs in ({"fuse_wave": 0, "enc_wave": 1}, {}, {"wave_streams": 1}, {"wave_s
             print("  per-imageset max:", bad.cpu().numpy().round(5).tolist()[:8])
             r = rows[int(bad.argmax())].cpu().numpy(); print("  bad SR rows (of %d):" % r.shape[0], np.nonzero(r > 0)[0][:40].tolist())
 lrs = torch.rand(32, 16, 128, 128, device=dev); al = torch.ones(32, 16, device=dev)
-nets = [("per-layer launches", ref_net), ("fusion wavefront only", make(enc_wave=0)), ("encoder + fusion wavefronts", make()),
-        ("enc ring 16", make(enc_ring_rows=16)), ("enc ring 48", make(enc_ring_rows=48))]
+nets = [("per-layer launches", ref_net), ("fusion wavefront only", make()), ("encoder + fusion wavefronts", make(enc_wave=1))]
 for name, m in nets + nets[:3]:
     for _ in range(20): m(lrs, al)
     torch.cuda.synchronize()
