@@ -120,9 +120,8 @@ class ImageSet(OrderedDict):
         return "\n".join(lines)
 
 
-def read_imageset(imset_dir, create_patches=False, patch_size=64, seed=None, top_k=None, beta=0., threads=0):
-    """DataLoader.py:73-148.  Returns an ImageSet whose 'lr' (L, H, W) and 'hr' are UINT16 tensors in pinned memory (the
-    reference returns uint16 numpy arrays at this stage as well), 'hr_map' a bool array, 'clearances' the sorted scores."""
+def _pick_views(imset_dir, top_k, beta, seed):
+    """View ids of an imageset in the order the reference reads them (DataLoader.py:107-131) and their clearances."""
     ids = _view_ids(imset_dir)
     if not isfile(join(imset_dir, "clearance.npy")):
         raise Exception("please call the save_clearance.py before call DataLoader")
@@ -131,7 +130,32 @@ def read_imageset(imset_dir, create_patches=False, patch_size=64, seed=None, top
         picked = sample_clearest(clearances, n=min(top_k, len(ids)), beta=beta, seed=seed)
     else:
         picked = clearance_order(clearances)                                   # max to min
-    ids, clearances = ids[picked], clearances[picked]
+    return ids[picked], clearances[picked]
+
+
+def read_imagesets(imset_dirs, seed=None, top_k=None, beta=0., threads=0):
+    """Many imagesets at once: every LR view of every directory is decoded by ONE native call (one thread pool over
+    hundreds of files instead of a pool per imageset), the HR images and status maps by a second and third one.  All
+    imagesets must share one LR size.  Returns a list of ImageSets like read_imageset (no patch sampling)."""
+    imset_dirs = list(imset_dirs)
+    picked = [_pick_views(d, top_k, beta, seed) for d in imset_dirs]
+    lr_paths = [join(d, f"LR{i}.png") for d, (ids, _) in zip(imset_dirs, picked) for i in ids]
+    lrs = read_png_u16(lr_paths, threads=threads)
+    maps = read_png_u16([join(d, "SM.png") for d in imset_dirs], threads=threads, pin=False).numpy().astype(bool)
+    with_hr = [k for k, d in enumerate(imset_dirs) if exists(join(d, "HR.png"))]
+    hrs = read_png_u16([join(imset_dirs[k], "HR.png") for k in with_hr], threads=threads) if with_hr else None
+    out, at = [], 0
+    for k, (d, (ids, clearances)) in enumerate(zip(imset_dirs, picked)):
+        hr = hrs[with_hr.index(k)] if k in with_hr else None
+        out.append(ImageSet(name=basename(d), lr=lrs[at:at + len(ids)], hr=hr, hr_map=maps[k], clearances=clearances))
+        at += len(ids)
+    return out
+
+
+def read_imageset(imset_dir, create_patches=False, patch_size=64, seed=None, top_k=None, beta=0., threads=0):
+    """DataLoader.py:73-148.  Returns an ImageSet whose 'lr' (L, H, W) and 'hr' are UINT16 tensors in pinned memory (the
+    reference returns uint16 numpy arrays at this stage as well), 'hr_map' a bool array, 'clearances' the sorted scores."""
+    ids, clearances = _pick_views(imset_dir, top_k, beta, seed)
     lr = read_png_u16([join(imset_dir, f"LR{i}.png") for i in ids], threads=threads)
     hr_map = read_png_u16([join(imset_dir, "SM.png")], threads=1, pin=False)[0].numpy().astype(bool)
     hr = read_png_u16([join(imset_dir, "HR.png")], threads=1)[0] if exists(join(imset_dir, "HR.png")) else None
@@ -166,6 +190,9 @@ class ImagesetDataset(torch.utils.data.Dataset):
     def _load(self, directory):
         imset = read_imageset(directory, create_patches=self.create_patches, patch_size=self.patch_size, seed=self.seed,
                               top_k=self.top_k, beta=self.beta, threads=self.threads)
+        return self._finish(imset)
+
+    def _finish(self, imset):
         if not self.raw16:                                              # DataLoader.py:195-198
             imset["lr"] = (imset["lr"].to(torch.float32) / 65535.0)
             if imset["hr"] is not None:
@@ -183,7 +210,14 @@ class ImagesetDataset(torch.utils.data.Dataset):
             dirs = self.imset_dir[index]
         else:
             raise KeyError("index must be int, string, or slice")
-        imsets = [self._load(d) for d in dirs]
+        if len(dirs) > 1 and not self.create_patches:          # a slice: one native decode call for all views of all imagesets
+            try:
+                imsets = [self._finish(im) for im in read_imagesets(dirs, seed=self.seed, top_k=self.top_k, beta=self.beta,
+                                                                    threads=self.threads)]
+            except RuntimeError:                               # imagesets of different sizes: one by one
+                imsets = [self._load(d) for d in dirs]
+        else:
+            imsets = [self._load(d) for d in dirs]
         return imsets[0] if len(imsets) == 1 else imsets
 
 

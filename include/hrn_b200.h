@@ -164,8 +164,15 @@ int32_t hrn_forward_dump(hrn_handle* h, const float* lrs, const float* alphas, i
  * compute every view and pair even when alpha = 0 padding keeps it from reaching the output (default 1: skipped; the
  * super-resolved image is bit-identical either way).  "mcast" = 0 launches the 128 -> 128 convolutions of the fusion stage
  * as independent CTAs instead of cluster pairs that multicast their input rows, "fuse_resblock" = 0 runs an encoder
- * ResidualBlock as two launches instead of one (defaults 1; bit-identical either way).  "debug_flags" disables parts of the conv kernel for
- * performance triage (results are then garbage). */
+ * ResidualBlock as two launches instead of one (defaults 1; bit-identical either way).  "fuse_wave" = 0 runs every fusion
+ * level as three launches of the conv kernel instead of one wavefront launch (default 1 for images up to 128 pixels wide),
+ * "enc_wave" = 1 runs the encoder's two ResidualBlocks and final conv as one wavefront launch (default 0: measured slower);
+ * "wave_streams" (0 = SM count / 5), "wave_ring_rows" (16), "enc_ring_rows" (24), "wave_publish_rows" (1) and
+ * "wave_lag_rows" (0) move the stream partition, ring depth and hand-over granularity of the wavefront launches -- all
+ * bit-identical.  "wave_stats" / "enc_stats" = 1 start per-CTA wait counters of the wavefront kernels, = 0 print their per-role
+ * means to stderr.  "debug_flags" disables parts of the conv / wavefront kernels for performance triage (results are then
+ * garbage): 1 no TMEM load, 2 no stores, 4 no TMA loads, 8 no residual loads, 32 no hand-over waits, 64 relaxed publication,
+ * 128 relaxed polls + fence instead of acquire polls, 256 no proxy fence, 1024 every epilogue warp polls global memory. */
 int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value);
 /* Process-wide test knobs of the scoring entry points (they take no handle).  "cpsnr_generic" = 1 makes hrn_shift_cpsnr use
  * the general shift-window kernel also for border_w = 3 (default 0: the 49-site window kernel); "cpsnr_window_v1" = 0 selects

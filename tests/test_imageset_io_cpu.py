@@ -132,6 +132,12 @@ def test_read_imageset_and_dataset_mirror_the_reference_loader(io, arrays, tmp_p
     want = (arrays[f"imgset0001/LR{order[0]:03d}"].astype(np.float64) / 65535).astype(np.float32)
     assert item["lr"].dtype == torch.float32 and np.array_equal(item["lr"][0].numpy(), want)
     assert item["hr_map"].dtype == torch.float32 and ds["imgset0002"]["name"] == "imgset0002" and len(ds[0:2]) == 2
+    # a slice goes through ONE native decode call for all views of all imagesets (read_imagesets): same content
+    both = io.ImagesetDataset(dirs, {"create_patches": False, "patch_size": 8}, raw16=True)
+    for one, many in zip([both[0], both[1], both[2]], both[0:3]):
+        assert one["name"] == many["name"] and torch.equal(one["lr"], many["lr"]) and np.array_equal(one["clearances"], many["clearances"])
+        assert (one["hr"] is None) == (many["hr"] is None) and (one["hr"] is None or torch.equal(one["hr"], many["hr"]))
+        assert np.array_equal(np.asarray(one["hr_map"]), np.asarray(many["hr_map"]))
     raw = io.ImagesetDataset(dirs, {"create_patches": False, "patch_size": 8}, raw16=True)[1]
     assert raw["lr"].dtype == torch.uint16 and tuple(raw["lr"].shape) == (3, 24, 24)
     # sampled / patched variant: same draws as the reference for a seed (np.random.seed -> choice / randint)
