@@ -590,9 +590,12 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
             const size_t r_step = static_cast<size_t>(w.W) * 64;
             __nv_bfloat16* op = nullptr;
             if (conv == 2) op = w.stack_out + (static_cast<size_t>(b * w.src_views + ip) * w.H * w.W + pix0) * 64 + co0;
-            // The residual row (skip connection / alice) is fetched one whole row ahead into the other register buffer:
-            // at the L2 latency under load (~2000 cycles) a load issued at the top of its own row made the epilogue as slow
-            // as the tensor pipe (2400 vs 2300 cycles per row) and cost the stream 12 %.
+            // The residual row (skip connection / alice) is fetched one whole row ahead into the other register buffer.
+            // Measured alternative (not kept): the row by TMA into a shared-memory slot (a quarter of the load/store-unit
+            // wavefronts: a warp's 256-bit global load touches 32 different lines) -- single-buffered in the 16 KB that are
+            // left, it arrives too late to help (4.55 vs 4.53 ms), and it needs fence.proxy.async.shared::cta before every
+            // refill: the epilogue's ld.shared (generic proxy) and the TMA write (async proxy) of the same slot are NOT ordered
+            // by the mbarrier hand-shake alone (without the fence one forward in ten came back with rows off by 1e-3).
             uint32_t rv_a[2][8], rv_b[2][8];
             if (use_res) {
                 ptx::ldg_nc_v8(rp, rv_a[0]);

@@ -20,10 +20,10 @@ def timed(m, n=60):
     for _ in range(n): m(lrs, al)
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
-configs = [("three launches", dict(wave=0)), ("wave (MMA in warp 9)", dict(wave=1)), ("wave (MMA in warp 1)", dict(wave=1, debug_flags=2048)),
-           ("three launches", dict(wave=0)), ("wave (MMA in warp 9)", dict(wave=1)), ("wave (MMA in warp 1)", dict(wave=1, debug_flags=2048))]
+configs = [("three launches", dict(wave=0)), ("wave", dict(wave=1)), ("wave ring 12", dict(wave=1, wave_ring_rows=12)),
+           ("wave ring 24", dict(wave=1, wave_ring_rows=24)), ("three launches", dict(wave=0)), ("wave", dict(wave=1))]
 ref = make(0)(lrs, al)
-for name, kw in (("wave", dict(wave=1)), ("wave MMA in warp 1", dict(wave=1, debug_flags=2048)), ("wave no flag waits", dict(wave=1, debug_flags=32))):
+for name, kw in (("wave", dict(wave=1)), ("wave no flag waits", dict(wave=1, debug_flags=32))):
     kw = dict(kw); wave = kw.pop("wave")
     net = make(wave, **kw)
     for _ in range(10): net(lrs, al)
@@ -36,7 +36,12 @@ for name, kw in configs:
     kw = dict(kw); wave = kw.pop("wave")
     net = make(wave, **kw)
     ms = timed(net)
-    same = all(bool(torch.equal(net(lrs, al), ref)) for _ in range(10))
+    outs = [net(lrs, al) for _ in range(30)]
+    bad = [i for i, o in enumerate(outs) if not torch.equal(o, ref)]
+    same = not bad
+    if bad:
+        d = (outs[bad[0]] - ref).abs()[:, 0]; per = d.amax(dim=(1, 2))
+        print('   mismatching forwards', bad, 'imagesets', [int(i) for i in torch.nonzero(per > 0)[:, 0][:10]], 'max', float(d.max()), 'rows', (lambda rr: (int(rr.min()), int(rr.max()), int(rr.numel())))(torch.nonzero(d[int(per.argmax())].amax(dim=1) > 0)[:, 0]))
     prof = None
     net.profile_begin(dev)
     for _ in range(5): net(lrs, al)
