@@ -1035,7 +1035,7 @@ int32_t hrn_scoring_debug_set(const char* knob, int32_t value) {
         return 0;
     }
     if (knob != nullptr && strcmp(knob, "cpsnr_window_v1") == 0) {
-        hrn::g_cpsnr_window_v1 = value != 0;      // 1 = scalar window kernel (default), 0 = packed fp32x2 kernel
+        hrn::g_cpsnr_window_v1 = value;           // 1 = scalar window kernel (default), 0 = split + packed fp32x2, 2 = split, scalar
         return 0;
     }
     if (knob != nullptr && strcmp(knob, "cpsnr_chunk") == 0) {

@@ -467,6 +467,7 @@ enc_wave_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constan
                     if (conv == SKIP_STAGE)
                         st_relaxed(flags + F_SKIP, skip_base + static_cast<uint32_t>(i + 1 == s.rows ? sk.rows : s.y0 + i + 1 - sk.y0));
                     if (conv < STAGES - 1 && (k + 1 >= next_pub || k + 1 == total_rows)) {   // rows 0 .. k are in the ring
+                        fence_proxy_async_global();      // the rows will be read through the async proxy (TMA)
                         st_release(prod, k + 1);
                         next_pub = k + 2;
                     }

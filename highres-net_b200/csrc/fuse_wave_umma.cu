@@ -542,6 +542,7 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
                     // conv A, B: rows 0 .. k are in the ring.  One device-scope release per `publish_rows` rows (and at the end
                     // of the stream): the fence drains the SM's store path, which every epilogue warp shares.
                     if (conv < 2 && (k + 1 >= next_pub || k + 1 == total_rows)) {
+                        fence_proxy_async_global();      // the rows will be read through the async proxy (TMA)
                         if (w.debug_flags & 64) st_relaxed(prod, k + 1);
                         else st_release(prod, k + 1);
                         next_pub = k + 1 + w.publish_rows;

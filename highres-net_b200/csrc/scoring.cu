@@ -571,7 +571,35 @@ __device__ __forceinline__ void cw2_terms(f2 (&acc)[XN][2][4], f2 (*aux)[2][4], 
     }
 }
 
-template <int PASS, int X0, int XN>
+// The same terms with scalar fp32 instructions (the arithmetic and sum order of cpsnr_window_kernel, for the shifts of one
+// half-block): with the packed variant this separates the two changes of the third generation -- more warps per SM from the
+// split, fewer instructions from the packing.
+template <int PASS, int XN, bool CPRED>
+__device__ __forceinline__ void cw2_terms_scalar(float (&acc)[XN][CW_S], const float* bias_s, const float (&hw)[12],
+                                                 const float (&mw)[12], const float (&svw)[XN][4], int xlo, int xhi, int ncol) {
+#pragma unroll
+    for (int x = 0; x < XN; ++x) {
+        if (x < xlo || x > xhi) continue;
+#pragma unroll
+        for (int y = 0; y < CW_S; ++y) {
+            const float b = PASS == 2 ? bias_s[x * 8 + y] : 0.0f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (CPRED && c >= ncol) continue;
+                const float m = mw[c + y];
+                const float d = hw[c + y] - svw[x][c];               // diff = hr - sr            (Evaluator.py:35)
+                if (PASS == 1) {
+                    acc[x][y] += d * m;                              // sum(diff * hr_map)        (Evaluator.py:36)
+                } else {
+                    const float t = (d - b) * m;                     // (diff - bias) * hr_map    (Evaluator.py:37)
+                    acc[x][y] += t * t;
+                }
+            }
+        }
+    }
+}
+
+template <int PASS, int X0, int XN, bool PACKED>
 __device__ __forceinline__ void cpsnr_window2_body(const float* __restrict__ sr, const float* __restrict__ hr,
                                                    const float* __restrict__ hm, const CpGeom& g, int clip_sr,
                                                    const float* __restrict__ bias, double* __restrict__ partial,
@@ -597,14 +625,23 @@ __device__ __forceinline__ void cpsnr_window2_body(const float* __restrict__ sr,
     // over the odd columns (see cw2_terms).  PASS 2: the sites' biases sit in shared memory as the same pairs (broadcast
     // LDS.64) instead of 32 more registers per lane.
     f2 acc[XN][2][4];
+    float accs[XN][CW_S];                        // !PACKED: plain fp32 accumulators, one per (x, y)
+    float* bias_s = reinterpret_cast<float*>(aux);   // !PACKED, PASS 2: bias of site (x, y) at [x * 8 + y]
     float n_all[CW_S];                           // PASS 1: sum of rs over the rows that count for every x of this block
 #pragma unroll
     for (int y = 0; y < CW_S; ++y) n_all[y] = 0.0f;
 #pragma unroll
-    for (int x = 0; x < XN; ++x)
+    for (int x = 0; x < XN; ++x) {
 #pragma unroll
         for (int yp = 0; yp < 4; ++yp) acc[x][0][yp] = acc[x][1][yp] = pk(0.0f, 0.0f);
-    if (PASS == 2) {
+#pragma unroll
+        for (int y = 0; y < CW_S; ++y) accs[x][y] = 0.0f;
+    }
+    if (PASS == 2 && !PACKED) {
+        if (lane < XN * 8) bias_s[lane] = (lane & 7) < CW_S ? bias[(set * CW_S + X0 + (lane >> 3)) * CW_S + (lane & 7)] : 0.0f;
+        __syncwarp();
+    }
+    if (PASS == 2 && PACKED) {
         if (lane < XN * 8) {
             const int x = lane >> 3, odd = (lane >> 2) & 1, yp = lane & 3;
             const int y0 = 2 * yp - odd, y1 = y0 + 1;                // the two shifts of this pair; -1 and 7 are dummies
@@ -634,7 +671,8 @@ __device__ __forceinline__ void cpsnr_window2_body(const float* __restrict__ sr,
 #pragma unroll
             for (int y = 0; y < CW_S; ++y) {
                 const int q = x * CW_S + y;
-                const float a = ev[y] + od[y + 1];                   // even columns + odd columns
+                const float a = PACKED ? ev[y] + od[y + 1] : accs[x][y];     // even columns + odd columns
+                accs[x][y] = 0.0f;
                 if (PASS == 1) {
                     stage[q * 2][lane] = n_all[y] + edge_n[q][lane];
                     stage[q * 2 + 1][lane] = a;
@@ -724,10 +762,17 @@ __device__ __forceinline__ void cpsnr_window2_body(const float* __restrict__ sr,
                     for (int y = 0; y < CW_S; ++y) edge_n[(x - X0) * CW_S + y][lane] += rs[y];
             }
         }
-        if (all_full)
-            cw2_terms<PASS, XN, false>(acc, aux, hw, mw, svw, xlo - X0, xhi - X0, 4);
-        else
-            cw2_terms<PASS, XN, true>(acc, aux, hw, mw, svw, xlo - X0, xhi - X0, ncol);
+        if (PACKED) {
+            if (all_full)
+                cw2_terms<PASS, XN, false>(acc, aux, hw, mw, svw, xlo - X0, xhi - X0, 4);
+            else
+                cw2_terms<PASS, XN, true>(acc, aux, hw, mw, svw, xlo - X0, xhi - X0, ncol);
+        } else {
+            if (all_full)
+                cw2_terms_scalar<PASS, XN, false>(accs, bias_s, hw, mw, svw, xlo - X0, xhi - X0, 4);
+            else
+                cw2_terms_scalar<PASS, XN, true>(accs, bias_s, hw, mw, svw, xlo - X0, xhi - X0, ncol);
+        }
         if (++since_flush == CW_FLUSH) {
             flush();
             since_flush = 0;
@@ -750,7 +795,7 @@ __device__ __forceinline__ void cpsnr_window2_body(const float* __restrict__ sr,
 }
 
 constexpr int CW2_X_SPLIT = 4;                 // blockIdx.z = 0: x in [0, 4); 1: x in [4, 7)
-template <int PASS>
+template <int PASS, bool PACKED>
 __global__ void __launch_bounds__(32, 16)
 cpsnr_window2_kernel(const float* __restrict__ sr, const float* __restrict__ hr, const float* __restrict__ hm, CpGeom g,
                      int clip_sr, const float* __restrict__ bias, double* __restrict__ partial) {
@@ -759,9 +804,9 @@ cpsnr_window2_kernel(const float* __restrict__ sr, const float* __restrict__ hr,
     __shared__ float edge_n[PASS == 1 ? CW2_X_SPLIT * CW_S : 1][32];
     __shared__ f2 aux[CW2_X_SPLIT][2][4];
     if (blockIdx.z == 0)
-        cpsnr_window2_body<PASS, 0, CW2_X_SPLIT>(sr, hr, hm, g, clip_sr, bias, partial, stage, edge_n, aux);
+        cpsnr_window2_body<PASS, 0, CW2_X_SPLIT, PACKED>(sr, hr, hm, g, clip_sr, bias, partial, stage, edge_n, aux);
     else
-        cpsnr_window2_body<PASS, CW2_X_SPLIT, CW_S - CW2_X_SPLIT>(sr, hr, hm, g, clip_sr, bias, partial, stage, edge_n, aux);
+        cpsnr_window2_body<PASS, CW2_X_SPLIT, CW_S - CW2_X_SPLIT, PACKED>(sr, hr, hm, g, clip_sr, bias, partial, stage, edge_n, aux);
 }
 
 // One block per imageset, one thread per site.  MODE 1: bias = sum(d*m) / n.  MODE 2: scores + argmax.
@@ -1082,7 +1127,9 @@ int g_cpsnr_generic = 0;
 // with the batch cut into L2-sized chunks 2.13-3.85 ms (chunk 64 ... 12).  The search is bound by the fp32 pipe (three-register
 // FFMA / FADD issue at one warp instruction per two cycles per scheduler, and an FFMA2 costs two of those), not by issue
 // slots or DRAM, so neither packing nor L2 residency of pass 2 pays; both stay behind knobs as measured alternatives.
-int g_cpsnr_window_v1 = 1;     // 1 (default) = scalar 49-sites-per-warp window kernel; 0 = packed fp32x2 kernel, x split over two warps
+int g_cpsnr_window_v1 = -1;    // -1 (default) = automatic: the split scalar kernel for small batches (twice the blocks: 0.131 vs 0.145 ms
+                               // on 32 imagesets), the 49-sites-per-warp kernel for large ones (1.86 vs 2.01 ms on 512); 1 = scalar
+                               // 49-sites-per-warp kernel; 0 = x split over two warps + packed fp32x2; 2 = x split, scalar fp32
 int g_cpsnr_chunk = 0;         // imagesets per pass-1 / pass-2 round trip: 0 (default) = whole batch; -1 = by L2 budget; n > 0 = n
 constexpr size_t CP_L2_BUDGET = 56ull << 20;   // chunk = -1: bytes of sr + hr + map per chunk that pass 2 should still find in L2
 constexpr int CW2_TARGET_WARPS = 148 * 14;
@@ -1136,7 +1183,8 @@ int shift_cpsnr_launch(const float* sr, const float* hr, const float* hm, int B,
     g.vec_ok = (W % 4 == 0) && (((reinterpret_cast<uintptr_t>(sr) | reinterpret_cast<uintptr_t>(hr) | reinterpret_cast<uintptr_t>(hm)) & 15) == 0);
     // border_w = 3 on 16-byte aligned rows (every case the reference produces) takes the 49-site window kernel
     const bool window = g.S == CW_S && g.vec_ok && g_cpsnr_generic == 0;
-    const bool window2 = window && g_cpsnr_window_v1 == 0;
+    const int variant = g_cpsnr_window_v1 >= 0 ? g_cpsnr_window_v1 : (B <= 128 ? 2 : 1);
+    const bool window2 = window && variant != 1;
     // Both passes read sr, hr and the map.  Optionally (knob cpsnr_chunk) a batch that does not fit in L2 is processed in
     // chunks of imagesets -- pass 1 -> bias -> pass 2 of one chunk back to back, so that pass 2 finds the chunk in L2 and
     // every byte comes from HBM once.  Off by default: the kernels are fp32-bound and the extra launches cost more.
@@ -1180,8 +1228,10 @@ int shift_cpsnr_launch(const float* sr, const float* hr, const float* hm, int B,
         float* bias = bias_all + static_cast<size_t>(b0) * sites;
         float* site_c = site_db != nullptr ? site_db + static_cast<size_t>(b0) * sites : nullptr;
         dim3 grid(g.blocks_per_set, nb), grid2(g.blocks_per_set, nb, 2), block(CP_LANES, g.S);
-        if (window2)
-            cpsnr_window2_kernel<1><<<grid2, 32, 0, s>>>(sr_c, hr_c, hm_c, g, clip_sr, nullptr, partial);
+        if (window2 && variant == 2)
+            cpsnr_window2_kernel<1, false><<<grid2, 32, 0, s>>>(sr_c, hr_c, hm_c, g, clip_sr, nullptr, partial);
+        else if (window2)
+            cpsnr_window2_kernel<1, true><<<grid2, 32, 0, s>>>(sr_c, hr_c, hm_c, g, clip_sr, nullptr, partial);
         else if (window)
             cpsnr_window_kernel<1><<<grid, 32, 0, s>>>(sr_c, hr_c, hm_c, g, clip_sr, nullptr, partial);
         else if (g.S == 7)
@@ -1189,8 +1239,10 @@ int shift_cpsnr_launch(const float* sr, const float* hr, const float* hm, int B,
         else
             cpsnr_pass_kernel<1, 0><<<grid, block, 0, s>>>(sr_c, hr_c, hm_c, g, clip_sr, nullptr, partial);
         cpsnr_finalize_kernel<1><<<nb, 64, 0, s>>>(partial, g, bias, nclear, nullptr, nullptr, nullptr);
-        if (window2)
-            cpsnr_window2_kernel<2><<<grid2, 32, 0, s>>>(sr_c, hr_c, hm_c, g, clip_sr, bias, partial);
+        if (window2 && variant == 2)
+            cpsnr_window2_kernel<2, false><<<grid2, 32, 0, s>>>(sr_c, hr_c, hm_c, g, clip_sr, bias, partial);
+        else if (window2)
+            cpsnr_window2_kernel<2, true><<<grid2, 32, 0, s>>>(sr_c, hr_c, hm_c, g, clip_sr, bias, partial);
         else if (window)
             cpsnr_window_kernel<2><<<grid, 32, 0, s>>>(sr_c, hr_c, hm_c, g, clip_sr, bias, partial);
         else if (g.S == 7)

@@ -175,8 +175,9 @@ int32_t hrn_forward_dump(hrn_handle* h, const float* lrs, const float* alphas, i
  * 128 relaxed polls + fence instead of acquire polls, 256 no proxy fence, 1024 every epilogue warp polls global memory. */
 int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value);
 /* Process-wide test knobs of the scoring entry points (they take no handle).  "cpsnr_generic" = 1 makes hrn_shift_cpsnr use
- * the general shift-window kernel also for border_w = 3 (default 0: the 49-site window kernel); "cpsnr_window_v1" = 0 selects
- * the packed-fp32x2 variant of the window kernel (default 1: the scalar one, which measures faster); "cpsnr_chunk" = n > 0 runs
+ * the general shift-window kernel also for border_w = 3 (default 0: the 49-site window kernel); "cpsnr_window_v1" picks the window
+ * kernel variant: 1 = scalar, all 49 sites per warp; 2 = the 7 row shifts split over two warps, scalar; 0 = split + packed
+ * fp32x2 (measured slowest); default -1 = automatic (2 for batches up to 128 imagesets, 1 above); "cpsnr_chunk" = n > 0 runs
  * pass 1 -> bias -> pass 2 per chunk of n imagesets, -1 sizes the chunk by the L2 (default 0: the whole batch).  All agree. */
 int32_t hrn_scoring_debug_set(const char* knob, int32_t value);
 

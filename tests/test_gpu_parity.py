@@ -771,8 +771,16 @@ def test_shift_cpsnr_window_kernel_vs_generic_and_oracle(hb, dev, b, s, kind):
     hb.scoring_debug_set("cpsnr_window_v1", 0)
     try:
         best_1, xy_1, tab_1 = hb.shift_cPSNR_argmax(*args)
+        hb.scoring_debug_set("cpsnr_window_v1", 2)                # x split over two warps, scalar fp32
+        best_2, xy_2, tab_2 = hb.shift_cPSNR_argmax(*args)
+        assert torch.equal(xy_2, xy_1)
+        assert np.abs(np.nan_to_num(tab_2.cpu().numpy() - tab_1.cpu().numpy(), nan=0.0, posinf=0.0, neginf=0.0)).max() <= CPSNR_KERNEL_GATE_DB
+        hb.scoring_debug_set("cpsnr_window_v1", 1)                # the 49-sites-per-warp kernel, whatever the batch size
+        best_3, xy_3, tab_3 = hb.shift_cPSNR_argmax(*args)
+        assert torch.equal(xy_3, xy_1)
+        assert np.abs(np.nan_to_num(tab_3.cpu().numpy() - tab_1.cpu().numpy(), nan=0.0, posinf=0.0, neginf=0.0)).max() <= CPSNR_KERNEL_GATE_DB
     finally:
-        hb.scoring_debug_set("cpsnr_window_v1", 1)
+        hb.scoring_debug_set("cpsnr_window_v1", -1)
     hb.scoring_debug_set("cpsnr_chunk", 2)
     try:
         best_c, xy_c, tab_c = hb.shift_cPSNR_argmax(*args)

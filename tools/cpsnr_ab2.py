@@ -20,16 +20,16 @@ def timed(fn, n):
 for n in (512, 32):
     sr = torch.rand(n, 384, 384, device=dev); hr = torch.rand(n, 384, 384, device=dev); hm = (torch.rand(n, 384, 384, device=dev) > 0.1).float()
     ref = None
-    for v1 in (1, 0):
-        for chunk in ((0, -1, 12, 16, 24, 32, 48, 64) if n == 512 else (0,)):
+    for v1 in (1, 0, 2, 1, 2):
+        for chunk in ((0, 64) if n == 512 else (0,)):
             hb.scoring_debug_set("cpsnr_window_v1", v1); hb.scoring_debug_set("cpsnr_chunk", chunk)
             best, xy, tab = hb.shift_cPSNR_argmax(sr, hr, hm)
             if ref is None: ref = (xy.clone(), tab.clone())
             ms = timed(lambda: hb.shift_cPSNR_argmax(sr, hr, hm), 20 if n == 512 else 100)
-            print(json.dumps({"n": n, "kernel": "v2 scalar" if v1 else "v3 packed", "chunk": chunk, "ms": round(ms, 4),
+            print(json.dumps({"n": n, "kernel": {1: "scalar, 49 sites per warp", 0: "split + packed fp32x2", 2: "split, scalar"}[v1], "chunk": chunk, "ms": round(ms, 4),
                               "GBps_alg": round(n * 1769472 / ms / 1e6, 1), "argmax_same": bool(torch.equal(xy, ref[0])),
                               "max_db_diff": float((tab - ref[1]).abs().max())}), flush=True)
-hb.scoring_debug_set("cpsnr_window_v1", 1); hb.scoring_debug_set("cpsnr_chunk", 0)
+hb.scoring_debug_set("cpsnr_window_v1", -1); hb.scoring_debug_set("cpsnr_chunk", 0)
 big = torch.rand(1, 512, 384, 384, device=dev); sh = torch.rand(512, 2, device=dev) * 2 - 1
 ms = timed(lambda: hb.lanczos_shift(big, sh, p=5), 100)
 print(json.dumps({"lanczos_512_ms": ms, "GBps": 512 * 1179648 / ms / 1e6}), flush=True)
