@@ -1124,9 +1124,9 @@ int lanczos_taps_launch(const float* d, int n, int a, int ntaps, float* out, cud
 
 int g_cpsnr_generic = 0;
 // Measured on a B200 (profiles/r02_cpsnr_ab.log, 512 x 384^2): scalar window kernel 1.86 ms, packed / split kernel 2.25 ms;
-// with the batch cut into L2-sized chunks 2.13-3.85 ms (chunk 64 ... 12).  The search is bound by the fp32 pipe (three-register
-// FFMA / FADD issue at one warp instruction per two cycles per scheduler, and an FFMA2 costs two of those), not by issue
-// slots or DRAM, so neither packing nor L2 residency of pass 2 pays; both stay behind knobs as measured alternatives.
+// with the batch cut into L2-sized chunks 2.13-3.85 ms (chunk 64 ... 12).  ncu on the scalar kernel: issue slots 44-51 % active,
+// fp32 pipe 27-40 %, DRAM 12-14 %: latency-bound at three warps per scheduler, and an FFMA2 is no cheaper for the pipe than
+// two FFMAs, so neither packing nor L2 residency of pass 2 pays; both stay behind knobs as measured alternatives.
 int g_cpsnr_window_v1 = -1;    // -1 (default) = automatic: the split scalar kernel for small batches (twice the blocks: 0.131 vs 0.145 ms
                                // on 32 imagesets), the 49-sites-per-warp kernel for large ones (1.86 vs 2.01 ms on 512); 1 = scalar
                                // 49-sites-per-warp kernel; 0 = x split over two warps + packed fp32x2; 2 = x split, scalar fp32
