@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libhrn_b200.so")
-SOURCES = ["api.cu", "conv3x3_umma.cu", "fuse_wave_umma.cu", "enc_wave_umma.cu", "resblock64_umma.cu", "conv_init_umma.cu", "decoder_umma.cu", "pointwise.cu", "scoring.cu", "shiftnet.cu", "imageset_io.cu"]
+SOURCES = ["api.cu", "conv3x3_umma.cu", "fuse_wave_umma.cu", "enc_wave_umma.cu", "resblock64_umma.cu", "conv_init_umma.cu", "decoder_umma.cu", "pointwise.cu", "scoring.cu", "lanczos7_tma.cu", "shiftnet.cu", "imageset_io.cu"]
 HEADERS = ["internal.h", "ptx.cuh", "umma_common.cuh", "strips.cuh", os.path.join("..", "..", "include", "hrn_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -1038,6 +1038,10 @@ int32_t hrn_scoring_debug_set(const char* knob, int32_t value) {
         hrn::g_cpsnr_window_v1 = value;           // 1 = scalar window kernel (default), 0 = split + packed fp32x2, 2 = split, scalar
         return 0;
     }
+    if (knob != nullptr && strcmp(knob, "lanczos_scalar") == 0) {
+        hrn::g_lanczos_scalar = value != 0;
+        return 0;
+    }
     if (knob != nullptr && strcmp(knob, "cpsnr_chunk") == 0) {
         hrn::g_cpsnr_chunk = value;
         return 0;

@@ -1096,8 +1096,13 @@ int lanczos_shift_launch(const float* img, const float* shift, int nb, int c, in
         float* taps = nullptr;
         if (scratch_alloc(reinterpret_cast<void**>(&taps), static_cast<size_t>(c) * 2 * 7 * sizeof(float), s)) return -1;
         lanczos_taps_kernel<<<(2 * c + 127) / 128, 128, 0, s>>>(shift, 2 * c, a, 7, taps);
-        dim3 grid((W + L7_TW - 1) / L7_TW, (H + L7_TH - 1) / L7_TH, static_cast<unsigned>(planes));
-        lanczos_shift7_kernel<<<grid, L7_THREADS, 0, s>>>(img, taps, c, H, W, p, out);
+        if (!g_lanczos_scalar && lanczos7_tma_usable(img, out, H, W)) {
+            // TMA-fed tiles (lanczos7_tma.cu): 16-byte aligned rows
+            if (lanczos7_tma_launch(img, taps, static_cast<int>(planes), c, H, W, p, out, s)) return -1;
+        } else {
+            dim3 grid((W + L7_TW - 1) / L7_TW, (H + L7_TH - 1) / L7_TH, static_cast<unsigned>(planes));
+            lanczos_shift7_kernel<<<grid, L7_THREADS, 0, s>>>(img, taps, c, H, W, p, out);
+        }
         note_launches(1);
         HRN_CUDA_OK(cudaFreeAsync(taps, s));
     } else {
@@ -1123,6 +1128,7 @@ int lanczos_taps_launch(const float* d, int n, int a, int ntaps, float* out, cud
 }
 
 int g_cpsnr_generic = 0;
+int g_lanczos_scalar = 0;       // test knob: 1 = the register-window Lanczos kernel also for rows that TMA can address
 // Measured on a B200 (profiles/r02_cpsnr_ab.log, 512 x 384^2): scalar window kernel 1.86 ms, packed / split kernel 2.25 ms;
 // with the batch cut into L2-sized chunks 2.13-3.85 ms (chunk 64 ... 12).  ncu on the scalar kernel: issue slots 44-51 % active,
 // fp32 pipe 27-40 %, DRAM 12-14 %: latency-bound at three warps per scheduler, and an FFMA2 is no cheaper for the pipe than

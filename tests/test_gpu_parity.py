@@ -669,6 +669,40 @@ def test_lanczos_shift_matches_reference_golden(hb, dev, golden, name):
     assert np.abs(out - scoring_oracle.lanczos_shift(img, shift, p=p)).max() <= LANCZOS_GATE
 
 
+@pytest.mark.parametrize("shape", [(1, 3, 8, 8, 3), (2, 2, 37, 96, 5), (1, 2, 70, 132, 5), (1, 3, 33, 260, 4), (1, 2, 130, 128, 1),
+                                   (1, 2, 64, 12, 2), (3, 2, 5, 384, 4), (1, 2, 150, 37, 5), (1, 40, 384, 384, 5)])
+def test_lanczos_both_kernels_match_oracle(hb, dev, shape):
+    """The N = 7 path has two kernels (TMA-fed tiles for 16-byte aligned rows, a register-window kernel otherwise): both
+    against the oracle on shapes that put the reflect ring, the zero ring (p < 3) and the image edge inside, at the edge of
+    and across tiles -- and against each other bit for bit where both apply (same fmaf order)."""
+    nb, c, h, w, p = shape
+    rng = np.random.RandomState(h * 1000 + w)
+    img = rng.rand(nb, c, h, w).astype(np.float32)
+    shift = rng.uniform(-1, 1, size=(c, 2)).astype(np.float32)
+    ref = scoring_oracle.lanczos_shift(img, shift, p=p)
+    outs = []
+    try:
+        for knob in (0, 1):
+            hb.scoring_debug_set("lanczos_scalar", knob)
+            out = hb.lanczos_shift(torch.from_numpy(img).to(dev), torch.from_numpy(shift).to(dev), p=p, a=3, N=7)
+            outs.append(out.cpu().numpy())
+            assert np.abs(outs[-1] - ref).max() <= LANCZOS_GATE, f"knob {knob}"
+    finally:
+        hb.scoring_debug_set("lanczos_scalar", 0)
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_lanczos_unaligned_view_falls_back(hb, dev):
+    """A storage offset of one float makes the rows 4-byte aligned only: the launcher must take the other kernel, not fault."""
+    rng = np.random.RandomState(5)
+    flat = torch.from_numpy(rng.rand(1 + 2 * 64 * 64).astype(np.float32)).to(dev)
+    img = flat[1:].view(1, 2, 64, 64)
+    shift = torch.tensor([[0.25, -0.5], [-0.75, 0.1]], device=dev)
+    out = hb.lanczos_shift(img, shift, p=5)
+    ref = scoring_oracle.lanczos_shift(img.cpu().numpy(), shift.cpu().numpy(), p=5)
+    assert np.abs(out.cpu().numpy() - ref).max() <= LANCZOS_GATE
+
+
 def test_lanczos_properties_full_size(hb, dev):
     """384x384 SR size: linearity, and an integer shift is a plain translation away from the border."""
     g = torch.Generator().manual_seed(9)
