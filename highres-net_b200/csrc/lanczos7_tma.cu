@@ -124,26 +124,29 @@ lanczos7_tma_kernel(const __grid_constant__ CUtensorMap map, const L7Args a) {
     }
     __syncwarp();
     const int g = lane % GROUPS, r0 = (lane / GROUPS) * SEG;    // (group of four columns, segment of eight output rows)
-    float ky[7], kx[7];
-    int taps_plane = -1;
-    for (int i = 0; i < n_my; ++i, cur.advance(step, a)) {
+    // taps of a sub-tile's channel: 14 floats, ky[7] then kx[7] (lanczos_taps_kernel).  They are fetched one sub-tile ahead,
+    // underneath the x pass, so the y pass never waits for them.
+    auto load_taps = [&](int plane, float (&k14)[14]) {
+        const float2* tp = reinterpret_cast<const float2*>(a.taps) + (plane % a.C) * 7;
+#pragma unroll
+        for (int t = 0; t < 7; ++t) {
+            const float2 v = __ldg(tp + t);
+            k14[2 * t] = v.x;
+            k14[2 * t + 1] = v.y;
+        }
+    };
+    ptx::pdl_wait();                                            // the taps come from the kernel launched just before this one
+    float nk[14];
+    load_taps(cur.plane, nk);
+    for (int i = 0; i < n_my; ++i) {
         const int b = i & 1;
-        const int x0 = cur.tx * T_W, y0 = cur.ty * T_H;
-        if (cur.plane != taps_plane) {                          // 14 floats per channel: ky[7], kx[7] (lanczos_taps_kernel)
-            taps_plane = cur.plane;
-            const float2* tp = reinterpret_cast<const float2*>(a.taps) + (cur.plane % a.C) * 7;
-            float k14[14];
+        const int x0 = cur.tx * T_W, y0 = cur.ty * T_H, plane = cur.plane;
+        cur.advance(step, a);
+        float ky[7], kx[7];
 #pragma unroll
-            for (int t = 0; t < 7; ++t) {
-                const float2 v = __ldg(tp + t);
-                k14[2 * t] = v.x;
-                k14[2 * t + 1] = v.y;
-            }
-#pragma unroll
-            for (int t = 0; t < 7; ++t) {
-                ky[t] = k14[t];
-                kx[t] = k14[7 + t];
-            }
+        for (int t = 0; t < 7; ++t) {
+            ky[t] = nk[t];
+            kx[t] = nk[7 + t];
         }
         ptx::mbar_wait(b ? bar1 : bar0, (i >> 1) & 1, 1);
         float4 yv[SEG];                                          // y-filtered columns x .. x + 3 of rows y0 + r0 .. + 7
@@ -154,11 +157,16 @@ lanczos7_tma_kernel(const __grid_constant__ CUtensorMap map, const L7Args a) {
             ptx::fence_proxy_async_shared();                     // the warp's ld.shared of in[b] before the async-proxy refill
             issue(i + 2);
         }
+        if (i + 1 < n_my) load_taps(cur.plane, nk);
         const int x = x0 - 4 + 4 * g;
-        const bool writer = g >= 1 && g <= GROUPS - 2 && x < a.W;
-        const bool left = x == 0, right = x + 4 == a.W;          // W % 4 == 0: the image ends at a lane boundary
-        float* dst = a.out + (static_cast<size_t>(cur.plane) * a.H + y0 + r0) * a.W + x;
-        const int rows = a.H - y0 - r0;                          // rows of this lane's segment inside the image (may be <= 0)
+        // W % 4 == 0: the image ends at a lane boundary.  Columns -1, -2, -3 mirror 1, 2, 3 and W, W + 1, W + 2 mirror
+        // W - 2, W - 3, W - 4 inside the p-wide ring; beyond it they stay zero.
+        const bool left = x == 0, right = x + 4 == a.W;
+        const bool l1 = left && a.p >= 1, l2 = left && a.p >= 2, l3 = left && a.p >= 3;
+        const bool r1 = right && a.p >= 1, r2 = right && a.p >= 2, r3 = right && a.p >= 3;
+        // rows of this lane's segment it has to store: none for the two halo groups and for columns beyond the image
+        const int rows = (g >= 1 && g <= GROUPS - 2 && x < a.W) ? a.H - y0 - r0 : 0;
+        float* dst = a.out + (static_cast<size_t>(plane) * a.H + y0 + r0) * a.W + x;
 #pragma unroll
         for (int r = 0; r < SEG; ++r) {
             float v[10];                                         // v[j] = column x - 3 + j of the y-filtered row
@@ -172,16 +180,12 @@ lanczos7_tma_kernel(const __grid_constant__ CUtensorMap map, const L7Args a) {
             v[7] = __shfl_down_sync(0xffffffffu, yv[r].x, 1);
             v[8] = __shfl_down_sync(0xffffffffu, yv[r].y, 1);
             v[9] = __shfl_down_sync(0xffffffffu, yv[r].z, 1);
-            if (left) {                                          // columns -1, -2, -3 mirror 1, 2, 3 inside the p-wide ring, zero beyond
-                if (a.p >= 1) v[2] = v[4];
-                if (a.p >= 2) v[1] = v[5];
-                if (a.p >= 3) v[0] = v[6];
-            }
-            if (right) {                                         // columns W, W + 1, W + 2 mirror W - 2, W - 3, W - 4
-                if (a.p >= 1) v[7] = v[5];
-                if (a.p >= 2) v[8] = v[4];
-                if (a.p >= 3) v[9] = v[3];
-            }
+            v[2] = l1 ? v[4] : v[2];
+            v[1] = l2 ? v[5] : v[1];
+            v[0] = l3 ? v[6] : v[0];
+            v[7] = r1 ? v[5] : v[7];
+            v[8] = r2 ? v[4] : v[8];
+            v[9] = r3 ? v[3] : v[9];
             float o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -190,7 +194,10 @@ lanczos7_tma_kernel(const __grid_constant__ CUtensorMap map, const L7Args a) {
                 for (int t = 0; t < 7; ++t) acc = fmaf(kx[t], v[e + t], acc);
                 o[e] = acc;
             }
-            if (writer && r < rows) *reinterpret_cast<float4*>(dst + static_cast<size_t>(r) * a.W) = make_float4(o[0], o[1], o[2], o[3]);
+            // predicated store, no branch: the rows of a lane stay one basic block that the scheduler can interleave
+            asm volatile("{\n\t.reg .pred q;\n\tsetp.lt.s32 q, %5, %6;\n\t@q st.global.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
+                         ::"l"(dst + static_cast<size_t>(r) * a.W), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "r"(r), "r"(rows)
+                         : "memory");
         }
     }
 }
@@ -243,7 +250,7 @@ int lanczos7_tma_launch(const float* img, const float* taps, int planes, int c, 
     if (allow_dynamic_smem(lanczos7_tma_kernel, static_cast<int>(sizeof(Smem)), attr_set)) return -1;
     const int resident = sm_count * CTAS_PER_SM, wanted = (a.tiles + WARPS - 1) / WARPS;
     const int ctas = wanted < resident ? wanted : resident;
-    lanczos7_tma_kernel<<<ctas, THREADS, sizeof(Smem), s>>>(map, a);
+    HRN_CUDA_OK(launch_pdl(lanczos7_tma_kernel, ctas, THREADS, sizeof(Smem), s, 1, map, a));
     HRN_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -38,6 +38,9 @@ __device__ __forceinline__ void lanczos_taps_device(float d, int a, int ntaps, f
 }
 
 __global__ void lanczos_taps_kernel(const float* __restrict__ d, int n, int a, int ntaps, float* __restrict__ out) {
+    // lets a kernel launched with programmatic stream serialisation (lanczos7_tma.cu) run its prologue underneath this one;
+    // it still waits for this grid to finish before it reads the taps
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float t[MAX_TAPS];
