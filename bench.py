@@ -453,7 +453,7 @@ class Bench:
         ms = self.timed(lambda i: hb.lanczos_shift(big, sh, p=5), 200, warm=20)
         gbps = n * LANCZOS_BYTES / ms / 1e6
         out["lanczos"] = {"GBps": gbps, "frac": gbps / hbm, "ms": ms, "images": n, "bytes_per_image": LANCZOS_BYTES,
-                          "traffic": self._scoring_traffic("lanczos_shift7_kernel", n)}
+                          "traffic": self._scoring_traffic("lanczos7_tma_kernel", n)}
         srb, hrb = big[0], torch.rand(n, 384, 384, device=dev)
         hmb = (torch.rand(n, 384, 384, device=dev) > 0.1).float()
         ms = self.timed(lambda i: hb.shift_cPSNR_argmax(srb, hrb, hmb), 40, warm=5)
@@ -461,8 +461,9 @@ class Bench:
         out["cpsnr"] = {"GBps_algorithmic": gbps, "frac": gbps / hbm, "ms": ms, "imagesets": n,
                         "bytes_per_imageset": CPSNR_BYTES, "imagesets_per_s": n / ms * 1e3,
                         "traffic": self._scoring_traffic("cpsnr_window_kernel", n),
-                        "note": "two passes (bias, centred squares) over 49 shifts: fp32-issue bound by construction, "
-                                "see DESIGN.md; frac is against the HBM copy peak as SURVEY 8d asks"}
+                        "note": "two passes (bias, centred squares) over 49 shifts, ~500 fp32 instructions per pixel: latency-bound "
+                                "on the fp32 pipe (ncu: issue slots 44-51 % active, DRAM 12-14 %), see DESIGN.md; frac is "
+                                "against the HBM copy peak as SURVEY 8d asks"}
         del big, hrb, hmb, srb
         # C4: BASELINE.json configs[3] -- forward + lanczos_shift + clip + shift_cPSNR on 32 x 16-view imagesets per
         # GPU; at N > 1 the (cPSNR, x, y) rows of every rank are all-gathered every step and the SR images on the side stream

@@ -321,6 +321,12 @@ cpsnr_pass_kernel(const float* __restrict__ sr, const float* __restrict__ hr, co
 constexpr int CW_COLS = 128, CW_FLUSH = 16, CW_S = 7, CW_SITES = CW_S * CW_S;
 constexpr int CW_TARGET_WARPS = 148 * 11;      // one-warp blocks resident per wave (168 registers, 19 KB of shared memory)
 
+struct CwRowS {                                // the same with the four sr values loaded as float, float2, float (cpsnr_window_kernel)
+    float4 h[3], m[3];
+    float s0;
+    float2 s12;
+    float s3;
+};
 struct CwRow {                                 // one hr / map row segment (12 columns) and the sr row that enters the window
     float4 h[3], m[3], s[2];
 };
@@ -433,7 +439,7 @@ cpsnr_window_kernel(const float* __restrict__ sr, const float* __restrict__ hr, 
     };
 
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto load_row = [&](int h, CwRow& r) {
+    auto load_row = [&](int h, CwRowS& r) {
         const size_t off = static_cast<size_t>(h) * g.W;
         const bool in = h < h_end;
 #pragma unroll
@@ -443,7 +449,13 @@ cpsnr_window_kernel(const float* __restrict__ sr, const float* __restrict__ hr, 
         }
         const bool sin = h < i1;                                     // sr crop row h exists in this band
 #pragma unroll
-        for (int q = 0; q < 2; ++q) r.s[q] = (sin && q_ok[q]) ? __ldg(reinterpret_cast<const float4*>(srp + off) + q) : zero4;
+                // crop column j0 + c is image column j0 + c + 3: one float, one float2, one float.  Two aligned 128-bit loads would
+        // be fewer instructions, but the unused fourth float of the second quad got its register reused as scratch a few
+        // instructions after the load was issued -- a write-after-write hazard on a load in flight, the whole memory latency
+        // once per row (ncu: 22 % of all stall samples sat on that one MOV).
+        r.s0 = (sin && q_ok[0]) ? __ldg(srp + off + 3) : 0.0f;
+        r.s12 = (sin && q_ok[1]) ? __ldg(reinterpret_cast<const float2*>(srp + off + 4)) : make_float2(0.f, 0.f);
+        r.s3 = (sin && q_ok[1]) ? __ldg(srp + off + 6) : 0.0f;
     };
 
     float svw[CW_S][4];                                              // svw[x] = sr crop row h - x (columns j0 .. j0 + 3)
@@ -451,11 +463,11 @@ cpsnr_window_kernel(const float* __restrict__ sr, const float* __restrict__ hr, 
     for (int x = 0; x < CW_S; ++x)
 #pragma unroll
         for (int c = 0; c < 4; ++c) svw[x][c] = 0.0f;
-    CwRow nxt;
+    CwRowS nxt;
     load_row(i0, nxt);
     int since_flush = 0;
     for (int h = i0; h < h_end; ++h) {
-        const CwRow cur = nxt;
+        const CwRowS cur = nxt;
         load_row(h + 1, nxt);                                        // in flight while this row is being consumed
         float hw[12], mw[12];
 #pragma unroll
@@ -467,7 +479,7 @@ cpsnr_window_kernel(const float* __restrict__ sr, const float* __restrict__ hr, 
         for (int x = CW_S - 1; x > 0; --x)
 #pragma unroll
             for (int c = 0; c < 4; ++c) svw[x][c] = svw[x - 1][c];
-        svw[0][0] = cur.s[0].w, svw[0][1] = cur.s[1].x, svw[0][2] = cur.s[1].y, svw[0][3] = cur.s[1].z;   // crop column j0 + c = image column j0 + c + 3
+        svw[0][0] = cur.s0, svw[0][1] = cur.s12.x, svw[0][2] = cur.s12.y, svw[0][3] = cur.s3;   // crop column j0 + c = image column j0 + c + 3
         if (clip_sr) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) svw[0][c] = fminf(fmaxf(svw[0][c], 0.0f), 1.0f);
