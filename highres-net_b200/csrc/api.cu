@@ -1042,6 +1042,10 @@ int32_t hrn_scoring_debug_set(const char* knob, int32_t value) {
         hrn::g_lanczos_scalar = value != 0;
         return 0;
     }
+    if (knob != nullptr && strcmp(knob, "cpsnr_onepass") == 0) {
+        hrn::g_cpsnr_onepass = value != 0;
+        return 0;
+    }
     if (knob != nullptr && strcmp(knob, "cpsnr_chunk") == 0) {
         hrn::g_cpsnr_chunk = value;
         return 0;

@@ -189,7 +189,7 @@ bool lanczos7_tma_usable(const float* img, const float* out, int H, int W);
 int lanczos7_tma_launch(const float* img, const float* taps_dev, int planes, int c, int H, int W, int p, float* out, cudaStream_t s);
 int clear_loss_launch(const float* sr, const float* hr, const float* hm, int B, int H, int W, int metric, float* out,
                       cudaStream_t s);
-extern int g_cpsnr_generic, g_cpsnr_window_v1, g_cpsnr_chunk, g_lanczos_scalar;   // test knobs (hrn_scoring_debug_set)
+extern int g_cpsnr_generic, g_cpsnr_window_v1, g_cpsnr_chunk, g_cpsnr_onepass, g_lanczos_scalar;   // test knobs (hrn_scoring_debug_set)
 int shift_cpsnr_launch(const float* sr, const float* hr, const float* hm, int B, int H, int W, int border,
                        int clip_sr, float* best_db, int32_t* best_site, float* site_db, cudaStream_t s);
 

@@ -983,6 +983,393 @@ cpsnr_any_finalize_kernel(const double* __restrict__ partial, int sites, float* 
     }
 }
 
+// ------------------------------------------------------------------ 49-site search in ONE pass over the data (border_w = 3)
+// The two-pass kernels above read sr, hr and the map twice and spend 2 + 4 fp32 instructions per (site, pixel): pass 1 for the
+// bias b = sum(m d) / n, pass 2 for sum(((d - b) m)^2).  For a 0/1 map the second sum is sum(m d^2) - n b^2, so one pass that
+// accumulates n, sum(m d) and sum(m d^2) per site (4 instructions per (site, pixel)) gives the same number -- provided the
+// cancellation in the last step is harmless.  It is made harmless by CENTRING: every work item subtracts a constant c of its
+// own from d (the masked mean difference of its first row, i.e. a good guess of the bias), accumulates the centred sums in
+// fp32 over at most 16 rows and folds them into fp64; the finalize kernel un-centres every item's sums in fp64
+// (sum(m d) = S1 + c n, sum(m d^2) = S2 + 2 c S1 + c^2 n), where a cancellation of even 1e6 costs nothing.  What is left is the
+// fp32 rounding of the centred partial sums, ~1e-7 of sum(m (d - c)^2): sites where that is more than 16 x the cMSE (or whose
+// result is not a positive finite number: empty masks, NaN / inf pixels, exact matches) are flagged and recomputed by the
+// two-pass fallback kernel below with the reference's element arithmetic; imagesets whose map is not 0/1 are flagged whole.
+// Tile: one warp per block, 6 crop columns per lane (192 per block: 378 = 192 + 186, two blocks, 63 of 64 lanes busy); a
+// block walks work items (imageset, column block, row band) in a fixed round-robin, the grid is one resident wave.
+constexpr int OP_TC = 6, OP_COLS = 32 * OP_TC, OP_S = 7, OP_SITES = OP_S * OP_S, OP_FLUSH = 16;   // OP_TC: even
+constexpr int OP_WIN = OP_TC + OP_S - 1;         // 12 hr / map columns per lane and row, as six float2
+constexpr int OP_NQ = 3 * OP_SITES;              // per site: n, S1, S2
+constexpr int OP_STRIDE = OP_NQ + 2;             // doubles per work item: the sums, c, "map is not 0/1"
+constexpr float OP_TRUST = 16.0f;                // flag a site when sum(m (d - c)^2) > OP_TRUST * n * cMSE
+
+struct OpGeom {
+    int H, W, size, col_blocks, band_rows, bands, items, items_per_set;
+};
+struct OpRow {
+    float2 h[OP_WIN / 2], m[OP_WIN / 2];
+    float s0;                                    // sr crop columns j0 .. j0 + OP_TC - 1 are image columns j0 + 3 ..: float,
+    float2 smid[(OP_TC - 2) / 2];                // (OP_TC - 2) / 2 aligned float2,
+    float slast;                                 // float
+};
+
+// All terms of one hr row.  The seven shifted differences of one (sr row, column) pair are formed side by side -- seven FADD,
+// seven FMUL, seven FADD, seven FFMA -- so that no instruction waits for its predecessor: with two scratch registers (what the
+// compiler chose for the straightforward loop once the 98 accumulators had filled the register file) every instruction
+// waited out the 4-cycle latency of the one before it.  The sr window lives in shared memory for the same reason (42 registers).
+template <bool CPRED, bool XALL>
+__device__ __forceinline__ void op_terms(float (&s2)[OP_S][OP_S], float (&s1)[OP_S][OP_S], const float (&hw)[OP_WIN],
+                                         const float (&mw)[OP_WIN], const float (*svs)[OP_TC][32], int lane, int slot0,
+                                         int xlo, int xhi, int ncol) {
+    int slot = slot0;                          // slot of sr crop row h (x = 0); row h - x sits x slots back in the ring of 7
+#pragma unroll
+    for (int x = 0; x < OP_S; ++x) {
+        if (XALL || (x >= xlo && x <= xhi)) {  // warp-uniform: sr crop row h - x lies inside this band
+#pragma unroll
+            for (int c = 0; c < OP_TC; ++c) {
+                if (CPRED && c >= ncol) continue;
+                const float sv = svs[slot][c][lane];
+                float d[OP_S], md[OP_S];
+#pragma unroll
+                for (int y = 0; y < OP_S; ++y) d[y] = hw[c + y] - sv;            // (hr - sr) - centre          (Evaluator.py:35)
+#pragma unroll
+                for (int y = 0; y < OP_S; ++y) md[y] = d[y] * mw[c + y];        // exact for a 0/1 map
+#pragma unroll
+                for (int y = 0; y < OP_S; ++y) s1[x][y] += md[y];
+#pragma unroll
+                for (int y = 0; y < OP_S; ++y) s2[x][y] = fmaf(md[y], d[y], s2[x][y]);
+            }
+        }
+        slot = slot == 0 ? OP_S - 1 : slot - 1;
+    }
+}
+
+__global__ void __launch_bounds__(32, 7)
+cpsnr_onepass_kernel(const float* __restrict__ sr, const float* __restrict__ hr, const float* __restrict__ hm, OpGeom g,
+                     int clip_sr, double* __restrict__ partial) {
+    __shared__ float stage[OP_SITES][33];
+    __shared__ float edge_n[OP_SITES][32];       // n of the rows at the top / bottom of a band (not all 7 sr partners inside)
+    __shared__ float svs[OP_S][OP_TC][32];       // ring of the last seven sr crop rows (+ centre), [slot][column][lane]
+    __shared__ double tot[6][32];                // fp64 running sums: [quantity * 2 + k][lane] for site lane + 32 k
+    const int lane = threadIdx.x;
+    const size_t plane = static_cast<size_t>(g.H) * g.W;
+    const float2 zero2 = make_float2(0.f, 0.f);
+    for (int item = blockIdx.x; item < g.items; item += gridDim.x) {
+        const int set = item / g.items_per_set, rest = item % g.items_per_set;
+        const int cb = rest / g.bands, band = rest % g.bands;
+        const int j0 = cb * OP_COLS + lane * OP_TC;                  // first crop column of this lane
+        const int ncol = max(0, min(OP_TC, g.size - j0));
+        // a lane beyond the crop loads nothing: zeros for hr, sr and the map add nothing to any sum, so it can run the same
+        // straight-line code as the others (378 = 63 x 6: with six columns per lane no lane is ever partly filled at 384^2)
+        const bool active = ncol > 0;
+        const bool all_full = __all_sync(0xffffffffu, ncol == OP_TC || ncol == 0);
+        const float* srp = sr + set * plane + static_cast<size_t>(3) * g.W + j0;     // crop (i, j) = image (i + 3, j + 3)
+        const float* hrp = hr + set * plane + j0;
+        const float* hmp = hm + set * plane + j0;
+        const int i0 = band * g.band_rows, i1 = min(g.size, i0 + g.band_rows);
+        const int h_end = i1 + OP_S - 1;                             // hr rows [i0, h_end) meet sr crop rows [i0, i1)
+        bool q_ok[OP_WIN / 2];
+#pragma unroll
+        for (int q = 0; q < OP_WIN / 2; ++q) q_ok[q] = j0 + 2 * q + 2 <= g.W;
+
+        float s1[OP_S][OP_S], s2[OP_S][OP_S], n_all[OP_S];
+#pragma unroll
+        for (int x = 0; x < OP_S; ++x) {
+            n_all[x] = 0.0f;
+#pragma unroll
+            for (int y = 0; y < OP_S; ++y) {
+                s1[x][y] = 0.0f;
+                s2[x][y] = 0.0f;
+                edge_n[x * OP_S + y][lane] = 0.0f;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) tot[k][lane] = 0.0;
+        uint32_t not_binary = 0;
+
+        // fold the fp32 partial sums into fp64: quantity by quantity (n, S1, S2) through one 49 x 32 staging tile -- every lane
+        // writes its 49 values, then lanes 0 .. 48 (two rounds) each add up one site's 32 values in a fixed order
+        auto fold = [&](int which) {
+            __syncwarp();
+#pragma unroll 1
+            for (int k = 0; k < 2; ++k) {
+                const int site = lane + 32 * k;
+                if (site < OP_SITES) {
+                    double a = 0.0;
+#pragma unroll 8
+                    for (int l = 0; l < 32; ++l) a += static_cast<double>(stage[site][l]);
+                    tot[which * 2 + k][lane] += a;
+                }
+            }
+            __syncwarp();
+        };
+        auto flush = [&]() {
+#pragma unroll
+            for (int x = 0; x < OP_S; ++x)
+#pragma unroll
+                for (int y = 0; y < OP_S; ++y) {
+                    stage[x * OP_S + y][lane] = n_all[y] + edge_n[x * OP_S + y][lane];
+                    edge_n[x * OP_S + y][lane] = 0.0f;
+                }
+#pragma unroll
+            for (int y = 0; y < OP_S; ++y) n_all[y] = 0.0f;
+            fold(0);
+#pragma unroll
+            for (int x = 0; x < OP_S; ++x)
+#pragma unroll
+                for (int y = 0; y < OP_S; ++y) {
+                    stage[x * OP_S + y][lane] = s1[x][y];
+                    s1[x][y] = 0.0f;
+                }
+            fold(1);
+#pragma unroll
+            for (int x = 0; x < OP_S; ++x)
+#pragma unroll
+                for (int y = 0; y < OP_S; ++y) {
+                    stage[x * OP_S + y][lane] = s2[x][y];
+                    s2[x][y] = 0.0f;
+                }
+            fold(2);
+        };
+        auto load_row = [&](int h, OpRow& r) {
+            const size_t off = static_cast<size_t>(h) * g.W;
+            const bool in = active && h < h_end;
+#pragma unroll
+            for (int q = 0; q < OP_WIN / 2; ++q) {
+                r.h[q] = (in && q_ok[q]) ? __ldg(reinterpret_cast<const float2*>(hrp + off) + q) : zero2;
+                r.m[q] = (in && q_ok[q]) ? __ldg(reinterpret_cast<const float2*>(hmp + off) + q) : zero2;
+            }
+            const bool sin = active && h < i1;                       // sr crop row h exists in this band
+            // every loaded value is used: a dead lane of a wider load gets its register recycled while the load is in flight
+            // (see cpsnr_window_kernel)
+            r.s0 = (sin && q_ok[1]) ? __ldg(srp + off + 3) : 0.0f;
+#pragma unroll
+            for (int q = 0; q < (OP_TC - 2) / 2; ++q)
+                r.smid[q] = (sin && q_ok[q + 2]) ? __ldg(reinterpret_cast<const float2*>(srp + off + 4) + q) : zero2;
+            r.slast = (sin && q_ok[OP_TC / 2 + 1]) ? __ldg(srp + off + OP_TC + 2) : 0.0f;
+        };
+
+        float centre = 0.0f;
+        OpRow nxt;
+        load_row(i0, nxt);
+        int since_flush = 0, slot = 0;
+        for (int h = i0; h < h_end; ++h) {
+            const OpRow cur = nxt;
+            load_row(h + 1, nxt);                                    // in flight while this row is being consumed
+            float hw[OP_WIN], mw[OP_WIN];
+#pragma unroll
+            for (int q = 0; q < OP_WIN / 2; ++q) {
+                hw[2 * q] = cur.h[q].x, hw[2 * q + 1] = cur.h[q].y;
+                mw[2 * q] = cur.m[q].x, mw[2 * q + 1] = cur.m[q].y;
+            }
+#pragma unroll
+            for (int k = 0; k < OP_WIN; ++k) {                       // anything but +0.0f or 1.0f in the map?
+                const uint32_t bits = __float_as_uint(mw[k]);
+                not_binary |= min(bits, bits ^ 0x3f800000u);
+            }
+            float sv[OP_TC];
+            sv[0] = cur.s0;
+#pragma unroll
+            for (int q = 0; q < (OP_TC - 2) / 2; ++q) sv[1 + 2 * q] = cur.smid[q].x, sv[2 + 2 * q] = cur.smid[q].y;
+            sv[OP_TC - 1] = cur.slast;
+            if (clip_sr) {
+#pragma unroll
+                for (int c = 0; c < OP_TC; ++c) sv[c] = fminf(fmaxf(sv[c], 0.0f), 1.0f);
+            }
+            if (h == i0) {
+                // centring constant of this item: masked mean of hr - sr over its first row at shift (0, 3); any finite
+                // value is correct, a good one keeps the fp32 partial sums small
+                float num = 0.0f, den = 0.0f;
+#pragma unroll
+                for (int c = 0; c < OP_TC; ++c)
+                    if (c < ncol) {
+                        num = fmaf(mw[c + 3], hw[c + 3] - sv[c], num);
+                        den += mw[c + 3];
+                    }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    num += __shfl_xor_sync(0xffffffffu, num, o);
+                    den += __shfl_xor_sync(0xffffffffu, den, o);
+                }
+                const float c0 = num / den;
+                centre = (den > 0.0f && fabsf(c0) <= 4.0f) ? c0 : 0.0f;   // also false for NaN
+            }
+            slot = slot == OP_S - 1 ? 0 : slot + 1;                  // sr crop row h goes into the next slot of the ring
+#pragma unroll
+            for (int c = 0; c < OP_TC; ++c) svs[slot][c][lane] = sv[c] + centre;
+            // sr crop rows i = h - x that lie in this band: x in [xlo, xhi]
+            const int xlo = max(0, h - i1 + 1), xhi = min(OP_S - 1, h - i0);
+            if (all_full && xlo == 0 && xhi == OP_S - 1) {
+                // the hot path, straight-line code: every lane has all its columns (or none) and all seven sr partners of this
+                // hr row lie inside the band
+#pragma unroll
+                for (int y = 0; y < OP_S; ++y) {
+                    float r = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < OP_TC; ++c) r += mw[c + y];                               // n_clear (Evaluator.py:34)
+                    n_all[y] += r;
+                }
+                op_terms<false, true>(s2, s1, hw, mw, svs, lane, slot, 0, OP_S - 1, OP_TC);
+            } else {
+                float rs[OP_S];                                      // sum of the map over this lane's columns, per column shift
+#pragma unroll
+                for (int y = 0; y < OP_S; ++y) {
+                    float r = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < OP_TC; ++c) r += c < ncol ? mw[c + y] : 0.0f;
+                    rs[y] = r;
+                }
+                op_terms<true, false>(s2, s1, hw, mw, svs, lane, slot, xlo, xhi, ncol);
+                for (int x = xlo; x <= xhi; ++x)
+#pragma unroll
+                    for (int y = 0; y < OP_S; ++y) edge_n[x * OP_S + y][lane] += rs[y];
+            }
+            if (++since_flush == OP_FLUSH) {
+                flush();
+                since_flush = 0;
+            }
+        }
+        if (since_flush > 0) flush();
+        double* dst = partial + static_cast<size_t>(item) * OP_STRIDE;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int site = lane + 32 * k;
+            if (site < OP_SITES) {
+#pragma unroll
+                for (int which = 0; which < 3; ++which) dst[site * 3 + which] = tot[which * 2 + k][lane];
+            }
+        }
+        const bool any_bad = __any_sync(0xffffffffu, not_binary != 0);
+        if (lane == 0) {
+            dst[OP_NQ] = static_cast<double>(centre);
+            dst[OP_NQ + 1] = any_bad ? 1.0 : 0.0;
+        }
+        __syncwarp();
+    }
+}
+
+// One block per imageset, one thread per site: un-centre and add the items' sums in fp64, score, decide which sites the
+// fallback has to redo.
+__global__ void cpsnr_onepass_scores_kernel(const double* __restrict__ partial, OpGeom g, float* __restrict__ score,
+                                            uint8_t* __restrict__ redo) {
+    const int set = blockIdx.x, site = threadIdx.x;
+    if (site >= OP_SITES) return;
+    double n = 0.0, a = 0.0, q = 0.0, e = 0.0;
+    bool bad_map = false;
+    const double* src = partial + static_cast<size_t>(set) * g.items_per_set * OP_STRIDE;
+    for (int it = 0; it < g.items_per_set; ++it, src += OP_STRIDE) {
+        const double nk = src[site * 3], s1 = src[site * 3 + 1], s2 = src[site * 3 + 2], c = src[OP_NQ];
+        n += nk;
+        a += s1 + c * nk;
+        q += s2 + 2.0 * c * s1 + c * c * nk;
+        e += s2;
+        bad_map = bad_map || src[OP_NQ + 1] != 0.0;
+    }
+    const double b = a / n, cmse = q / n - b * b;
+    const bool trusted = !bad_map && cmse > 0.0 && cmse < 1e300 && e <= static_cast<double>(OP_TRUST) * n * cmse;   // false for NaN
+    score[set * OP_SITES + site] = static_cast<float>(-10.0 * log10(cmse));
+    redo[set * OP_SITES + site] = trusted ? 0 : 1;
+}
+
+// Fallback: one block per flagged (site, imageset), both passes of the reference inside the block with the reference's
+// element arithmetic (diff, diff * map, (diff - bias) * map, square in fp32; sums in fp64).  A warp takes every 32nd row and
+// has a whole row of loads in flight, so a flagged site costs tens of microseconds, not hundreds.
+constexpr int RD_THREADS = 1024;
+__global__ void __launch_bounds__(RD_THREADS)
+cpsnr_redo_kernel(const float* __restrict__ sr, const float* __restrict__ hr, const float* __restrict__ hm, int H, int W,
+                  int clip_sr, const uint8_t* __restrict__ redo, float* __restrict__ score) {
+    const int site = blockIdx.x, set = blockIdx.y;
+    if (!redo[set * OP_SITES + site]) return;
+    __shared__ double red[2][RD_THREADS / 32];
+    __shared__ float bias_s;
+    __shared__ double n_s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x = site / OP_S, y = site % OP_S, size = W - 6;
+    const size_t plane = static_cast<size_t>(H) * W;
+    const float* srp = sr + set * plane + static_cast<size_t>(3) * W + 3;
+    const float* hrp = hr + set * plane + static_cast<size_t>(x) * W + y;
+    const float* hmp = hm + set * plane + static_cast<size_t>(x) * W + y;
+    for (int pass = 1; pass <= 2; ++pass) {
+        const float b = pass == 2 ? bias_s : 0.0f;
+        double a0 = 0.0, a1 = 0.0;
+        for (int i = warp; i < size; i += RD_THREADS / 32) {
+            float p0 = 0.0f, p1 = 0.0f;
+#pragma unroll 12
+            for (int j = lane; j < size; j += 32) {
+                const size_t off = static_cast<size_t>(i) * W + j;
+                float sv = __ldg(srp + off);
+                if (clip_sr) sv = fminf(fmaxf(sv, 0.0f), 1.0f);
+                const float m = __ldg(hmp + off), d = __ldg(hrp + off) - sv;
+                if (pass == 1) {
+                    p0 += m;
+                    p1 += d * m;
+                } else {
+                    const float t = (d - b) * m;
+                    p0 += t * t;
+                }
+            }
+            a0 += static_cast<double>(p0);
+            a1 += static_cast<double>(p1);
+        }
+        a0 = warp_sum(a0);
+        a1 = warp_sum(a1);
+        if (lane == 0) {
+            red[0][warp] = a0;
+            red[1][warp] = a1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double r0 = 0.0, r1 = 0.0;
+            for (int w = 0; w < RD_THREADS / 32; ++w) {
+                r0 += red[0][w];
+                r1 += red[1][w];
+            }
+            if (pass == 1) {
+                n_s = r0;
+                bias_s = static_cast<float>(r1 / r0);                // 0/0 -> NaN like numpy
+            } else {
+                score[set * OP_SITES + site] = static_cast<float>(-10.0 * log10(r0 / n_s));   // cMSE = 0 -> +inf
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// np.max / np.argmax over the 49 scores of an imageset: NaN beats everything, the first NaN (else the first maximum) wins.
+__global__ void cpsnr_argmax_kernel(const float* __restrict__ score, float* __restrict__ best_db, int32_t* __restrict__ best_site,
+                                    float* __restrict__ site_db) {
+    const int set = blockIdx.x, site = threadIdx.x;
+    float v = site < OP_SITES ? score[set * OP_SITES + site] : -INFINITY;
+    int arg = site < OP_SITES ? site : 0x7fffffff;
+    if (site < OP_SITES && site_db != nullptr) site_db[set * OP_SITES + site] = v;
+    auto better = [](float av, int ai, float bv, int bi) {
+        const bool an = av != av, bn = bv != bv;
+        if (an || bn) return (an && bn) ? ai < bi : an;
+        if (av != bv) return av > bv;
+        return ai < bi;
+    };
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (better(ov, oi, v, arg)) {
+            v = ov;
+            arg = oi;
+        }
+    }
+    __shared__ float wv[2];
+    __shared__ int wi[2];
+    if ((threadIdx.x & 31) == 0) {
+        wv[threadIdx.x >> 5] = v;
+        wi[threadIdx.x >> 5] = arg;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const bool second = better(wv[1], wi[1], wv[0], wi[0]);
+        best_db[set] = second ? wv[1] : wv[0];
+        best_site[set] = second ? wi[1] : wi[0];
+    }
+}
+
 // ------------------------------------------------------------------ clear loss (train.py:66-87 without autograd)
 // metric 0: masked_MSE = mean over ALL pixels of (m*sr - m*hr)^2
 // metric 1: cMSE       = sum(m * (sr + b - hr)^2) / sum(m),  b = sum(m * (hr - sr)) / sum(m)   (weight m, not m^2)
@@ -1155,6 +1542,60 @@ int g_cpsnr_chunk = 0;         // imagesets per pass-1 / pass-2 round trip: 0 (d
 constexpr size_t CP_L2_BUDGET = 56ull << 20;   // chunk = -1: bytes of sr + hr + map per chunk that pass 2 should still find in L2
 constexpr int CW2_TARGET_WARPS = 148 * 14;
 
+int g_cpsnr_onepass = 1;       // 1 (default) = border_w = 3 on aligned rows takes the one-pass kernel; 0 = the two-pass window kernels
+
+// border_w = 3, rows 16-byte aligned: one pass over the data + scores + fallback for flagged sites + argmax.
+static int shift_cpsnr_onepass(const float* sr, const float* hr, const float* hm, int B, int H, int W, int clip_sr,
+                               float* best_db, int32_t* best_site, float* site_db, cudaStream_t s) {
+    int dev = 0, sm_count = 0, per_sm = 0;
+    HRN_CUDA_OK(cudaGetDevice(&dev));
+    HRN_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    HRN_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cpsnr_onepass_kernel, 32, 0));
+    const int resident = sm_count * (per_sm < 1 ? 1 : per_sm);
+    OpGeom g;
+    g.H = H;
+    g.W = W;
+    g.size = W - 6;
+    g.col_blocks = (g.size + OP_COLS - 1) / OP_COLS;
+    // Row bands: every block of the one resident wave walks items round-robin, so the cost is the number of rounds; pick the
+    // band count (bands of at least 24 rows, each pays 6 extra row loads) that wastes the least of the last round.
+    const long long columns = static_cast<long long>(B) * g.col_blocks;
+    const int max_bands = g.size / 24 < 1 ? 1 : g.size / 24;
+    int best_bands = 1;
+    double best_cost = 1e300;
+    for (int bands = 1; bands <= max_bands; ++bands) {
+        const int rows = (g.size + bands - 1) / bands;
+        const long long items = columns * ((g.size + rows - 1) / rows);
+        const long long rounds = (items + resident - 1) / resident;
+        const double cost = static_cast<double>(rounds) * (rows + 8);           // row iterations of the busiest block (+ fill / flush)
+        if (cost < best_cost * 0.995) {
+            best_cost = cost;
+            best_bands = bands;
+        }
+    }
+    g.band_rows = (g.size + best_bands - 1) / best_bands;
+    g.bands = (g.size + g.band_rows - 1) / g.band_rows;
+    g.items_per_set = g.col_blocks * g.bands;
+    const long long items = static_cast<long long>(B) * g.items_per_set;
+    g.items = static_cast<int>(items);
+    const size_t partial_bytes = static_cast<size_t>(items) * OP_STRIDE * sizeof(double);
+    const size_t score_bytes = static_cast<size_t>(B) * OP_SITES * sizeof(float);
+    uint8_t* ws = nullptr;
+    if (scratch_alloc(reinterpret_cast<void**>(&ws), partial_bytes + score_bytes + static_cast<size_t>(B) * OP_SITES, s)) return -1;
+    double* partial = reinterpret_cast<double*>(ws);
+    float* score = reinterpret_cast<float*>(ws + partial_bytes);
+    uint8_t* redo = ws + partial_bytes + score_bytes;
+    const int grid = items < resident ? static_cast<int>(items) : resident;
+    cpsnr_onepass_kernel<<<grid, 32, 0, s>>>(sr, hr, hm, g, clip_sr, partial);
+    cpsnr_onepass_scores_kernel<<<B, 64, 0, s>>>(partial, g, score, redo);
+    cpsnr_redo_kernel<<<dim3(OP_SITES, B), RD_THREADS, 0, s>>>(sr, hr, hm, H, W, clip_sr, redo, score);
+    cpsnr_argmax_kernel<<<B, 64, 0, s>>>(score, best_db, best_site, site_db);
+    note_launches(4);
+    HRN_CUDA_OK(cudaGetLastError());
+    HRN_CUDA_OK(cudaFreeAsync(ws, s));
+    return 0;
+}
+
 int shift_cpsnr_launch(const float* sr, const float* hr, const float* hm, int B, int H, int W, int border,
                        int clip_sr, float* best_db, int32_t* best_site, float* site_db, cudaStream_t s) {
     if (H != W) {
@@ -1202,6 +1643,8 @@ int shift_cpsnr_launch(const float* sr, const float* hr, const float* hm, int B,
         return 0;
     }
     g.vec_ok = (W % 4 == 0) && (((reinterpret_cast<uintptr_t>(sr) | reinterpret_cast<uintptr_t>(hr) | reinterpret_cast<uintptr_t>(hm)) & 15) == 0);
+    if (g.S == OP_S && g.vec_ok && g_cpsnr_generic == 0 && g_cpsnr_onepass != 0 && g_cpsnr_window_v1 < 0 && g_cpsnr_chunk == 0)
+        return shift_cpsnr_onepass(sr, hr, hm, B, H, W, clip_sr, best_db, best_site, site_db, s);
     // border_w = 3 on 16-byte aligned rows (every case the reference produces) takes the 49-site window kernel
     const bool window = g.S == CW_S && g.vec_ok && g_cpsnr_generic == 0;
     const int variant = g_cpsnr_window_v1 >= 0 ? g_cpsnr_window_v1 : (B <= 128 ? 2 : 1);

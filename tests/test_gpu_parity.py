@@ -794,7 +794,15 @@ def test_shift_cpsnr_window_kernel_vs_generic_and_oracle(hb, dev, b, s, kind):
         hm[2] = 0.0
         hm[2, s // 2, s // 2] = 1.0
     args = [torch.from_numpy(a).to(dev) for a in (sr, hr, hm)]
-    best_w, xy_w, tab_w = hb.shift_cPSNR_argmax(*args)
+    best_w, xy_w, tab_w = hb.shift_cPSNR_argmax(*args)                # default: the one-pass kernel (+ fallback for flagged sites)
+    hb.scoring_debug_set("cpsnr_onepass", 0)                         # the two-pass window kernels, variant by batch size
+    try:
+        best_t, xy_t, tab_t = hb.shift_cPSNR_argmax(*args)
+    finally:
+        hb.scoring_debug_set("cpsnr_onepass", 1)
+    assert torch.equal(xy_t, xy_w)
+    assert torch.equal(torch.isnan(tab_t), torch.isnan(tab_w)) and torch.equal(torch.isinf(tab_t), torch.isinf(tab_w))
+    assert np.abs(np.nan_to_num(tab_t.cpu().numpy() - tab_w.cpu().numpy(), nan=0.0, posinf=0.0, neginf=0.0)).max() <= CPSNR_KERNEL_GATE_DB
     hb.scoring_debug_set("cpsnr_generic", 1)
     try:
         best_g, xy_g, tab_g = hb.shift_cPSNR_argmax(*args)
@@ -836,6 +844,63 @@ def test_shift_cpsnr_window_kernel_vs_generic_and_oracle(hb, dev, b, s, kind):
     # run to run: fixed-order reductions -> bit-identical
     best_w2, xy_w2, tab_w2 = hb.shift_cPSNR_argmax(*args)
     assert np.array_equal(tab_w2.cpu().numpy(), tab_w, equal_nan=True) and torch.equal(xy_w2, xy_w)
+
+
+@pytest.mark.parametrize("kind", ["bias_dominates", "local_bias", "exact_match", "nan_pixel", "inf_pixel", "huge_values",
+                                  "masked_rows", "near_ties"])
+def test_shift_cpsnr_onepass_hazards(hb, dev, kind):
+    """The one-pass kernel computes sum(m d^2) - n b^2 from centred fp32 partial sums and hands the sites it does not
+    trust (and everything that is not a positive finite number) to a two-pass fallback.  Inputs built to break exactly
+    that: a brightness bias 3000 x the noise, a bias that changes across the image (each work item centres on its own
+    first row), exact matches (cMSE = 0 -> +inf), NaN / inf pixels, hr values far outside [0, 1], whole rows masked out
+    (a work item may see an empty first row) and 49 nearly identical scores.  Against the oracle and the two-pass path."""
+    rng = np.random.RandomState(len(kind) * 7 + 1)
+    b, s = 4, 200                                                    # two column blocks (194 crop columns), several row bands
+    sr = rng.rand(b, s, s).astype(np.float32)
+    hm = (rng.rand(b, s, s) > 0.15).astype(np.float32)
+    hr = np.roll(sr, (1, -2), (1, 2)).copy()
+    if kind == "bias_dominates":
+        hr = (hr + 0.3 + 1e-4 * rng.randn(b, s, s)).astype(np.float32)
+    elif kind == "local_bias":
+        ramp = np.linspace(-0.4, 0.4, s, dtype=np.float32)
+        hr = (hr + ramp[None, :, None] + 0.2 * ramp[None, None, :] + 1e-3 * rng.randn(b, s, s)).astype(np.float32)
+    elif kind == "exact_match":
+        hr = (hr + 0.125).astype(np.float32)                         # exact in fp32: d - b == 0 at the matching site
+    elif kind == "nan_pixel":
+        hr = (hr + 0.01 * rng.randn(b, s, s)).astype(np.float32)
+        hr[0, 50, 60] = np.nan                                       # (the reference asserts 0 <= sr <= 1, so only hr can carry one)
+        hr[1, 100:103, 100] = np.nan
+    elif kind == "inf_pixel":
+        hr = (hr + 0.01 * rng.randn(b, s, s)).astype(np.float32)
+        hr[0, 50, 60] = np.inf
+        hm[1] = 0.0                                                  # and an empty map: 0 / 0
+    elif kind == "huge_values":
+        hr = (hr * 3000.0 + 500.0 + 0.5 * rng.randn(b, s, s)).astype(np.float32)
+    elif kind == "masked_rows":
+        hr = (hr + 0.05 + 0.01 * rng.randn(b, s, s)).astype(np.float32)
+        hm[:, ::24] = 0.0
+        hm[:, 1::24] = 0.0
+        hm[2, :120] = 0.0
+    elif kind == "near_ties":
+        hr = rng.rand(b, s, s).astype(np.float32)                    # uncorrelated: all 49 scores within ~1e-2 dB
+    args = [torch.from_numpy(a).to(dev) for a in (sr, hr, hm)]
+    with np.errstate(all="ignore"):
+        ref_max, ref_arg, ref_sites = scoring_oracle.shift_cpsnr(sr, hr, hm)
+    ref_sites = ref_sites.T
+    best, xy, tab = hb.shift_cPSNR_argmax(*args)
+    hb.scoring_debug_set("cpsnr_onepass", 0)
+    try:
+        best2, xy2, tab2 = hb.shift_cPSNR_argmax(*args)
+    finally:
+        hb.scoring_debug_set("cpsnr_onepass", 1)
+    for t, a in ((tab, xy), (tab2, xy2)):
+        t = t.cpu().numpy()
+        assert np.array_equal(np.isnan(t), np.isnan(ref_sites))
+        assert np.array_equal(np.isposinf(t), np.isposinf(ref_sites))
+        fin = np.isfinite(ref_sites)
+        assert np.abs(t[fin] - ref_sites[fin]).max(initial=0.0) <= CPSNR_KERNEL_GATE_DB
+        assert np.array_equal((a[:, 0] * 7 + a[:, 1]).cpu().numpy(), ref_arg)
+    assert torch.equal(torch.isnan(best), torch.isnan(best2))
 
 
 def test_shift_cpsnr_rejects_bad_arguments(hb, dev):

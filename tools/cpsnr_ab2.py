@@ -1,5 +1,7 @@
-"""Same-box A/B of the shifted-cPSNR search: second-generation window kernel (scalar fp32, 49 sites per warp) against the
-third generation (x split over two warps, packed fp32x2), and the pass-1/pass-2 chunk size (L2 residency of pass 2).
+"""Same-box A/B of the shifted-cPSNR search: the one-pass kernel (default) against the two-pass window kernels -- second
+generation (scalar fp32, 49 sites per warp), third generation (x split over two warps, packed fp32x2 or scalar) -- and the
+pass-1/pass-2 chunk size (L2 residency of pass 2); on uncorrelated inputs and on inputs with an exact-match site per
+imageset (those sites go through the one-pass kernel's two-pass fallback).
     python tools/cpsnr_ab2.py"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -20,16 +22,25 @@ def timed(fn, n):
 for n in (512, 32):
     sr = torch.rand(n, 384, 384, device=dev); hr = torch.rand(n, 384, 384, device=dev); hm = (torch.rand(n, 384, 384, device=dev) > 0.1).float()
     ref = None
-    for v1 in (1, 0, 2, 1, 2):
-        for chunk in ((0, 64) if n == 512 else (0,)):
+    for v1 in (-1, 1, 0, 2, -1, 1, 2):
+        for chunk in ((0, 64) if n == 512 and v1 >= 0 else (0,)):
             hb.scoring_debug_set("cpsnr_window_v1", v1); hb.scoring_debug_set("cpsnr_chunk", chunk)
             best, xy, tab = hb.shift_cPSNR_argmax(sr, hr, hm)
             if ref is None: ref = (xy.clone(), tab.clone())
             ms = timed(lambda: hb.shift_cPSNR_argmax(sr, hr, hm), 20 if n == 512 else 100)
-            print(json.dumps({"n": n, "kernel": {1: "scalar, 49 sites per warp", 0: "split + packed fp32x2", 2: "split, scalar"}[v1], "chunk": chunk, "ms": round(ms, 4),
+            print(json.dumps({"n": n, "kernel": {-1: "one pass", 1: "scalar, 49 sites per warp", 0: "split + packed fp32x2", 2: "split, scalar"}[v1], "chunk": chunk, "ms": round(ms, 4),
                               "GBps_alg": round(n * 1769472 / ms / 1e6, 1), "argmax_same": bool(torch.equal(xy, ref[0])),
                               "max_db_diff": float((tab - ref[1]).abs().max())}), flush=True)
 hb.scoring_debug_set("cpsnr_window_v1", -1); hb.scoring_debug_set("cpsnr_chunk", 0)
+# every imageset has one site where hr == sr + const exactly (cMSE = 0): 1 of 49 sites per imageset takes the fallback
+for n in (512, 32):
+    sr = torch.rand(n, 384, 384, device=dev); hm = (torch.rand(n, 384, 384, device=dev) > 0.1).float()
+    hr = torch.roll(sr, (1, -2), (1, 2)) + 0.125
+    for onepass in (1, 0, 1, 0):
+        hb.scoring_debug_set("cpsnr_onepass", onepass)
+        ms = timed(lambda: hb.shift_cPSNR_argmax(sr, hr, hm), 20 if n == 512 else 100)
+        print(json.dumps({"n": n, "inputs": "exact match at one site", "kernel": "one pass + fallback" if onepass else "two pass", "ms": round(ms, 4)}), flush=True)
+hb.scoring_debug_set("cpsnr_onepass", 1)
 big = torch.rand(1, 512, 384, 384, device=dev); sh = torch.rand(512, 2, device=dev) * 2 - 1
 ms = timed(lambda: hb.lanczos_shift(big, sh, p=5), 100)
 print(json.dumps({"lanczos_512_ms": ms, "GBps": 512 * 1179648 / ms / 1e6}), flush=True)
