@@ -460,10 +460,10 @@ class Bench:
         gbps = n * CPSNR_BYTES / ms / 1e6
         out["cpsnr"] = {"GBps_algorithmic": gbps, "frac": gbps / hbm, "ms": ms, "imagesets": n,
                         "bytes_per_imageset": CPSNR_BYTES, "imagesets_per_s": n / ms * 1e3,
-                        "traffic": self._scoring_traffic("cpsnr_window_kernel", n),
-                        "note": "two passes (bias, centred squares) over 49 shifts, ~500 fp32 instructions per pixel: latency-bound "
-                                "on the fp32 pipe (ncu: issue slots 44-51 % active, DRAM 12-14 %), see DESIGN.md; frac is "
-                                "against the HBM copy peak as SURVEY 8d asks"}
+                        "traffic": self._scoring_traffic("cpsnr_onepass_kernel", n),
+                        "note": "one pass over sr, hr and the map: n, sum(m d), sum(m d^2) for 49 shifts from centred fp32 "
+                                "partial sums, 4 fp32 instructions per (shift, pixel) = ~200 per pixel: bound by fp32 issue, not "
+                                "by HBM (DESIGN.md); frac is against the HBM copy peak as SURVEY 8d asks"}
         del big, hrb, hmb, srb
         # C4: BASELINE.json configs[3] -- forward + lanczos_shift + clip + shift_cPSNR on 32 x 16-view imagesets per
         # GPU; at N > 1 the (cPSNR, x, y) rows of every rank are all-gathered every step and the SR images on the side stream

@@ -1045,8 +1045,9 @@ __device__ __forceinline__ void op_terms(float (&s2)[OP_S][OP_S], float (&s1)[OP
 
 __global__ void __launch_bounds__(32, 7)
 cpsnr_onepass_kernel(const float* __restrict__ sr, const float* __restrict__ hr, const float* __restrict__ hm, OpGeom g,
-                     int clip_sr, double* __restrict__ partial) {
+                     int clip_sr, double* __restrict__ partial, int* __restrict__ redo_list) {
     __shared__ float stage[OP_SITES][33];
+    if (blockIdx.x == 0 && threadIdx.x == 0) redo_list[0] = 0;       // number of flagged (site, imageset) pairs, filled in by the scores kernel
     __shared__ float edge_n[OP_SITES][32];       // n of the rows at the top / bottom of a band (not all 7 sr partners inside)
     __shared__ float svs[OP_S][OP_TC][32];       // ring of the last seven sr crop rows (+ centre), [slot][column][lane]
     __shared__ double tot[6][32];                // fp64 running sums: [quantity * 2 + k][lane] for site lane + 32 k
@@ -1215,10 +1216,13 @@ cpsnr_onepass_kernel(const float* __restrict__ sr, const float* __restrict__ hr,
                 for (int y = 0; y < OP_S; ++y) {
                     float r = 0.0f;
 #pragma unroll
-                    for (int c = 0; c < OP_TC; ++c) r += c < ncol ? mw[c + y] : 0.0f;
+                    for (int c = 0; c < OP_TC; ++c) r += (all_full || c < ncol) ? mw[c + y] : 0.0f;
                     rs[y] = r;
                 }
-                op_terms<true, false>(s2, s1, hw, mw, svs, lane, slot, xlo, xhi, ncol);
+                if (all_full)                                        // the rows at the top / bottom of a band
+                    op_terms<false, false>(s2, s1, hw, mw, svs, lane, slot, xlo, xhi, OP_TC);
+                else                                                 // a partly filled lane (crop widths that 6 does not divide)
+                    op_terms<true, false>(s2, s1, hw, mw, svs, lane, slot, xlo, xhi, ncol);
                 for (int x = xlo; x <= xhi; ++x)
 #pragma unroll
                     for (int y = 0; y < OP_S; ++y) edge_n[x * OP_S + y][lane] += rs[y];
@@ -1250,7 +1254,7 @@ cpsnr_onepass_kernel(const float* __restrict__ sr, const float* __restrict__ hr,
 // One block per imageset, one thread per site: un-centre and add the items' sums in fp64, score, decide which sites the
 // fallback has to redo.
 __global__ void cpsnr_onepass_scores_kernel(const double* __restrict__ partial, OpGeom g, float* __restrict__ score,
-                                            uint8_t* __restrict__ redo) {
+                                            uint8_t* __restrict__ redo, int* __restrict__ redo_list) {
     const int set = blockIdx.x, site = threadIdx.x;
     if (site >= OP_SITES) return;
     double n = 0.0, a = 0.0, q = 0.0, e = 0.0;
@@ -1268,77 +1272,99 @@ __global__ void cpsnr_onepass_scores_kernel(const double* __restrict__ partial, 
     const bool trusted = !bad_map && cmse > 0.0 && cmse < 1e300 && e <= static_cast<double>(OP_TRUST) * n * cmse;   // false for NaN
     score[set * OP_SITES + site] = static_cast<float>(-10.0 * log10(cmse));
     redo[set * OP_SITES + site] = trusted ? 0 : 1;
+    if (!trusted) redo_list[1 + atomicAdd(redo_list, 1)] = set * OP_SITES + site;   // [0] = count (zeroed by the one-pass kernel)
 }
 
-// Fallback: one block per flagged (site, imageset), both passes of the reference inside the block with the reference's
-// element arithmetic (diff, diff * map, (diff - bias) * map, square in fp32; sums in fp64).  A warp takes every 32nd row and
-// has a whole row of loads in flight, so a flagged site costs tens of microseconds, not hundreds.
-constexpr int RD_THREADS = 1024;
+// Fallback for flagged (site, imageset) pairs: the reference's two passes with the reference's element arithmetic (diff,
+// diff * map, (diff - bias) * map, square in fp32; sums in fp64).  RD_SLICES blocks share the rows of a pair, so 32 flagged
+// pairs already fill the GPU; pass 2 adds up the slices of pass 1 itself, the argmax kernel those of pass 2.  Blocks of
+// the flagged pairs come as a list (count first) written by the scores kernel: usually empty, two launches of a few microseconds.
+constexpr int RD_THREADS = 256, RD_SLICES = 16;
+template <int PASS>
 __global__ void __launch_bounds__(RD_THREADS)
 cpsnr_redo_kernel(const float* __restrict__ sr, const float* __restrict__ hr, const float* __restrict__ hm, int H, int W,
-                  int clip_sr, const uint8_t* __restrict__ redo, float* __restrict__ score) {
-    const int site = blockIdx.x, set = blockIdx.y;
-    if (!redo[set * OP_SITES + site]) return;
+                  int clip_sr, const int* __restrict__ redo_list, double* __restrict__ slices) {
     __shared__ double red[2][RD_THREADS / 32];
-    __shared__ float bias_s;
-    __shared__ double n_s;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int units = redo_list[0] * RD_SLICES;                      // usually 0: the whole grid leaves at once
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    const int pair = redo_list[1 + unit / RD_SLICES], slice = unit % RD_SLICES;
+    const int set = pair / OP_SITES, site = pair % OP_SITES;
     const int x = site / OP_S, y = site % OP_S, size = W - 6;
     const size_t plane = static_cast<size_t>(H) * W;
     const float* srp = sr + set * plane + static_cast<size_t>(3) * W + 3;
     const float* hrp = hr + set * plane + static_cast<size_t>(x) * W + y;
     const float* hmp = hm + set * plane + static_cast<size_t>(x) * W + y;
-    for (int pass = 1; pass <= 2; ++pass) {
-        const float b = pass == 2 ? bias_s : 0.0f;
-        double a0 = 0.0, a1 = 0.0;
-        for (int i = warp; i < size; i += RD_THREADS / 32) {
-            float p0 = 0.0f, p1 = 0.0f;
+    // slices[pair][slice] = {n, sum d m, sum t t}
+    float b = 0.0f;
+    if (PASS == 2) {
+        double n = 0.0, a = 0.0;
+        for (int k = 0; k < RD_SLICES; ++k) {
+            n += slices[(static_cast<size_t>(pair) * RD_SLICES + k) * 3];
+            a += slices[(static_cast<size_t>(pair) * RD_SLICES + k) * 3 + 1];
+        }
+        b = static_cast<float>(a / n);                               // 0/0 -> NaN like numpy
+    }
+    const int rows = (size + RD_SLICES - 1) / RD_SLICES, i0 = slice * rows, i1 = min(size, i0 + rows);
+    double a0 = 0.0, a1 = 0.0;
+    for (int i = i0 + warp; i < i1; i += RD_THREADS / 32) {
+        float p0 = 0.0f, p1 = 0.0f;
 #pragma unroll 12
-            for (int j = lane; j < size; j += 32) {
-                const size_t off = static_cast<size_t>(i) * W + j;
-                float sv = __ldg(srp + off);
-                if (clip_sr) sv = fminf(fmaxf(sv, 0.0f), 1.0f);
-                const float m = __ldg(hmp + off), d = __ldg(hrp + off) - sv;
-                if (pass == 1) {
-                    p0 += m;
-                    p1 += d * m;
-                } else {
-                    const float t = (d - b) * m;
-                    p0 += t * t;
-                }
-            }
-            a0 += static_cast<double>(p0);
-            a1 += static_cast<double>(p1);
-        }
-        a0 = warp_sum(a0);
-        a1 = warp_sum(a1);
-        if (lane == 0) {
-            red[0][warp] = a0;
-            red[1][warp] = a1;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double r0 = 0.0, r1 = 0.0;
-            for (int w = 0; w < RD_THREADS / 32; ++w) {
-                r0 += red[0][w];
-                r1 += red[1][w];
-            }
-            if (pass == 1) {
-                n_s = r0;
-                bias_s = static_cast<float>(r1 / r0);                // 0/0 -> NaN like numpy
+        for (int j = lane; j < size; j += 32) {
+            const size_t off = static_cast<size_t>(i) * W + j;
+            float sv = __ldg(srp + off);
+            if (clip_sr) sv = fminf(fmaxf(sv, 0.0f), 1.0f);
+            const float m = __ldg(hmp + off), d = __ldg(hrp + off) - sv;
+            if (PASS == 1) {
+                p0 += m;
+                p1 += d * m;
             } else {
-                score[set * OP_SITES + site] = static_cast<float>(-10.0 * log10(r0 / n_s));   // cMSE = 0 -> +inf
+                const float t = (d - b) * m;
+                p0 += t * t;
             }
         }
-        __syncthreads();
+        a0 += static_cast<double>(p0);
+        a1 += static_cast<double>(p1);
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    if (lane == 0) {
+        red[0][warp] = a0;
+        red[1][warp] = a1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r0 = 0.0, r1 = 0.0;
+        for (int w = 0; w < RD_THREADS / 32; ++w) {
+            r0 += red[0][w];
+            r1 += red[1][w];
+        }
+        double* dst = slices + (static_cast<size_t>(pair) * RD_SLICES + slice) * 3;
+        if (PASS == 1) {
+            dst[0] = r0;
+            dst[1] = r1;
+        } else {
+            dst[2] = r0;
+        }
+    }
+    __syncthreads();                                                 // red[] is reused by the next unit
     }
 }
 
 // np.max / np.argmax over the 49 scores of an imageset: NaN beats everything, the first NaN (else the first maximum) wins.
-__global__ void cpsnr_argmax_kernel(const float* __restrict__ score, float* __restrict__ best_db, int32_t* __restrict__ best_site,
-                                    float* __restrict__ site_db) {
+__global__ void cpsnr_argmax_kernel(const float* __restrict__ score, const uint8_t* __restrict__ redo,
+                                    const double* __restrict__ slices, float* __restrict__ best_db,
+                                    int32_t* __restrict__ best_site, float* __restrict__ site_db) {
     const int set = blockIdx.x, site = threadIdx.x;
     float v = site < OP_SITES ? score[set * OP_SITES + site] : -INFINITY;
+    if (site < OP_SITES && redo[set * OP_SITES + site]) {            // the fallback's answer replaces the one-pass score
+        double n = 0.0, q = 0.0;
+        for (int k = 0; k < RD_SLICES; ++k) {
+            n += slices[(static_cast<size_t>(set * OP_SITES + site) * RD_SLICES + k) * 3];
+            q += slices[(static_cast<size_t>(set * OP_SITES + site) * RD_SLICES + k) * 3 + 2];
+        }
+        v = static_cast<float>(-10.0 * log10(q / n));                // cMSE = 0 -> +inf
+    }
     int arg = site < OP_SITES ? site : 0x7fffffff;
     if (site < OP_SITES && site_db != nullptr) site_db[set * OP_SITES + site] = v;
     auto better = [](float av, int ai, float bv, int bi) {
@@ -1544,7 +1570,7 @@ constexpr int CW2_TARGET_WARPS = 148 * 14;
 
 int g_cpsnr_onepass = 1;       // 1 (default) = border_w = 3 on aligned rows takes the one-pass kernel; 0 = the two-pass window kernels
 
-// border_w = 3, rows 16-byte aligned: one pass over the data + scores + fallback for flagged sites + argmax.
+// border_w = 3, rows 16-byte aligned: one pass over the data, scores + flags, the two fallback passes for flagged sites, argmax.
 static int shift_cpsnr_onepass(const float* sr, const float* hr, const float* hm, int B, int H, int W, int clip_sr,
                                float* best_db, int32_t* best_site, float* site_db, cudaStream_t s) {
     int dev = 0, sm_count = 0, per_sm = 0;
@@ -1579,18 +1605,25 @@ static int shift_cpsnr_onepass(const float* sr, const float* hr, const float* hm
     const long long items = static_cast<long long>(B) * g.items_per_set;
     g.items = static_cast<int>(items);
     const size_t partial_bytes = static_cast<size_t>(items) * OP_STRIDE * sizeof(double);
+    const size_t slice_bytes = static_cast<size_t>(B) * OP_SITES * RD_SLICES * 3 * sizeof(double);
     const size_t score_bytes = static_cast<size_t>(B) * OP_SITES * sizeof(float);
+    const size_t list_bytes = (static_cast<size_t>(B) * OP_SITES + 1) * sizeof(int);
     uint8_t* ws = nullptr;
-    if (scratch_alloc(reinterpret_cast<void**>(&ws), partial_bytes + score_bytes + static_cast<size_t>(B) * OP_SITES, s)) return -1;
+    if (scratch_alloc(reinterpret_cast<void**>(&ws), partial_bytes + slice_bytes + score_bytes + list_bytes + static_cast<size_t>(B) * OP_SITES, s)) return -1;
     double* partial = reinterpret_cast<double*>(ws);
-    float* score = reinterpret_cast<float*>(ws + partial_bytes);
-    uint8_t* redo = ws + partial_bytes + score_bytes;
+    double* slices = reinterpret_cast<double*>(ws + partial_bytes);
+    float* score = reinterpret_cast<float*>(ws + partial_bytes + slice_bytes);
+    int* redo_list = reinterpret_cast<int*>(ws + partial_bytes + slice_bytes + score_bytes);
+    uint8_t* redo = ws + partial_bytes + slice_bytes + score_bytes + list_bytes;
     const int grid = items < resident ? static_cast<int>(items) : resident;
-    cpsnr_onepass_kernel<<<grid, 32, 0, s>>>(sr, hr, hm, g, clip_sr, partial);
-    cpsnr_onepass_scores_kernel<<<B, 64, 0, s>>>(partial, g, score, redo);
-    cpsnr_redo_kernel<<<dim3(OP_SITES, B), RD_THREADS, 0, s>>>(sr, hr, hm, H, W, clip_sr, redo, score);
-    cpsnr_argmax_kernel<<<B, 64, 0, s>>>(score, best_db, best_site, site_db);
-    note_launches(4);
+    cpsnr_onepass_kernel<<<grid, 32, 0, s>>>(sr, hr, hm, g, clip_sr, partial, redo_list);
+    cpsnr_onepass_scores_kernel<<<B, 64, 0, s>>>(partial, g, score, redo, redo_list);
+    const long long max_units = static_cast<long long>(B) * OP_SITES * RD_SLICES;
+    const int rgrid = static_cast<int>(max_units < 4LL * sm_count ? max_units : 4LL * sm_count);
+    cpsnr_redo_kernel<1><<<rgrid, RD_THREADS, 0, s>>>(sr, hr, hm, H, W, clip_sr, redo_list, slices);
+    cpsnr_redo_kernel<2><<<rgrid, RD_THREADS, 0, s>>>(sr, hr, hm, H, W, clip_sr, redo_list, slices);
+    cpsnr_argmax_kernel<<<B, 64, 0, s>>>(score, redo, slices, best_db, best_site, site_db);
+    note_launches(5);
     HRN_CUDA_OK(cudaGetLastError());
     HRN_CUDA_OK(cudaFreeAsync(ws, s));
     return 0;

@@ -174,11 +174,14 @@ int32_t hrn_forward_dump(hrn_handle* h, const float* lrs, const float* alphas, i
  * garbage): 1 no TMEM load, 2 no stores, 4 no TMA loads, 8 no residual loads, 32 no hand-over waits, 64 relaxed publication,
  * 128 relaxed polls + fence instead of acquire polls, 256 no proxy fence, 1024 every epilogue warp polls global memory. */
 int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value);
-/* Process-wide test knobs of the scoring entry points (they take no handle).  "cpsnr_generic" = 1 makes hrn_shift_cpsnr use
- * the general shift-window kernel also for border_w = 3 (default 0: the 49-site window kernel); "cpsnr_window_v1" picks the window
+/* Process-wide test knobs of the scoring entry points (they take no handle).  hrn_shift_cpsnr with border_w = 3 on 16-byte
+ * aligned rows runs the one-pass kernel (centred sums, per-site trust test, two-pass fallback for flagged sites);
+ * "cpsnr_onepass" = 0 selects the two-pass window kernels instead, and so does any explicit "cpsnr_window_v1" / "cpsnr_chunk".
+ * "cpsnr_generic" = 1 uses the general shift-window kernel also for border_w = 3; "cpsnr_window_v1" picks the two-pass window
  * kernel variant: 1 = scalar, all 49 sites per warp; 2 = the 7 row shifts split over two warps, scalar; 0 = split + packed
  * fp32x2 (measured slowest); default -1 = automatic (2 for batches up to 128 imagesets, 1 above); "cpsnr_chunk" = n > 0 runs
- * pass 1 -> bias -> pass 2 per chunk of n imagesets, -1 sizes the chunk by the L2 (default 0: the whole batch).  All agree. */
+ * pass 1 -> bias -> pass 2 per chunk of n imagesets, -1 sizes the chunk by the L2 (default 0: the whole batch).  All agree.
+ * "lanczos_scalar" = 1 makes hrn_lanczos_shift use the register-window kernel also for rows that TMA can address. */
 int32_t hrn_scoring_debug_set(const char* knob, int32_t value);
 
 /* Per-launch device timing of HRNet.forward, by kernel class, with CUDA events recorded on the stream the

@@ -13,7 +13,7 @@ timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/${tag}_pytest.log 2>&
 tail -8 gpurun_out/${tag}_pytest.log
 if [[ " $* " == *" cpsnr "* ]]; then
   timeout 300 python tools/cpsnr_ab2.py > gpurun_out/${tag}_cpsnr_ab.log 2>&1; echo "cpsnr_ab rc=$?"; cat gpurun_out/${tag}_cpsnr_ab.log
-  timeout 600 ncu --set full --clock-control none -k 'regex:lanczos7_tma|lanczos_shift7|cpsnr_window' -s 6 -c 3 -f -o gpurun_out/${tag}_scoring_full \
+  timeout 600 ncu --set full --clock-control none -k 'regex:lanczos7_tma|lanczos_shift7|cpsnr_onepass_kernel|cpsnr_window' -s 4 -c 2 -f -o gpurun_out/${tag}_scoring_full \
       python tools/scoring_ncu.py > gpurun_out/${tag}_ncu_scoring.log 2>&1; echo "ncu scoring rc=$?"
 fi
 if [[ " $* " == *" bench "* ]]; then

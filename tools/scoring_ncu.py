@@ -1,5 +1,5 @@
 """One call each of lanczos_shift and shift_cPSNR_argmax on 512 x 384^2 after a warm-up, for
-   ncu --set full --clock-control none -k regex:"lanczos_shift7|cpsnr_window" -s <warm-up launches> ..."""
+   ncu --set full --clock-control none -k regex:"lanczos7_tma|cpsnr_onepass_kernel" -s 4 -c 2 ..."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,7 +8,7 @@ dev = torch.device("cuda:0")
 n = 512
 sr = torch.rand(n, 384, 384, device=dev); hr = torch.rand(n, 384, 384, device=dev); hm = (torch.rand(n, 384, 384, device=dev) > 0.1).float()
 sh = torch.rand(n, 2, device=dev) * 2 - 1
-for _ in range(3):      # two warm-up rounds, the third is captured (ncu -s 6 -c 3: one Lanczos launch, cPSNR pass 1 and pass 2)
+for _ in range(3):      # two warm-up rounds, the third is captured (ncu -s 4 -c 2: the Lanczos kernel and the one-pass cPSNR kernel)
     hb.lanczos_shift(sr[None], sh, p=5)
     hb.shift_cPSNR_argmax(sr, hr, hm)
 torch.cuda.synchronize()
