@@ -474,7 +474,9 @@ class Bench:
         shift = (torch.rand(b, 2, generator=g) * 2 - 1).to(dev)
         hm = (torch.rand(b, 3 * s, 3 * s, generator=g) > 0.1).float().to(dev)
         sr0 = net(tl, ta)[:, 0]
-        hr = (torch.roll(hb.lanczos_shift(sr0[None], shift, p=5)[0].clamp(0, 1), (1, -2), (1, 2)) + 0.02).clamp(0, 1)
+        # hr = clip(roll(clip(sr)) + 0.02 + N(0, sigma^2)), sigma = 0.01 (about 40 dB at the known shift)
+        noise = (0.01 * torch.randn(b, 3 * s, 3 * s, generator=g)).to(dev)
+        hr = (torch.roll(hb.lanczos_shift(sr0[None], shift, p=5)[0].clamp(0, 1), (1, -2), (1, 2)) + 0.02 + noise).clamp(0, 1)
         gbuf = torch.empty((world * b, 1, 3 * s, 3 * s), dtype=torch.float32, device=dev) if world > 1 else None
         rows = torch.empty((world * b, 3), dtype=torch.float32, device=dev) if world > 1 else None
 
