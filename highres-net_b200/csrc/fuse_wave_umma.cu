@@ -263,6 +263,8 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
             uint32_t seen0 = 0, seen1 = 0;   // last values read from the producer's two "rows stored" counters
             const uint32_t* prod = flags + (conv == 1 ? F_PROD1 : F_PROD2);
             WAVE_STAT_BEGIN(t9);
+            const bool l2_hints = !(w.debug_flags & 2048);   // debug flag 2048 = no L2 eviction hints (A/B)
+            const uint64_t keep = ptx::l2_policy_evict_last();
             for (; have; have = walk.next(s)) {
                 int img[2] = {0, 0};
                 if (conv == 0) {
@@ -307,8 +309,12 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
                         ptx::mbar_wait(bar_empty + 8 * slot, ph ^ 1, 1);
                         WAVE_STAT_END(t1, 2);
                         ptx::mbar_expect_tx(bar_full + 8 * slot, CHUNK_TX);
-                        if (conv == 0)
+                        if (conv == 0 && l2_hints)      // view rows come back as the skip / alice rows of conv B and conv C: keep them in L2
+                            ptx::tma_load_4d_hint(ring_s + slot * CHUNK_BYTES, in_map, 0, -1, yc, img[c], bar_full + 8 * slot, keep);
+                        else if (conv == 0)
                             ptx::tma_load_4d(ring_s + slot * CHUNK_BYTES, in_map, 0, -1, yc, img[c], bar_full + 8 * slot);
+                        else if (l2_hints && !(w.debug_flags & 4096))   // ring rows: written and read in L2, overwritten 16 rows later
+                            ptx::tma_load_4d_hint(ring_s + slot * CHUNK_BYTES, in_map, 64 * c, -1, yc, stream, bar_full + 8 * slot, keep);
                         else
                             ptx::tma_load_4d(ring_s + slot * CHUNK_BYTES, in_map, 64 * c, -1, yc, stream, bar_full + 8 * slot);
                     }
@@ -597,17 +603,23 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
             // left, it arrives too late to help (4.55 vs 4.53 ms), and it needs fence.proxy.async.shared::cta before every
             // refill: the epilogue's ld.shared (generic proxy) and the TMA write (async proxy) of the same slot are NOT ordered
             // by the mbarrier hand-shake alone (without the fence one forward in ten came back with rows off by 1e-3).
+            // conv C's alice row and conv B's bob row are read for the last time here: first in line for eviction from L2
+            // (conv B's alice row comes back once more in conv C)
+            const bool last_use = !(w.debug_flags & 2048) && (conv == 2 || (conv == 1 && part == 1));
+            auto res_load = [&](const __nv_bfloat16* p, uint32_t (&r)[2][8]) {
+                if (last_use) {
+                    ptx::ldg_nc_v8_last_use(p, r[0]);
+                    ptx::ldg_nc_v8_last_use(p + 16, r[1]);
+                } else {
+                    ptx::ldg_nc_v8(p, r[0]);
+                    ptx::ldg_nc_v8(p + 16, r[1]);
+                }
+            };
             uint32_t rv_a[2][8], rv_b[2][8];
-            if (use_res) {
-                ptx::ldg_nc_v8(rp, rv_a[0]);
-                ptx::ldg_nc_v8(rp + 16, rv_a[1]);
-            }
+            if (use_res) res_load(rp, rv_a);
             auto do_row = [&](int i, uint32_t (&rv)[2][8], uint32_t (&rv_next)[2][8]) {
                 const uint32_t acc = tile % ACC_SLOTS, aph = (tile / ACC_SLOTS) & 1;
-                if (use_res && i + 1 < s.rows) {
-                    ptx::ldg_nc_v8(rp + r_step, rv_next[0]);
-                    ptx::ldg_nc_v8(rp + r_step + 16, rv_next[1]);
-                }
+                if (use_res && i + 1 < s.rows) res_load(rp + r_step, rv_next);
                 {
                     WAVE_STAT_BEGIN(t4);
                     ptx::mbar_wait(bar_tfull + 8 * acc, aph, 5);
@@ -663,13 +675,23 @@ fuse_wave_kernel(const __grid_constant__ CUtensorMap map_stack, const __grid_con
                     }
                     if (valid) {
                         __nv_bfloat16* dst = ring_out + ((static_cast<size_t>(stream) * R + tile % R) * w.W + x) * out_c + co0;
-                        ptx::stg_v8(dst, o[0]);
-                        ptx::stg_v8(dst + 16, o[1]);
+                        if (w.debug_flags & 2048) {
+                            ptx::stg_v8(dst, o[0]);
+                            ptx::stg_v8(dst + 16, o[1]);
+                        } else {                     // ring rows are consumed from L2 and overwritten 16 rows later: never worth a write-back
+                            ptx::stg_v8_keep(dst, o[0]);
+                            ptx::stg_v8_keep(dst + 16, o[1]);
+                        }
                     }
                 } else {
                     if (valid) {
-                        ptx::stg_v8(op, o[0]);
-                        ptx::stg_v8(op + 16, o[1]);
+                        if (w.debug_flags & 2048) {
+                            ptx::stg_v8(op, o[0]);
+                            ptx::stg_v8(op + 16, o[1]);
+                        } else {                     // the level's output: read by the next launch only
+                            ptx::stg_v8_stream(op, o[0]);
+                            ptx::stg_v8_stream(op + 16, o[1]);
+                        }
                     }
                     op += static_cast<size_t>(w.W) * 64;
                 }

@@ -52,7 +52,7 @@ struct ConvArgs {
     int cin, cout;            // cin in {64, 128}; cout in {64, 128}
     int max_ctas;             // 0 = one CTA per SM; tests shrink it to force odd strip boundaries
     int strip_split;          // 0/1 = one contiguous row range per CTA; k > 1 = k shorter ranges per CTA, dealt round-robin
-    int debug_flags;          // perf triage only: 1 = no TMEM load, 2 = no stores, 4 = no TMA loads, 8 = no residual loads
+    int debug_flags;          // perf triage only: 1 = no TMEM load, 2 = no stores, 4 = no TMA loads, 8 = no residual loads; 2048 = no L2 eviction hints
     // A operand gather.  pair_mode: output image m = (b, i) reads chunk 0 from view i and chunk 1 from
     // view top-1-i of the 64-channel view stack (HRNet.py:114-119); otherwise chunk c = channels [64c, 64c+64).
     // src_views is the STRIDE of the view stack in images per imageset (the original L at every level: the fusion

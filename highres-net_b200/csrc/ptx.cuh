@@ -208,6 +208,49 @@ __device__ __forceinline__ void stg_v8(void* p, const uint32_t (&r)[8]) {
                  : "memory");
 }
 
+// ---------------------------------------------------------------- L2 eviction priorities
+// A row that is read twice a few microseconds apart (conv operand by TMA, then skip connection by the epilogue) is loaded
+// with evict_last the first time and evict_first the second time, so that the second read finds it in L2 and then frees it.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_4d_hint(uint32_t dst, const void* map, int c0, int c1, int c2, int c3, uint32_t bar,
+                                                 uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%2, %3, %4, %5}], [%6], %7;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d_hint(const void* map, int c0, int c1, int c2, int c3, uint64_t policy) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile.L2::cache_hint [%0, {%1, %2, %3, %4}], %5;"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+                 : "memory");
+}
+// Last use of the data: no L1 allocation, first in line for eviction from L2 (LDG.E.NA.EFL2.256; no policy register).
+__device__ __forceinline__ void ldg_nc_v8_last_use(const void* p, uint32_t (&r)[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
+
+// Store to a buffer that lives in L2 and is overwritten again soon (hand-over rings): last in line for eviction (STG.E.ELL2.256).
+__device__ __forceinline__ void stg_v8_keep(void* p, const uint32_t (&r)[8]) {
+    asm volatile("st.global.L2::evict_last.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                 "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
+// Store of a tensor that is far larger than L2 and only read by the next kernel: first in line for eviction (STG.E.EFL2.256),
+// so that it does not push out rows that are read again soon.
+__device__ __forceinline__ void stg_v8_stream(void* p, const uint32_t (&r)[8]) {
+    asm volatile("st.global.L2::evict_first.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                 "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor, K-major, 128-byte swizzle (sm_100 format; built in umma_common.cuh):
 //   [0,14)  start address >> 4        [16,30) leading byte offset >> 4 (unused for SW128 K-major: 1)

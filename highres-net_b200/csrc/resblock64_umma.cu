@@ -261,13 +261,24 @@ resblock64_umma_kernel(const __grid_constant__ CUtensorMap in_map, const RbArgs 
                 // With two slots the ring cannot hide an HBM round trip, so rows are pulled into L2 X_AHEAD rows ahead
                 // of the load that brings them into shared memory.
                 constexpr int X_AHEAD = 6;
-                for (int q = 0; q < X_AHEAD && q < s.rows + 4; ++q) ptx::tma_prefetch_4d(&in_map, 0, -1, s.y0 - 2 + q, s.m);
+                // x rows are read again as the skip connection a few rows later: keep them in L2 until then (evict_last);
+                // debug flag 2048 = no eviction hints (A/B)
+                const bool hint = !(a.debug_flags & 2048);
+                const uint64_t keep = ptx::l2_policy_evict_last();
+                for (int q = 0; q < X_AHEAD && q < s.rows + 4; ++q) {
+                    if (hint) ptx::tma_prefetch_4d_hint(&in_map, 0, -1, s.y0 - 2 + q, s.m, keep);
+                    else ptx::tma_prefetch_4d(&in_map, 0, -1, s.y0 - 2 + q, s.m);
+                }
                 for (int q = 0; q < s.rows + 4; ++q, ++it) {
                     const uint32_t slot = it % RING, ph = (it / RING) & 1;
-                    if (q + X_AHEAD < s.rows + 4) ptx::tma_prefetch_4d(&in_map, 0, -1, s.y0 - 2 + q + X_AHEAD, s.m);
+                    if (q + X_AHEAD < s.rows + 4) {
+                        if (hint) ptx::tma_prefetch_4d_hint(&in_map, 0, -1, s.y0 - 2 + q + X_AHEAD, s.m, keep);
+                        else ptx::tma_prefetch_4d(&in_map, 0, -1, s.y0 - 2 + q + X_AHEAD, s.m);
+                    }
                     ptx::mbar_wait(p1.bar_empty + 8 * slot, ph ^ 1, 1);
                     ptx::mbar_expect_tx(p1.bar_full + 8 * slot, CHUNK_TX);
-                    ptx::tma_load_4d(p1.ring_s + slot * CHUNK_BYTES, &in_map, 0, -1, s.y0 - 2 + q, s.m, p1.bar_full + 8 * slot);
+                    if (hint) ptx::tma_load_4d_hint(p1.ring_s + slot * CHUNK_BYTES, &in_map, 0, -1, s.y0 - 2 + q, s.m, p1.bar_full + 8 * slot, keep);
+                    else ptx::tma_load_4d(p1.ring_s + slot * CHUNK_BYTES, &in_map, 0, -1, s.y0 - 2 + q, s.m, p1.bar_full + 8 * slot);
                 }
             }
         }
@@ -282,6 +293,7 @@ resblock64_umma_kernel(const __grid_constant__ CUtensorMap in_map, const RbArgs 
         const int co0 = hf * 32;
         const float slope_m1 = r.prelu2 - 1.0f;
         const float* bias = r.bias2 + hf * 32;
+        const bool skip_hint = !(a.debug_flags & 2048);
         StripWalker walk(geo, a, group);
         Strip s;
         bool have = walk.next(s);
@@ -299,8 +311,13 @@ resblock64_umma_kernel(const __grid_constant__ CUtensorMap in_map, const RbArgs 
                 const uint32_t acc = tile % ACCS, aph = (tile / ACCS) & 1;
                 uint32_t rv[2][8];
                 if (valid) {
-                    ptx::ldg_nc_v8(rp, rv[0]);
-                    ptx::ldg_nc_v8(rp + 16, rv[1]);
+                    if (skip_hint) {                                   // last use of this x row: free its L2 lines first
+                        ptx::ldg_nc_v8_last_use(rp, rv[0]);
+                        ptx::ldg_nc_v8_last_use(rp + 16, rv[1]);
+                    } else {
+                        ptx::ldg_nc_v8(rp, rv[0]);
+                        ptx::ldg_nc_v8(rp + 16, rv[1]);
+                    }
                 }
                 ptx::mbar_wait(p2.bar_tfull + 8 * acc, aph, 5);
                 ptx::tc_fence_after();
@@ -325,7 +342,10 @@ resblock64_umma_kernel(const __grid_constant__ CUtensorMap in_map, const RbArgs 
                         if (valid) y = __hfma2(one2, y, *reinterpret_cast<const __nv_bfloat162*>(&rv[g][e]));
                         o[e] = *reinterpret_cast<const uint32_t*>(&y);
                     }
-                    if (valid) ptx::stg_v8(op + 16 * g, o);
+                    if (valid) {
+                        if (skip_hint) ptx::stg_v8_stream(op + 16 * g, o);
+                        else ptx::stg_v8(op + 16 * g, o);
+                    }
                 }
             }
         }

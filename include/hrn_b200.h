@@ -172,7 +172,8 @@ int32_t hrn_forward_dump(hrn_handle* h, const float* lrs, const float* alphas, i
  * bit-identical.  "wave_stats" / "enc_stats" = 1 start per-CTA wait counters of the wavefront kernels, = 0 print their per-role
  * means to stderr.  "debug_flags" disables parts of the conv / wavefront kernels for performance triage (results are then
  * garbage): 1 no TMEM load, 2 no stores, 4 no TMA loads, 8 no residual loads, 32 no hand-over waits, 64 relaxed publication,
- * 128 relaxed polls + fence instead of acquire polls, 256 no proxy fence, 1024 every epilogue warp polls global memory. */
+ * 128 relaxed polls + fence instead of acquire polls, 256 no proxy fence, 1024 every epilogue warp polls global memory; and two
+ * that keep results intact: 2048 no L2 eviction hints in the ResidualBlock / wavefront kernels, 4096 none on the wavefront's ring reads. */
 int32_t hrn_debug_set(hrn_handle* h, const char* knob, int32_t value);
 /* Process-wide test knobs of the scoring entry points (they take no handle).  hrn_shift_cpsnr with border_w = 3 on 16-byte
  * aligned rows runs the one-pass kernel (centred sums, per-site trust test, two-pass fallback for flagged sites);
