@@ -366,10 +366,30 @@ __device__ __forceinline__ void cw_terms(float (&acc)[CW_S][CW_S], const float (
     }
 }
 
-template <int PASS>
+// Out of line on purpose: inlined, its fp64 temporaries pushed the row loop of the kernel below over its register budget.
+static __device__ __noinline__ void cw_fallback_bias(const double* __restrict__ pass1, int set, int blocks_per_set, float* bias_sh) {
+    for (int site = threadIdx.x; site < CW_SITES; site += 32) {
+        double a0 = 0.0, a1 = 0.0;
+        const double* src = pass1 + (static_cast<size_t>(set) * blocks_per_set * CW_SITES + site) * 2;
+        for (int blk = 0; blk < blocks_per_set; ++blk) {
+            a0 += src[static_cast<size_t>(blk) * CW_SITES * 2];
+            a1 += src[static_cast<size_t>(blk) * CW_SITES * 2 + 1];
+        }
+        bias_sh[site] = static_cast<float>(a1 / a0);                  // 0/0 -> NaN like numpy
+    }
+    __syncwarp();
+}
+
+template <int PASS, bool FALLBACK = false>       // FALLBACK: the whole-imageset fallback of the one-pass path (set_sel, pass1)
 __global__ void __launch_bounds__(32, 9)
 cpsnr_window_kernel(const float* __restrict__ sr, const float* __restrict__ hr, const float* __restrict__ hm, CpGeom g,
-                    int clip_sr, const float* __restrict__ bias, double* __restrict__ partial) {
+                    int clip_sr, const float* __restrict__ bias, double* __restrict__ partial,
+                    const uint8_t* __restrict__ set_sel = nullptr, const double* __restrict__ pass1 = nullptr) {
+    if (FALLBACK && !set_sel[blockIdx.y]) return;                // selected imagesets only
+    // PASS 2 of the fallback gets the pass-1 partial sums instead of a bias array and forms the bias itself, exactly like
+    // cpsnr_finalize_kernel<1> (same order of additions), which saves a launch that nearly always has nothing to do
+    __shared__ float bias_sh[PASS == 2 && FALLBACK ? CW_SITES : 1];
+    if (PASS == 2 && FALLBACK) cw_fallback_bias(pass1, blockIdx.y, g.blocks_per_set, bias_sh);
     constexpr int NQ = PASS == 1 ? 2 * CW_SITES : CW_SITES;      // quantities per block: [site][n, sum d*m] or [site]
     constexpr int NK = (NQ + 31) / 32;
     __shared__ float stage[NQ][33];
@@ -398,7 +418,7 @@ cpsnr_window_kernel(const float* __restrict__ sr, const float* __restrict__ hr, 
 #pragma unroll
         for (int y = 0; y < CW_S; ++y) {
             acc[x][y] = 0.0f;
-            aux[x][y] = PASS == 2 ? bias[(set * CW_S + x) * CW_S + y] : 0.0f;
+            aux[x][y] = PASS == 2 ? (FALLBACK ? bias_sh[x * CW_S + y] : bias[(set * CW_S + x) * CW_S + y]) : 0.0f;
             if (PASS == 1) edge_n[x * CW_S + y][lane] = 0.0f;
         }
     }
@@ -1001,6 +1021,7 @@ constexpr int OP_WIN = OP_TC + OP_S - 1;         // 12 hr / map columns per lane
 constexpr int OP_NQ = 3 * OP_SITES;              // per site: n, S1, S2
 constexpr int OP_STRIDE = OP_NQ + 2;             // doubles per work item: the sums, c, "map is not 0/1"
 constexpr float OP_TRUST = 16.0f;                // flag a site when sum(m (d - c)^2) > OP_TRUST * n * cMSE
+constexpr int OP_MAX_REDO = 6;                   // more flagged sites than this in one imageset: redo the whole imageset instead
 
 struct OpGeom {
     int H, W, size, col_blocks, band_rows, bands, items, items_per_set;
@@ -1254,25 +1275,35 @@ cpsnr_onepass_kernel(const float* __restrict__ sr, const float* __restrict__ hr,
 // One block per imageset, one thread per site: un-centre and add the items' sums in fp64, score, decide which sites the
 // fallback has to redo.
 __global__ void cpsnr_onepass_scores_kernel(const double* __restrict__ partial, OpGeom g, float* __restrict__ score,
-                                            uint8_t* __restrict__ redo, int* __restrict__ redo_list) {
+                                            uint8_t* __restrict__ redo, int* __restrict__ redo_list, uint8_t* __restrict__ set_sel) {
     const int set = blockIdx.x, site = threadIdx.x;
-    if (site >= OP_SITES) return;
-    double n = 0.0, a = 0.0, q = 0.0, e = 0.0;
-    bool bad_map = false;
-    const double* src = partial + static_cast<size_t>(set) * g.items_per_set * OP_STRIDE;
-    for (int it = 0; it < g.items_per_set; ++it, src += OP_STRIDE) {
-        const double nk = src[site * 3], s1 = src[site * 3 + 1], s2 = src[site * 3 + 2], c = src[OP_NQ];
-        n += nk;
-        a += s1 + c * nk;
-        q += s2 + 2.0 * c * s1 + c * c * nk;
-        e += s2;
-        bad_map = bad_map || src[OP_NQ + 1] != 0.0;
+    bool flagged = false, bad_map = false;
+    if (site < OP_SITES) {
+        double n = 0.0, a = 0.0, q = 0.0, e = 0.0;
+        const double* src = partial + static_cast<size_t>(set) * g.items_per_set * OP_STRIDE;
+        for (int it = 0; it < g.items_per_set; ++it, src += OP_STRIDE) {
+            const double nk = src[site * 3], s1 = src[site * 3 + 1], s2 = src[site * 3 + 2], c = src[OP_NQ];
+            n += nk;
+            a += s1 + c * nk;
+            q += s2 + 2.0 * c * s1 + c * c * nk;
+            e += s2;
+            bad_map = bad_map || src[OP_NQ + 1] != 0.0;
+        }
+        const double b = a / n, cmse = q / n - b * b;
+        const bool trusted = cmse > 0.0 && cmse < 1e300 && e <= static_cast<double>(OP_TRUST) * n * cmse;   // false for NaN
+        score[set * OP_SITES + site] = static_cast<float>(-10.0 * log10(cmse));
+        flagged = !trusted;
     }
-    const double b = a / n, cmse = q / n - b * b;
-    const bool trusted = !bad_map && cmse > 0.0 && cmse < 1e300 && e <= static_cast<double>(OP_TRUST) * n * cmse;   // false for NaN
-    score[set * OP_SITES + site] = static_cast<float>(-10.0 * log10(cmse));
-    redo[set * OP_SITES + site] = trusted ? 0 : 1;
-    if (!trusted) redo_list[1 + atomicAdd(redo_list, 1)] = set * OP_SITES + site;   // [0] = count (zeroed by the one-pass kernel)
+    // A few flagged sites are redone one by one (each re-reads the imageset twice); an imageset with many of them, or with a
+    // map that is not 0/1, goes through the two-pass window kernels as a whole instead (two more reads for all 49 sites).
+    const int count = __syncthreads_count(flagged);
+    const bool whole = __syncthreads_or(bad_map) || count > OP_MAX_REDO;
+    if (threadIdx.x == 0) set_sel[set] = whole ? 1 : 0;
+    if (site < OP_SITES) {
+        const bool single = flagged && !whole;
+        redo[set * OP_SITES + site] = single ? 1 : 0;
+        if (single) redo_list[1 + atomicAdd(redo_list, 1)] = set * OP_SITES + site;   // [0] = count (zeroed by the one-pass kernel)
+    }
 }
 
 // Fallback for flagged (site, imageset) pairs: the reference's two passes with the reference's element arithmetic (diff,
@@ -1353,10 +1384,20 @@ cpsnr_redo_kernel(const float* __restrict__ sr, const float* __restrict__ hr, co
 
 // np.max / np.argmax over the 49 scores of an imageset: NaN beats everything, the first NaN (else the first maximum) wins.
 __global__ void cpsnr_argmax_kernel(const float* __restrict__ score, const uint8_t* __restrict__ redo,
-                                    const double* __restrict__ slices, float* __restrict__ best_db,
-                                    int32_t* __restrict__ best_site, float* __restrict__ site_db) {
+                                    const double* __restrict__ slices, const uint8_t* __restrict__ set_sel,
+                                    const double* __restrict__ pass1, const double* __restrict__ pass2, int blocks_per_set,
+                                    float* __restrict__ best_db, int32_t* __restrict__ best_site, float* __restrict__ site_db) {
     const int set = blockIdx.x, site = threadIdx.x;
     float v = site < OP_SITES ? score[set * OP_SITES + site] : -INFINITY;
+    if (site < OP_SITES && set_sel[set]) {                           // imageset redone by the two-pass window kernels: cpsnr_finalize_kernel<2>
+        double n = 0.0, q = 0.0;
+        const size_t first = (static_cast<size_t>(set) * blocks_per_set * OP_SITES + site) * 2;
+        for (int blk = 0; blk < blocks_per_set; ++blk) {
+            n += pass1[first + static_cast<size_t>(blk) * OP_SITES * 2];
+            q += pass2[first + static_cast<size_t>(blk) * OP_SITES * 2];
+        }
+        v = static_cast<float>(-10.0 * log10(q / n));                // cMSE = 0 -> +inf
+    }
     if (site < OP_SITES && redo[set * OP_SITES + site]) {            // the fallback's answer replaces the one-pass score
         double n = 0.0, q = 0.0;
         for (int k = 0; k < RD_SLICES; ++k) {
@@ -1570,7 +1611,9 @@ constexpr int CW2_TARGET_WARPS = 148 * 14;
 
 int g_cpsnr_onepass = 1;       // 1 (default) = border_w = 3 on aligned rows takes the one-pass kernel; 0 = the two-pass window kernels
 
-// border_w = 3, rows 16-byte aligned: one pass over the data, scores + flags, the two fallback passes for flagged sites, argmax.
+// border_w = 3, rows 16-byte aligned: one pass over the data, scores + flags, the two fallback passes for single flagged sites, the
+// two-pass window kernels for imagesets flagged as a whole (pass 2 forms the bias, the argmax kernel the scores), argmax.  The
+// four fallback launches leave at once when nothing is flagged.
 static int shift_cpsnr_onepass(const float* sr, const float* hr, const float* hm, int B, int H, int W, int clip_sr,
                                float* best_db, int32_t* best_site, float* site_db, cudaStream_t s) {
     int dev = 0, sm_count = 0, per_sm = 0;
@@ -1608,22 +1651,50 @@ static int shift_cpsnr_onepass(const float* sr, const float* hr, const float* hm
     const size_t slice_bytes = static_cast<size_t>(B) * OP_SITES * RD_SLICES * 3 * sizeof(double);
     const size_t score_bytes = static_cast<size_t>(B) * OP_SITES * sizeof(float);
     const size_t list_bytes = (static_cast<size_t>(B) * OP_SITES + 1) * sizeof(int);
+    // whole-imageset fallback: the two-pass 49-sites-per-warp window kernels on the selected imagesets
+    CpGeom g2;
+    g2.H = H;
+    g2.W = W;
+    g2.border = 3;
+    g2.S = CW_S;
+    g2.size = g.size;
+    g2.vec_ok = 1;
+    g2.col_blocks = (g.size + CW_COLS - 1) / CW_COLS;
+    int want = CW_TARGET_WARPS / (B * g2.col_blocks);
+    want = want < 1 ? 1 : (want > (g.size + 7) / 8 ? (g.size + 7) / 8 : want);
+    g2.band_rows = (g.size + want - 1) / want;
+    g2.blocks_per_set = ((g.size + g2.band_rows - 1) / g2.band_rows) * g2.col_blocks;
+    const size_t partial2_bytes = static_cast<size_t>(B) * g2.blocks_per_set * OP_SITES * 2 * sizeof(double);
     uint8_t* ws = nullptr;
-    if (scratch_alloc(reinterpret_cast<void**>(&ws), partial_bytes + slice_bytes + score_bytes + list_bytes + static_cast<size_t>(B) * OP_SITES, s)) return -1;
-    double* partial = reinterpret_cast<double*>(ws);
-    double* slices = reinterpret_cast<double*>(ws + partial_bytes);
-    float* score = reinterpret_cast<float*>(ws + partial_bytes + slice_bytes);
-    int* redo_list = reinterpret_cast<int*>(ws + partial_bytes + slice_bytes + score_bytes);
-    uint8_t* redo = ws + partial_bytes + slice_bytes + score_bytes + list_bytes;
+    if (scratch_alloc(reinterpret_cast<void**>(&ws), partial_bytes + slice_bytes + 2 * partial2_bytes + score_bytes + list_bytes +
+                                                     static_cast<size_t>(B) * (OP_SITES + 1), s))
+        return -1;
+    uint8_t* at = ws;
+    auto take = [&](size_t bytes) {
+        uint8_t* p = at;
+        at += bytes;
+        return p;
+    };
+    double* partial = reinterpret_cast<double*>(take(partial_bytes));
+    double* slices = reinterpret_cast<double*>(take(slice_bytes));
+    double* partial2 = reinterpret_cast<double*>(take(partial2_bytes));      // pass 1 of the whole-imageset fallback: n, sum d m
+    double* partial3 = reinterpret_cast<double*>(take(partial2_bytes));      // pass 2: sum t t
+    float* score = reinterpret_cast<float*>(take(score_bytes));
+    int* redo_list = reinterpret_cast<int*>(take(list_bytes));
+    uint8_t* redo = take(static_cast<size_t>(B) * OP_SITES);
+    uint8_t* set_sel = take(B);
     const int grid = items < resident ? static_cast<int>(items) : resident;
     cpsnr_onepass_kernel<<<grid, 32, 0, s>>>(sr, hr, hm, g, clip_sr, partial, redo_list);
-    cpsnr_onepass_scores_kernel<<<B, 64, 0, s>>>(partial, g, score, redo, redo_list);
+    cpsnr_onepass_scores_kernel<<<B, 64, 0, s>>>(partial, g, score, redo, redo_list, set_sel);
     const long long max_units = static_cast<long long>(B) * OP_SITES * RD_SLICES;
     const int rgrid = static_cast<int>(max_units < 4LL * sm_count ? max_units : 4LL * sm_count);
     cpsnr_redo_kernel<1><<<rgrid, RD_THREADS, 0, s>>>(sr, hr, hm, H, W, clip_sr, redo_list, slices);
     cpsnr_redo_kernel<2><<<rgrid, RD_THREADS, 0, s>>>(sr, hr, hm, H, W, clip_sr, redo_list, slices);
-    cpsnr_argmax_kernel<<<B, 64, 0, s>>>(score, redo, slices, best_db, best_site, site_db);
-    note_launches(5);
+    const dim3 wgrid(g2.blocks_per_set, B);
+    cpsnr_window_kernel<1, true><<<wgrid, 32, 0, s>>>(sr, hr, hm, g2, clip_sr, nullptr, partial2, set_sel, nullptr);
+    cpsnr_window_kernel<2, true><<<wgrid, 32, 0, s>>>(sr, hr, hm, g2, clip_sr, nullptr, partial3, set_sel, partial2);
+    cpsnr_argmax_kernel<<<B, 64, 0, s>>>(score, redo, slices, set_sel, partial2, partial3, g2.blocks_per_set, best_db, best_site, site_db);
+    note_launches(7);
     HRN_CUDA_OK(cudaGetLastError());
     HRN_CUDA_OK(cudaFreeAsync(ws, s));
     return 0;

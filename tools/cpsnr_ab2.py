@@ -41,6 +41,14 @@ for n in (512, 32):
         ms = timed(lambda: hb.shift_cPSNR_argmax(sr, hr, hm), 20 if n == 512 else 100)
         print(json.dumps({"n": n, "inputs": "exact match at one site", "kernel": "one pass + fallback" if onepass else "two pass", "ms": round(ms, 4)}), flush=True)
 hb.scoring_debug_set("cpsnr_onepass", 1)
+# a map that is not 0/1: every imageset goes through the two-pass window kernels as a whole after the one-pass attempt
+for n in (512, 32):
+    sr = torch.rand(n, 384, 384, device=dev); hr = torch.rand(n, 384, 384, device=dev); hm = torch.rand(n, 384, 384, device=dev)
+    for onepass in (1, 0, 1, 0):
+        hb.scoring_debug_set("cpsnr_onepass", onepass)
+        ms = timed(lambda: hb.shift_cPSNR_argmax(sr, hr, hm), 20 if n == 512 else 100)
+        print(json.dumps({"n": n, "inputs": "soft map (not 0/1)", "kernel": "one pass + whole-imageset fallback" if onepass else "two pass", "ms": round(ms, 4)}), flush=True)
+hb.scoring_debug_set("cpsnr_onepass", 1)
 big = torch.rand(1, 512, 384, 384, device=dev); sh = torch.rand(512, 2, device=dev) * 2 - 1
 ms = timed(lambda: hb.lanczos_shift(big, sh, p=5), 100)
 print(json.dumps({"lanczos_512_ms": ms, "GBps": 512 * 1179648 / ms / 1e6}), flush=True)
