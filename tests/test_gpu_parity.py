@@ -903,6 +903,43 @@ def test_shift_cpsnr_onepass_hazards(hb, dev, kind):
     assert torch.equal(torch.isnan(best), torch.isnan(best2))
 
 
+def test_shift_cpsnr_onepass_differential(hb, dev):
+    """Random sizes (crop widths that 6 does and does not divide, one to four column blocks, one to many row bands), batch
+    sizes, maps (dense, sparse, striped, empty) and brightness offsets / noise levels over four decades: the one-pass search
+    against the two-pass window kernels -- tables within 1e-4 dB, same NaN / inf pattern, and the best shift may differ only
+    where the two-pass table itself has the two candidates within 2e-4 dB (tools/cpsnr_fuzz.py is the long version)."""
+    rng = np.random.RandomState(4321)
+    for case in range(36):
+        s = int(rng.choice([8, 12, 20, 36, 64, 100, 128, 132, 200, 260, 384, 388]))
+        b = int(rng.randint(1, 5)) if s > 200 else int(rng.randint(1, 24))
+        sr = rng.rand(b, s, s).astype(np.float32)
+        kind = int(rng.randint(0, 6))
+        hr = np.roll(sr, (int(rng.randint(-3, 4)), int(rng.randint(-3, 4))), (1, 2)).copy() if kind != 0 else rng.rand(b, s, s).astype(np.float32)
+        hr = hr + np.float32(rng.uniform(-0.3, 0.3)) + np.float32(10.0 ** rng.uniform(-5, -1)) * rng.randn(b, s, s).astype(np.float32)
+        if kind == 2:
+            hr = hr + np.linspace(-0.2, 0.2, s, dtype=np.float32)[None, :, None]
+        hm = (rng.rand(b, s, s) > rng.uniform(0.0, 0.9)).astype(np.float32)
+        if kind == 4:
+            hm[:, ::int(rng.randint(2, 9))] = 0.0
+        if kind == 5:
+            hm[rng.randint(0, b)] = 0.0
+        args = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev) for a in (sr, hr, hm)]
+        _, xy1, tab1 = hb.shift_cPSNR_argmax(*args)
+        hb.scoring_debug_set("cpsnr_onepass", 0)
+        try:
+            _, xy2, tab2 = hb.shift_cPSNR_argmax(*args)
+        finally:
+            hb.scoring_debug_set("cpsnr_onepass", 1)
+        t1, t2 = tab1.cpu().numpy(), tab2.cpu().numpy()
+        assert np.array_equal(np.isnan(t1), np.isnan(t2)) and np.array_equal(np.isinf(t1), np.isinf(t2)), (case, b, s, kind)
+        fin = np.isfinite(t2)
+        assert np.abs(t1[fin] - t2[fin]).max(initial=0.0) <= CPSNR_KERNEL_GATE_DB, (case, b, s, kind)
+        a1 = (xy1[:, 0] * 7 + xy1[:, 1]).cpu().numpy()
+        a2 = (xy2[:, 0] * 7 + xy2[:, 1]).cpu().numpy()
+        for i in range(b):
+            assert a1[i] == a2[i] or abs(t2[i, a1[i]] - t2[i, a2[i]]) <= 2e-4, (case, b, s, kind, i)
+
+
 def test_shift_cpsnr_rejects_bad_arguments(hb, dev):
     sr = torch.rand(1, 20, 24, device=dev)
     with pytest.raises(RuntimeError):
