@@ -468,8 +468,7 @@ cpsnr_window_kernel(const float* __restrict__ sr, const float* __restrict__ hr, 
             r.m[q] = (in && q_ok[q]) ? __ldg(reinterpret_cast<const float4*>(hmp + off) + q) : zero4;
         }
         const bool sin = h < i1;                                     // sr crop row h exists in this band
-#pragma unroll
-                // crop column j0 + c is image column j0 + c + 3: one float, one float2, one float.  Two aligned 128-bit loads would
+        // crop column j0 + c is image column j0 + c + 3: one float, one float2, one float.  Two aligned 128-bit loads would
         // be fewer instructions, but the unused fourth float of the second quad got its register reused as scratch a few
         // instructions after the load was issued -- a write-after-write hazard on a load in flight, the whole memory latency
         // once per row (ncu: 22 % of all stall samples sat on that one MOV).
